@@ -1,0 +1,502 @@
+// api.cu — the C-ABI (include/cafe_gpu.h) over the CUDA kernels of this directory.
+//
+// Host-side bookkeeping only: topology, key de-duplication (gather_keys/add_key,
+// cafe/cafe_tree.c:374-446), key scalars (libtree/birthdeath.c:246-262), buffer management.
+// All arithmetic on families happens in the kernels; there is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "common.cuh"
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+int cafe_gpu_abi_version(void) { return CAFE_GPU_ABI_VERSION; }
+
+int cafe_gpu_create(cafe_gpu_ctx** out, int device) {
+    if (!out) return CAFE_GPU_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                         " — this library has no CPU fallback";
+        cudaGetLastError();
+        return CAFE_GPU_ERR_NO_DEVICE;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (device >= n) { g_create_error = "device index out of range"; return CAFE_GPU_ERR_ARG; }
+    cafe_gpu_ctx* ctx = new cafe_gpu_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice/cudaStreamCreate failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return CAFE_GPU_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+    cudaMalloc(&ctx->d_score, 2 * sizeof(double));
+    cudaMallocHost(&ctx->h_score, 2 * sizeof(double));
+    *out = ctx;
+    return CAFE_GPU_OK;
+}
+
+static void free_err_models(cafe_gpu_ctx* ctx) {
+    for (auto& e : ctx->errs) { cudaFree(e.d_rowptr); cudaFree(e.d_col); cudaFree(e.d_val); }
+    ctx->errs.clear();
+}
+
+void cafe_gpu_destroy(cafe_gpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_lnc); cudaFree(ctx->d_lncT); cudaFree(ctx->d_counts); cudaFree(ctx->d_mult); cudaFree(ctx->d_first);
+    cudaFree(ctx->d_logprior); cudaFree(ctx->d_keyparams); cudaFree(ctx->d_M); cudaFree(ctx->d_MT); cudaFree(ctx->d_vec);
+    cudaFree(ctx->d_logpost); cudaFree(ctx->d_maxlik); cudaFree(ctx->d_argmax); cudaFree(ctx->d_score);
+    cudaFreeHost(ctx->h_score);
+    free_err_models(ctx);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* cafe_gpu_last_error(const cafe_gpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int cafe_gpu_set_stream(cafe_gpu_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_synchronize(cafe_gpu_ctx* ctx) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return CAFE_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- setup
+int cafe_gpu_set_tree(cafe_gpu_ctx* ctx, int n_nodes, const int32_t* left, const int32_t* right, const double* branchlength) {
+    if (!ctx || n_nodes < 3 || (n_nodes & 1) == 0 || !left || !right || !branchlength)
+        CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_tree: need an odd number (>=3) of nodes and non-null arrays");
+    ctx->n_nodes = n_nodes;
+    ctx->n_leaves = (n_nodes + 1) / 2;
+    ctx->left.assign(left, left + n_nodes);
+    ctx->right.assign(right, right + n_nodes);
+    ctx->branchlength.assign(branchlength, branchlength + n_nodes);
+    ctx->parent.assign(n_nodes, -1);
+    for (int i = 0; i < n_nodes; ++i) {
+        bool leaf = left[i] < 0;
+        if (leaf != (right[i] < 0)) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_tree: tree must be binary");
+        if (leaf != ((i & 1) == 0)) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_tree: nodes must be in nlist (infix) order: leaves even, internal odd");
+        if (!leaf) {
+            if (left[i] >= n_nodes || right[i] >= n_nodes || left[i] == right[i]) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_tree: bad child index");
+            ctx->parent[left[i]] = i;
+            ctx->parent[right[i]] = i;
+        }
+    }
+    ctx->root = -1;
+    for (int i = 0; i < n_nodes; ++i)
+        if (ctx->parent[i] < 0) {
+            if (ctx->root >= 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_tree: more than one root");
+            ctx->root = i;
+        }
+    ctx->t_int.resize(n_nodes);
+    for (int i = 0; i < n_nodes; ++i) {
+        if (i != ctx->root && !(branchlength[i] > 0))  // cafe_cmd_tree rejects these, cafe_commands.cpp:1113-1116
+            CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_tree: non-root branch length must be > 0");
+        ctx->t_int[i] = (int)branchlength[i];  // add_key, cafe_tree.c:376
+    }
+    // prefix order (node, head subtree, tail subtree) — libtree/tree.c:101-124
+    ctx->prefix_nonroot.clear();
+    std::vector<int> st{ctx->root};
+    while (!st.empty()) {
+        int v = st.back(); st.pop_back();
+        if (ctx->left[v] >= 0) { st.push_back(ctx->right[v]); st.push_back(ctx->left[v]); }
+        if (v != ctx->root) ctx->prefix_nonroot.push_back(v);
+    }
+    ctx->keys.clear(); ctx->node_key.clear(); ctx->ops.clear();
+    ctx->matrices_valid = false; ctx->results_valid = false;
+    ctx->leaf_err.assign(ctx->n_leaves, -1);
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_set_ranges(cafe_gpu_ctx* ctx, int range_min, int range_max, int root_min, int root_max) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    if (range_min != 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "set_ranges: range_min must be 0 (init_family_size, cafe_family.c:357-364)");
+    if (range_max < 1 || root_min < 0 || root_max < root_min) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_ranges: bad range");
+    ctx->rmin = range_min; ctx->rmax = range_max; ctx->root_min = root_min; ctx->root_max = root_max;
+    ctx->W = range_max - range_min + 1;
+    ctx->R = root_max - root_min + 1;
+    ctx->S = std::max(range_max, root_max) + 1;  // cafe_main.c:325, birthdeath.c:241
+    ctx->Sp = round_up(ctx->S, 16);
+    ctx->Vp = round_up(std::max(ctx->W, ctx->R), 16);
+    ctx->have_ranges = true;
+    ctx->matrices_valid = false; ctx->results_valid = false;
+    // geometry changed: drop size-dependent buffers
+    cudaFree(ctx->d_M); cudaFree(ctx->d_MT); ctx->d_M = ctx->d_MT = nullptr; ctx->mat_cap = 0;
+    cudaFree(ctx->d_vec); ctx->d_vec = nullptr; ctx->vec_cap = 0;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_set_lnc_table(cafe_gpu_ctx* ctx, const double* lnc, int rows, int cols) {
+    if (!ctx || !lnc || rows < 2 || cols < 2) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_lnc_table: bad arguments");
+    cudaFree(ctx->d_lnc); cudaFree(ctx->d_lncT); ctx->d_lnc = ctx->d_lncT = nullptr;
+    size_t bytes = (size_t)rows * cols * sizeof(double);
+    CAFE_CK(ctx, cudaMalloc(&ctx->d_lnc, bytes));
+    CAFE_CK(ctx, cudaMalloc(&ctx->d_lncT, bytes));
+    std::vector<double> T((size_t)rows * cols);
+    for (int n = 0; n < rows; ++n)
+        for (int x = 0; x < cols; ++x) T[(size_t)x * rows + n] = lnc[(size_t)n * cols + x];
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_lnc, lnc, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_lncT, T.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->lnc_rows = rows; ctx->lnc_cols = cols;
+    ctx->matrices_valid = false;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, const int32_t* counts,
+                          const int32_t* multiplicity, const int32_t* first_index) {
+    if (!ctx || n_families < 1 || !counts) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_families: bad arguments");
+    if (ctx->n_nodes == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "set_families: set_tree first");
+    if (n_leaves != ctx->n_leaves) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_families: n_leaves does not match the tree");
+    const int F = n_families, F_pad = round_up(F, 128);
+    std::vector<int> T((size_t)n_leaves * F_pad, 0), mult(F_pad, 0), first(F_pad, 0);
+    int mx = 0;
+    for (int f = 0; f < F; ++f) {
+        for (int k = 0; k < n_leaves; ++k) {
+            int c = counts[(size_t)f * n_leaves + k];
+            if (c < 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_families: negative count");
+            mx = std::max(mx, c);
+            T[(size_t)k * F_pad + f] = c;
+        }
+        mult[f] = multiplicity ? multiplicity[f] : 1;
+        first[f] = first_index ? first_index[f] : f;
+    }
+    if (F_pad != ctx->F_pad) {
+        cudaFree(ctx->d_counts); cudaFree(ctx->d_mult); cudaFree(ctx->d_first);
+        cudaFree(ctx->d_logpost); cudaFree(ctx->d_maxlik); cudaFree(ctx->d_argmax);
+        ctx->d_counts = ctx->d_mult = ctx->d_first = ctx->d_argmax = nullptr; ctx->d_logpost = ctx->d_maxlik = nullptr;
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_counts, T.size() * sizeof(int)));
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_mult, F_pad * sizeof(int)));
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_first, F_pad * sizeof(int)));
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_logpost, F_pad * sizeof(double)));
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_maxlik, F_pad * sizeof(double)));
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_argmax, F_pad * sizeof(int)));
+        cudaFree(ctx->d_vec); ctx->d_vec = nullptr; ctx->vec_cap = 0;
+    }
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_counts, T.data(), T.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_mult, mult.data(), F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_first, first.data(), F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->F = F; ctx->F_pad = F_pad; ctx->max_count = mx;
+    ctx->h_counts.assign(counts, counts + (size_t)F * n_leaves);
+    ctx->results_valid = false;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_set_prior(cafe_gpu_ctx* ctx, const double* prior, int len) {
+    if (!ctx || !prior) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_prior: bad arguments");
+    if (!ctx->have_ranges) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "set_prior: set_ranges first");
+    if (len < ctx->R) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_prior: need at least root_max-root_min+1 values");
+    ctx->h_prior.assign(prior, prior + ctx->R);
+    std::vector<double> lp(ctx->R);
+    for (int i = 0; i < ctx->R; ++i) lp[i] = std::log(prior[i]);  // lambda.cpp:682
+    cudaFree(ctx->d_logprior); ctx->d_logprior = nullptr;
+    CAFE_CK(ctx, cudaMalloc(&ctx->d_logprior, ctx->R * sizeof(double)));
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_logprior, lp.data(), ctx->R * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->results_valid = false;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_set_error_model(cafe_gpu_ctx* ctx, int leaf, const double* errormatrix, int dim) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    if (ctx->n_nodes == 0 || !ctx->have_ranges) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "set_error_model: set_tree and set_ranges first");
+    if (leaf >= ctx->n_leaves) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_error_model: leaf out of range");
+    ctx->results_valid = false;
+    if (!errormatrix) {
+        if (leaf < 0) ctx->leaf_err.assign(ctx->n_leaves, -1); else ctx->leaf_err[leaf] = -1;
+        return CAFE_GPU_OK;
+    }
+    if (dim < ctx->rmax + 1) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_error_model: dim must be >= range_max+1");
+    std::vector<int> rowptr(dim + 1, 0), col;
+    std::vector<double> val;
+    for (int o = 0; o < dim; ++o) {
+        for (int j = 0; j < dim; ++j) {
+            double e = errormatrix[(size_t)o * dim + j];
+            if (e != 0.0) { col.push_back(j); val.push_back(e); }
+        }
+        rowptr[o + 1] = (int)col.size();
+    }
+    ErrModelDev E;
+    E.dim = dim;
+    CAFE_CK(ctx, cudaMalloc(&E.d_rowptr, rowptr.size() * sizeof(int)));
+    CAFE_CK(ctx, cudaMalloc(&E.d_col, std::max<size_t>(1, col.size()) * sizeof(int)));
+    CAFE_CK(ctx, cudaMalloc(&E.d_val, std::max<size_t>(1, val.size()) * sizeof(double)));
+    CAFE_CK(ctx, cudaMemcpy(E.d_rowptr, rowptr.data(), rowptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!col.empty()) {
+        CAFE_CK(ctx, cudaMemcpy(E.d_col, col.data(), col.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CAFE_CK(ctx, cudaMemcpy(E.d_val, val.data(), val.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    ctx->errs.push_back(E);
+    int idx = (int)ctx->errs.size() - 1;
+    if (leaf < 0) ctx->leaf_err.assign(ctx->n_leaves, idx); else ctx->leaf_err[leaf] = idx;
+    return CAFE_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- rates / K1
+static BdKeyParams key_params(const BdKey& k) {
+    // libtree/birthdeath.c:246-262 — evaluated on the host with the same libm as the reference
+    BdKeyParams P{};
+    double alpha, beta, coeff;
+    const double t = (double)k.t;
+    if (k.mu < 0 || k.lambda == k.mu) {
+        alpha = k.lambda * t / (1 + k.lambda * t);
+        beta = alpha;
+        coeff = 1 - 2 * alpha;
+    } else {
+        double e_diff = std::exp((k.lambda - k.mu) * t);
+        double numerator = e_diff - 1;
+        double denominator = k.lambda * e_diff - k.mu;
+        alpha = (k.mu * numerator) / denominator;
+        beta = (k.lambda * numerator) / denominator;
+        coeff = 1 - alpha - beta;
+    }
+    P.coeff = coeff;
+    if (!(coeff > 0)) { P.mode = 0; return P; }      // init_zero_matrix (also catches NaN like the reference's else-branch would not fill)
+    if (coeff == 1) { P.mode = 1; return P; }
+    P.log_alpha = std::log(alpha);
+    P.log_beta = std::log(beta);
+    P.log_coeff = std::log(coeff);
+    P.mode = (k.mu < 0) ? 2 : 3;                     // birthdeath.c:272-275
+    return P;
+}
+
+int cafe_gpu_set_rates(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node) {
+    if (!ctx || !lambda_per_node || !mu_per_node) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_rates: bad arguments");
+    if (ctx->n_nodes == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "set_rates: set_tree first");
+    const int n = ctx->n_nodes;
+    ctx->lambda.assign(lambda_per_node, lambda_per_node + n);
+    ctx->mu.assign(mu_per_node, mu_per_node + n);
+    ctx->keys.clear();
+    ctx->node_key.assign(n, -1);
+    // gather_keys over the prefix traversal, add_key's linear exact-compare de-duplication
+    for (int v : ctx->prefix_nonroot) {
+        BdKey k{ctx->t_int[v], ctx->lambda[v], ctx->mu[v]};
+        int found = -1;
+        for (size_t i = 0; i < ctx->keys.size(); ++i)
+            if (ctx->keys[i].t == k.t && ctx->keys[i].lambda == k.lambda && ctx->keys[i].mu == k.mu) { found = (int)i; break; }
+        if (found < 0) { ctx->keys.push_back(k); found = (int)ctx->keys.size() - 1; }
+        ctx->node_key[v] = found;
+    }
+    ctx->matrices_valid = false; ctx->results_valid = false;
+    return build_schedule(ctx);
+}
+
+static int ensure_matrix_buffers(cafe_gpu_ctx* ctx) {
+    const size_t D = ctx->keys.size();
+    if (D > ctx->mat_cap) {
+        cudaFree(ctx->d_M); cudaFree(ctx->d_MT); ctx->d_M = ctx->d_MT = nullptr;
+        size_t cap = std::max<size_t>(D, (size_t)ctx->n_nodes - 1);  // never more keys than branches
+        size_t bytes = cap * ctx->Sp * ctx->Sp * sizeof(double);
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_M, bytes));
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_MT, bytes));
+        CAFE_CK(ctx, cudaMemsetAsync(ctx->d_M, 0, bytes, ctx->stream));   // padding stays zero forever
+        CAFE_CK(ctx, cudaMemsetAsync(ctx->d_MT, 0, bytes, ctx->stream));
+        ctx->mat_cap = cap;
+    }
+    if ((int)D > ctx->keys_cap) {
+        cudaFree(ctx->d_keyparams); ctx->d_keyparams = nullptr;
+        int cap = std::max<int>((int)D, ctx->n_nodes - 1);
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_keyparams, cap * sizeof(BdKeyParams)));
+        ctx->keys_cap = cap;
+    }
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_build_matrices(cafe_gpu_ctx* ctx) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    if (!ctx->have_ranges || ctx->keys.empty()) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "build_matrices: set_ranges and set_rates first");
+    if (!ctx->d_lnc) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "build_matrices: set_lnc_table first");
+    const int maxfs = ctx->S - 1;
+    if (ctx->lnc_rows < 2 * maxfs || ctx->lnc_cols < maxfs + 1)
+        CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "build_matrices: lnC table too small (need rows >= 2*(S-1), cols >= S)");
+    int rc = ensure_matrix_buffers(ctx);
+    if (rc) return rc;
+    std::vector<BdKeyParams> kp(ctx->keys.size());
+    for (size_t i = 0; i < kp.size(); ++i) kp[i] = key_params(ctx->keys[i]);
+    // small synchronous-semantics copy from pageable memory: staged by the runtime before return
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_keyparams, kp.data(), kp.size() * sizeof(BdKeyParams), cudaMemcpyHostToDevice, ctx->stream));
+    rc = launch_bd_matrices(ctx);
+    if (rc) return rc;
+    ctx->matrices_valid = true;
+    ctx->results_valid = false;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_num_keys(const cafe_gpu_ctx* ctx) { return ctx ? (int)ctx->keys.size() : 0; }
+
+int cafe_gpu_get_matrix(cafe_gpu_ctx* ctx, int node, double* out, int out_dim) {
+    if (!ctx || !out) return CAFE_GPU_ERR_ARG;
+    if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "get_matrix: build_matrices first");
+    if (node < 0 || node >= ctx->n_nodes || ctx->node_key[node] < 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "get_matrix: node has no branch");
+    if (out_dim != ctx->S) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "get_matrix: out_dim must equal S = max(range_max, root_max)+1");
+    const double* src = ctx->d_M + (size_t)ctx->node_key[node] * ctx->Sp * ctx->Sp;
+    CAFE_CK(ctx, cudaMemcpy2DAsync(out, (size_t)ctx->S * sizeof(double), src, (size_t)ctx->Sp * sizeof(double),
+                                   (size_t)ctx->S * sizeof(double), ctx->S, cudaMemcpyDeviceToHost, ctx->stream));
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return CAFE_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- K2 + K3
+static int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad) {
+    size_t need = (size_t)ctx->n_slots * F_pad * ctx->Vp;
+    if (need > ctx->vec_cap) {
+        cudaFree(ctx->d_vec); ctx->d_vec = nullptr;
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_vec, need * sizeof(double)));
+        CAFE_CK(ctx, cudaMemsetAsync(ctx->d_vec, 0, need * sizeof(double), ctx->stream));
+        ctx->vec_cap = need;
+    }
+    return CAFE_GPU_OK;
+}
+
+static int check_ready(cafe_gpu_ctx* ctx, const char* who) {
+    if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + ": build_matrices first");
+    if (ctx->F == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + ": set_families first");
+    if (!ctx->d_logprior) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + ": set_prior first");
+    if (ctx->leaf_err.empty() || std::all_of(ctx->leaf_err.begin(), ctx->leaf_err.end(), [](int e) { return e < 0; })) {
+        // one-hot leaves must fit the vector (initialize_leaf_likelihoods asserts, cafe_tree.c:207)
+        if (ctx->max_count >= std::max(ctx->W, ctx->R))
+            CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, std::string(who) + ": a family count exceeds the likelihood vector (size_of_factor)");
+    }
+    for (int e : ctx->leaf_err)
+        if (e >= 0 && ctx->max_count >= ctx->errs[e].dim) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, std::string(who) + ": a family count exceeds the error matrix");
+    return CAFE_GPU_OK;
+}
+
+static int score_device(cafe_gpu_ctx* ctx, double* d_out2) {
+    int rc = check_ready(ctx, "score");
+    if (rc) return rc;
+    rc = ensure_vec_buffers(ctx, ctx->F_pad);
+    if (rc) return rc;
+    rc = launch_prune(ctx, nullptr);
+    if (rc) return rc;
+    rc = launch_score_reduce(ctx, d_out2);
+    if (rc) return rc;
+    ctx->results_valid = true;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_score(cafe_gpu_ctx* ctx, double* score_out, int32_t* first_zero_family) {
+    if (!ctx || !score_out) return CAFE_GPU_ERR_ARG;
+    int rc = score_device(ctx, ctx->d_score);
+    if (rc) return rc;
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->h_score, ctx->d_score, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (std::isinf(ctx->h_score[1])) {
+        *score_out = ctx->h_score[0];
+        if (first_zero_family) *first_zero_family = -1;
+        return CAFE_GPU_OK;
+    }
+    *score_out = -std::numeric_limits<double>::infinity();  // log(0), lambda.cpp:753-760
+    if (first_zero_family) *first_zero_family = (int32_t)ctx->h_score[1];
+    return CAFE_GPU_ZERO_LIKELIHOOD;
+}
+
+int cafe_gpu_objective(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node,
+                       double* score_out, int32_t* first_zero_family) {
+    int rc = cafe_gpu_set_rates(ctx, lambda_per_node, mu_per_node);
+    if (rc) return rc;
+    rc = cafe_gpu_build_matrices(ctx);
+    if (rc) return rc;
+    return cafe_gpu_score(ctx, score_out, first_zero_family);
+}
+
+int cafe_gpu_objective_device(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node, double* out_device) {
+    if (!out_device) return CAFE_GPU_ERR_ARG;
+    int rc = cafe_gpu_set_rates(ctx, lambda_per_node, mu_per_node);
+    if (rc) return rc;
+    rc = cafe_gpu_build_matrices(ctx);
+    if (rc) return rc;
+    return score_device(ctx, out_device);
+}
+
+int cafe_gpu_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, double* max_likelihood, int32_t* argmax_likelihood) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    if (!ctx->results_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "family_results: score first");
+    if (log_max_posterior) CAFE_CK(ctx, cudaMemcpyAsync(log_max_posterior, ctx->d_logpost, ctx->F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (max_likelihood) CAFE_CK(ctx, cudaMemcpyAsync(max_likelihood, ctx->d_maxlik, ctx->F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (argmax_likelihood) CAFE_CK(ctx, cudaMemcpyAsync(argmax_likelihood, ctx->d_argmax, ctx->F * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {
+    if (!ctx || !L_out) return CAFE_GPU_ERR_ARG;
+    int rc = check_ready(ctx, "family_likelihoods");
+    if (rc) return rc;
+    rc = ensure_vec_buffers(ctx, ctx->F_pad);
+    if (rc) return rc;
+    double* d_L = nullptr;
+    size_t bytes = (size_t)ctx->F * ctx->R * sizeof(double);
+    CAFE_CK(ctx, cudaMalloc(&d_L, bytes));
+    rc = launch_prune(ctx, d_L);
+    if (rc) { cudaFree(d_L); return rc; }
+    cudaError_t e = cudaMemcpyAsync(L_out, d_L, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_L);
+    CAFE_CK(ctx, e);
+    return CAFE_GPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- K4 / K5
+int cafe_gpu_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, double* cd_out) {
+    if (!ctx || !cd_out || n_samples < 1) return CAFE_GPU_ERR_ARG;
+    if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "conditional_distribution: build_matrices first");
+    return run_conditional_distribution(ctx, n_samples, uniforms, seed, cd_out);
+}
+
+int cafe_gpu_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* max_pvalue_out) {
+    if (!ctx || !cd || !max_pvalue_out || cd_rows < 1 || n_samples < 1) return CAFE_GPU_ERR_ARG;
+    if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "pvalues: build_matrices first");
+    if (ctx->F == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "pvalues: set_families first");
+    return run_pvalues(ctx, cd, cd_rows, n_samples, max_pvalue_out);
+}
+
+// ------------------------------------------------------------------------------------------- bookkeeping
+int64_t cafe_gpu_launch_count(const cafe_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void cafe_gpu_reset_launch_count(cafe_gpu_ctx* ctx) { if (ctx) ctx->launches = 0; }
+int cafe_gpu_enable_timing(cafe_gpu_ctx* ctx, int on) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    ctx->timing = on != 0; ctx->ev_k1 = ctx->ev_k2 = false;
+    return CAFE_GPU_OK;
+}
+int cafe_gpu_last_kernel_ms(cafe_gpu_ctx* ctx, float* k1_ms, float* k2_ms) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (k1_ms) { *k1_ms = -1.f; if (ctx->ev_k1) CAFE_CK(ctx, cudaEventElapsedTime(k1_ms, ctx->ev[0], ctx->ev[1])); }
+    if (k2_ms) { *k2_ms = -1.f; if (ctx->ev_k2) CAFE_CK(ctx, cudaEventElapsedTime(k2_ms, ctx->ev[2], ctx->ev[3])); }
+    return CAFE_GPU_OK;
+}
+
+double cafe_gpu_score_flops(const cafe_gpu_ctx* ctx) {
+    if (!ctx || ctx->n_nodes == 0 || !ctx->have_ranges) return 0.0;
+    // internal edges only; 2*W*W per non-root parent, 2*R*W under the root
+    double per_family = 0.0;
+    for (int v = 0; v < ctx->n_nodes; ++v) {
+        if (v == ctx->root || ctx->left[v] < 0) continue;  // v is an internal child => its edge is a real matvec
+        per_family += (ctx->parent[v] == ctx->root) ? 2.0 * ctx->R * ctx->W : 2.0 * ctx->W * ctx->W;
+    }
+    return per_family * ctx->F;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+// common.cuh — shared declarations of the sm_100a likelihood path (context, launch helpers, PTX wrappers).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cafe_gpu.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: every CUDA call goes through CK(); failures are recorded in ctx->err and surface
+// as CAFE_GPU_ERR_CUDA at the C-ABI.  There is no CPU fallback anywhere in this library.
+// ---------------------------------------------------------------------------------------------
+#define CAFE_CK(ctx, expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ +   \
+                         ":" + std::to_string(__LINE__) + ")";                                     \
+            return CAFE_GPU_ERR_CUDA;                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define CAFE_FAIL(ctx, code, msg)                                                                  \
+    do {                                                                                           \
+        (ctx)->err = (msg);                                                                        \
+        return (code);                                                                             \
+    } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// One distinct transition-matrix key, cafe/cafe_tree.c:374-391 (int branch length!).
+struct BdKey {
+    int t;
+    double lambda, mu;
+};
+
+// Host-computed scalars of one key (libtree/birthdeath.c:246-262), uploaded for K1.
+struct BdKeyParams {
+    double log_alpha, log_beta, log_coeff, coeff;
+    int mode;  // 0: rows>=1 zero (coeff<=0); 1: identity (coeff==1); 2: mu<0 sum; 3: mu>=0 sum
+    int pad;
+};
+
+// Sparse rows of an error matrix: for observed count `o`, the non-zero (true size j, value) pairs in
+// ascending j — the dense sum of cafe/cafe_tree.c:196-203 + libtree/birthdeath.c:172-180 adds exact
+// zeros for every other j, so the result is identical.
+struct ErrModelDev {
+    int dim = 0;
+    int* d_rowptr = nullptr;  // [dim+1]
+    int* d_col = nullptr;
+    double* d_val = nullptr;
+};
+
+// One step of the pruning schedule: a node of the tree in post-order.
+struct PruneOp {
+    int node;        // parent node v
+    int is_root;
+    int gemm_child;  // internal child whose vector is multiplied by its matrix (-1: none, leaf pair)
+    int gemm_key;    // key index of gemm_child's branch
+    int in_slot;     // slot of gemm_child's vector
+    int out_slot;    // slot of v's vector
+    int other_kind;  // 0: none (first of two internal children), 1: leaf sibling, 2: multiply into out_slot (second internal child)
+    int leaf_a, leaf_a_key;  // leaf ordinal (leaf order) / key for leaf factors; leaf_a used by other_kind==1 and leaf pairs
+    int leaf_b, leaf_b_key;  // second leaf of a leaf pair
+};
+
+struct cafe_gpu_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    int sm_count = 148;
+
+    // tree (nlist order)
+    int n_nodes = 0, n_leaves = 0, root = -1;
+    std::vector<int> left, right, parent, t_int;
+    std::vector<double> branchlength;
+    std::vector<int> prefix_nonroot;  // non-root nodes in prefix order (RNG consumption order of K4)
+
+    // ranges
+    bool have_ranges = false;
+    int rmin = 0, rmax = 0, root_min = 0, root_max = 0;
+    int W = 0, R = 0, S = 0;  // vector length, root rows, matrix dimension
+    int Sp = 0;               // padded matrix leading dimension
+    int Vp = 0;               // padded vector leading dimension (>= max(W,R))
+
+    // lnC
+    double* d_lnc = nullptr;   // [lnc_rows][lnc_cols]   lnC(n,x)
+    double* d_lncT = nullptr;  // [lnc_cols][lnc_rows]   transposed copy
+    int lnc_rows = 0, lnc_cols = 0;
+
+    // families
+    int F = 0, F_pad = 0;
+    int* d_counts = nullptr;  // [n_leaves][F_pad]  (leaf-major: coalesced over families)
+    int* d_mult = nullptr;    // [F_pad]
+    int* d_first = nullptr;   // [F_pad]
+    std::vector<int> h_counts;  // [F][n_leaves] as given
+    int max_count = 0;
+
+    // prior
+    double* d_logprior = nullptr;  // [R] log(prior[i])
+    std::vector<double> h_prior;
+
+    // error models, per leaf (leaf order)
+    std::vector<ErrModelDev> errs;        // owned models
+    std::vector<int> leaf_err;            // per leaf: index into errs or -1
+    int* d_leaf_err_rowptr_base = nullptr;
+
+    // rates / keys
+    std::vector<double> lambda, mu;  // per node
+    std::vector<BdKey> keys;
+    std::vector<int> node_key;  // per node: key index (-1 root)
+    BdKeyParams* d_keyparams = nullptr;
+    int keys_cap = 0;
+    bool matrices_valid = false;
+    double* d_M = nullptr;   // [D][Sp][Sp]  M[s][c]
+    double* d_MT = nullptr;  // [D][Sp][Sp]  MT[c][s]
+    size_t mat_cap = 0;      // allocated matrices
+
+    // pruning schedule + vector slots
+    std::vector<PruneOp> ops;
+    int n_slots = 0;
+    double* d_vec = nullptr;  // [n_slots][F_pad][Vp]
+    size_t vec_cap = 0;
+
+    // per-family outputs
+    double* d_logpost = nullptr;  // [F_pad]
+    double* d_maxlik = nullptr;   // [F_pad]
+    int* d_argmax = nullptr;      // [F_pad]
+    double* d_score = nullptr;    // [2] partial score, min first index of a zero family (as double)
+    double* h_score = nullptr;    // pinned [2]
+    bool results_valid = false;
+
+    // bookkeeping
+    int64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_k1 = false, ev_k2 = false;
+};
+
+// kernels (defined in the .cu files of this directory); all launch on ctx->stream
+int launch_bd_matrices(cafe_gpu_ctx* ctx);                              // bd_matrix.cu   (K1)
+int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out /*nullable*/);  // prune.cu       (K2)
+int launch_score_reduce(cafe_gpu_ctx* ctx, double* d_out2);             // reduce.cu      (K3)
+int build_schedule(cafe_gpu_ctx* ctx);                                  // prune.cu (host)
+int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed,
+                                 double* cd_out);                       // conddist.cu    (K4)
+int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out);  // pvalue.cu (K5)
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// fp64 tensor-core MMA: D(8x8) += A(8x4,row) * B(4x8,col).  SASS: DMMA.8x8x4 (the only fp64 MMA shape
+// sm_100a has; tcgen05.mma has no .kind::f64 — SURVEY.md §7).
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Row permutation inside an 8-row MMA block.  With 128-byte rows and the 128B swizzle (16-byte chunk
+// index ^= row & 7) the natural rows 0..3 of a half-warp collide pairwise; mapping MMA row g to
+// tile row pi(g) = 2*(g&3) + (g>>2) makes every fragment load conflict-free.
+__device__ __forceinline__ int mma_row_perm(int g) { return 2 * (g & 3) + (g >> 2); }
+
+#endif  // __CUDACC__

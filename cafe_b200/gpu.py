@@ -1,0 +1,241 @@
+"""ctypes binding of the C-ABI in include/cafe_gpu.h (libcafe_gpu.so).
+
+This is plumbing for tests and bench.py: numpy arrays in, numpy arrays out, every call goes through
+the C-ABI entry points a reference-side binding would use.  There is no fallback: if the library
+or a CUDA device is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import lru_cache
+
+import numpy as np
+
+from . import buildlib as _build
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+ZERO_LIKELIHOOD = 1
+
+# every symbol include/cafe_gpu.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "cafe_gpu_abi_version", "cafe_gpu_create", "cafe_gpu_destroy", "cafe_gpu_last_error", "cafe_gpu_set_stream",
+    "cafe_gpu_synchronize", "cafe_gpu_set_tree", "cafe_gpu_set_ranges", "cafe_gpu_set_lnc_table",
+    "cafe_gpu_set_families", "cafe_gpu_set_prior", "cafe_gpu_set_error_model", "cafe_gpu_set_rates",
+    "cafe_gpu_build_matrices", "cafe_gpu_num_keys", "cafe_gpu_get_matrix", "cafe_gpu_score", "cafe_gpu_objective",
+    "cafe_gpu_objective_device", "cafe_gpu_family_results", "cafe_gpu_family_likelihoods",
+    "cafe_gpu_conditional_distribution", "cafe_gpu_pvalues", "cafe_gpu_launch_count",
+    "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_last_kernel_ms", "cafe_gpu_score_flops",
+]
+
+
+class CafeGpuError(RuntimeError):
+    pass
+
+
+@lru_cache(maxsize=None)
+def load_library():
+    _build.ensure_built()
+    L = C.CDLL(_build.GPU_LIB)
+    vp = C.c_void_p
+    L.cafe_gpu_abi_version.restype = C.c_int
+    L.cafe_gpu_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.cafe_gpu_destroy.argtypes = [vp]
+    L.cafe_gpu_last_error.restype = C.c_char_p
+    L.cafe_gpu_last_error.argtypes = [vp]
+    L.cafe_gpu_set_stream.argtypes = [vp, vp]
+    L.cafe_gpu_synchronize.argtypes = [vp]
+    L.cafe_gpu_set_tree.argtypes = [vp, C.c_int, _ip, _ip, _dp]
+    L.cafe_gpu_set_ranges.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.cafe_gpu_set_lnc_table.argtypes = [vp, _dp, C.c_int, C.c_int]
+    L.cafe_gpu_set_families.argtypes = [vp, C.c_int, C.c_int, _ip, _ip, _ip]
+    L.cafe_gpu_set_prior.argtypes = [vp, _dp, C.c_int]
+    L.cafe_gpu_set_error_model.argtypes = [vp, C.c_int, _dp, C.c_int]
+    L.cafe_gpu_set_rates.argtypes = [vp, _dp, _dp]
+    L.cafe_gpu_build_matrices.argtypes = [vp]
+    L.cafe_gpu_num_keys.argtypes = [vp]
+    L.cafe_gpu_get_matrix.argtypes = [vp, C.c_int, _dp, C.c_int]
+    L.cafe_gpu_score.argtypes = [vp, _dp, _ip]
+    L.cafe_gpu_objective.argtypes = [vp, _dp, _dp, _dp, _ip]
+    L.cafe_gpu_objective_device.argtypes = [vp, _dp, _dp, vp]
+    L.cafe_gpu_family_results.argtypes = [vp, _dp, _dp, _ip]
+    L.cafe_gpu_family_likelihoods.argtypes = [vp, _dp]
+    L.cafe_gpu_conditional_distribution.argtypes = [vp, C.c_int, _dp, C.c_uint64, _dp]
+    L.cafe_gpu_pvalues.argtypes = [vp, _dp, C.c_int, C.c_int, _dp]
+    L.cafe_gpu_launch_count.restype = C.c_int64
+    L.cafe_gpu_launch_count.argtypes = [vp]
+    L.cafe_gpu_reset_launch_count.argtypes = [vp]
+    L.cafe_gpu_enable_timing.argtypes = [vp, C.c_int]
+    L.cafe_gpu_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.cafe_gpu_score_flops.restype = C.c_double
+    L.cafe_gpu_score_flops.argtypes = [vp]
+    return L
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+class CafeGpu:
+    """One C-ABI context (one device, one stream)."""
+
+    def __init__(self, device: int = -1):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.cafe_gpu_create(C.byref(h), device)
+        if rc != 0:
+            raise CafeGpuError(f"cafe_gpu_create failed ({rc}): {self.L.cafe_gpu_last_error(None).decode()}")
+        self.h = h
+        self.n_nodes = 0
+        self.n_leaves = 0
+        self.R = 0
+        self.S = 0
+        self.F = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.cafe_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc < 0:
+            raise CafeGpuError(f"{what} failed ({rc}): {self.L.cafe_gpu_last_error(self.h).decode()}")
+        return rc
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.cafe_gpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    def synchronize(self):
+        self._ck(self.L.cafe_gpu_synchronize(self.h), "synchronize")
+
+    def set_tree(self, left, right, branchlength):
+        left = np.ascontiguousarray(left, dtype=np.int32)
+        right = np.ascontiguousarray(right, dtype=np.int32)
+        bl = np.ascontiguousarray(branchlength, dtype=np.float64)
+        self._ck(self.L.cafe_gpu_set_tree(self.h, len(left), _i(left), _i(right), _d(bl)), "set_tree")
+        self.n_nodes = len(left)
+        self.n_leaves = (len(left) + 1) // 2
+
+    def set_ranges(self, rmin, rmax, root_min, root_max):
+        self._ck(self.L.cafe_gpu_set_ranges(self.h, rmin, rmax, root_min, root_max), "set_ranges")
+        self.R = root_max - root_min + 1
+        self.S = max(rmax, root_max) + 1
+
+    def set_lnc_table(self, table):
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        self._ck(self.L.cafe_gpu_set_lnc_table(self.h, _d(table), table.shape[0], table.shape[1]), "set_lnc_table")
+
+    def set_families(self, counts, multiplicity=None, first_index=None):
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        m = None if multiplicity is None else np.ascontiguousarray(multiplicity, dtype=np.int32)
+        fi = None if first_index is None else np.ascontiguousarray(first_index, dtype=np.int32)
+        self._ck(self.L.cafe_gpu_set_families(self.h, counts.shape[0], counts.shape[1], _i(counts),
+                                              None if m is None else _i(m), None if fi is None else _i(fi)),
+                 "set_families")
+        self.F = counts.shape[0]
+
+    def set_prior(self, prior):
+        prior = np.ascontiguousarray(prior, dtype=np.float64)
+        self._ck(self.L.cafe_gpu_set_prior(self.h, _d(prior), len(prior)), "set_prior")
+
+    def set_error_model(self, leaf, matrix):
+        if matrix is None:
+            self._ck(self.L.cafe_gpu_set_error_model(self.h, leaf, None, 0), "set_error_model")
+            return
+        matrix = np.ascontiguousarray(matrix, dtype=np.float64)
+        self._ck(self.L.cafe_gpu_set_error_model(self.h, leaf, _d(matrix), matrix.shape[0]), "set_error_model")
+
+    def set_rates(self, lam, mu):
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        self._ck(self.L.cafe_gpu_set_rates(self.h, _d(lam), _d(mu)), "set_rates")
+
+    def build_matrices(self):
+        self._ck(self.L.cafe_gpu_build_matrices(self.h), "build_matrices")
+
+    def num_keys(self):
+        return self.L.cafe_gpu_num_keys(self.h)
+
+    def get_matrix(self, node):
+        out = np.zeros((self.S, self.S))
+        self._ck(self.L.cafe_gpu_get_matrix(self.h, node, _d(out), self.S), "get_matrix")
+        return out
+
+    def score(self):
+        s = C.c_double()
+        fz = C.c_int32(-1)
+        rc = self._ck(self.L.cafe_gpu_score(self.h, C.byref(s), C.byref(fz)), "score")
+        return s.value, (fz.value if rc == ZERO_LIKELIHOOD else -1)
+
+    def objective(self, lam, mu):
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        s = C.c_double()
+        fz = C.c_int32(-1)
+        rc = self._ck(self.L.cafe_gpu_objective(self.h, _d(lam), _d(mu), C.byref(s), C.byref(fz)), "objective")
+        return s.value, (fz.value if rc == ZERO_LIKELIHOOD else -1)
+
+    def objective_device(self, lam, mu, out_device_ptr):
+        lam = np.ascontiguousarray(lam, dtype=np.float64)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        self._ck(self.L.cafe_gpu_objective_device(self.h, _d(lam), _d(mu), C.c_void_p(out_device_ptr)), "objective_device")
+
+    def family_results(self):
+        lp = np.zeros(self.F)
+        ml = np.zeros(self.F)
+        am = np.zeros(self.F, dtype=np.int32)
+        self._ck(self.L.cafe_gpu_family_results(self.h, _d(lp), _d(ml), _i(am)), "family_results")
+        return lp, ml, am
+
+    def family_likelihoods(self):
+        out = np.zeros((self.F, self.R))
+        self._ck(self.L.cafe_gpu_family_likelihoods(self.h, _d(out)), "family_likelihoods")
+        return out
+
+    def conditional_distribution(self, n_samples, uniforms=None, seed=0):
+        out = np.zeros((self.R, n_samples))
+        up = None
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+            need = self.R * n_samples * (self.n_nodes - 1)
+            if uniforms.size < need:
+                raise ValueError(f"replay stream needs {need} uniforms")
+            up = _d(uniforms)
+        self._ck(self.L.cafe_gpu_conditional_distribution(self.h, n_samples, up, C.c_uint64(seed), _d(out)),
+                 "conditional_distribution")
+        return out
+
+    def pvalues(self, cd):
+        cd = np.ascontiguousarray(cd, dtype=np.float64)
+        out = np.zeros(self.F)
+        self._ck(self.L.cafe_gpu_pvalues(self.h, _d(cd), cd.shape[0], cd.shape[1], _d(out)), "pvalues")
+        return out
+
+    def launch_count(self):
+        return int(self.L.cafe_gpu_launch_count(self.h))
+
+    def reset_launch_count(self):
+        self.L.cafe_gpu_reset_launch_count(self.h)
+
+    def enable_timing(self, on=True):
+        self._ck(self.L.cafe_gpu_enable_timing(self.h, 1 if on else 0), "enable_timing")
+
+    def last_kernel_ms(self):
+        a = C.c_float()
+        b = C.c_float()
+        self._ck(self.L.cafe_gpu_last_kernel_ms(self.h, C.byref(a), C.byref(b)), "last_kernel_ms")
+        return a.value, b.value
+
+    def score_flops(self):
+        return float(self.L.cafe_gpu_score_flops(self.h))

@@ -1,0 +1,168 @@
+/*
+ * cafe_gpu.h — C-ABI of the B200-native birth–death pruning likelihood path.
+ *
+ * This is the drop-in boundary for CAFE's per-family likelihood hot path.  The
+ * reference has no FFI layer; the seams this ABI replaces are, outermost first (paths relative to
+ * the reference root):
+ *
+ *   B1  double __cafe_best_lambda_search(double* x, void* args)        cafe/lambda.cpp:726
+ *       double cafe_best_lambda_mu_search(double* x, void* args)       cafe/lambdamu.cpp:323
+ *         -> after cafe_shell_set_lambdas (cafe/cafe_shell.c:31) has put (lambda, mu) on every node,
+ *            the body  reset_birthdeath_cache + get_posterior + cafe_free_birthdeath_cache  becomes
+ *            cafe_gpu_set_rates + cafe_gpu_build_matrices + cafe_gpu_score  (= cafe_gpu_objective).
+ *   B2  double get_posterior(pCafeFamily, pCafeTree, std::vector<double>& prior)   cafe/lambda.cpp:691
+ *         -> cafe_gpu_score  (+ cafe_gpu_family_results for maxlh / per-family values)
+ *   B3  void compute_tree_likelihoods(pCafeTree); double* get_likelihoods(pCafeTree)  cafe/cafe_tree.c:320-329
+ *         -> cafe_gpu_family_likelihoods (all families at once)
+ *       void reset_birthdeath_cache(pCafeTree, int, family_size_range*)  cafe/cafe_main.c:319
+ *         -> cafe_gpu_build_matrices  (+ cafe_gpu_get_matrix for inspection)
+ *   B4  matrix cafe_conditional_distribution(pCafeTree, family_size_range*, int, int)
+ *                                                        cafe/conditional_distribution.cpp:86
+ *         -> cafe_gpu_conditional_distribution
+ *   B5  void cafe_tree_p_values(...) cafe/pvalue.cpp:143 + viterbi_set_max_pvalue cafe/viterbi.cpp:32
+ *       as driven per family by viterbi_section cafe/viterbi.cpp:88-97
+ *         -> cafe_gpu_pvalues
+ *
+ * Conventions: plain C, plain pointers and sizes, host pointers unless a parameter says "device".
+ * Every function returns 0 on success, a negative cafe_gpu_status on error (text via
+ * cafe_gpu_last_error), and cafe_gpu_score/objective return CAFE_GPU_ZERO_LIKELIHOOD (1) when some
+ * family has likelihood 0 at every root size — the reference's "posterior = 0" exception
+ * (cafe/lambda.cpp:715-720) — in which case *score_out = -inf and *first_zero_family names it.
+ * One host thread per context; a context owns one device, one stream and all device memory.
+ * There is NO CPU fallback: without a CUDA device cafe_gpu_create fails with CAFE_GPU_ERR_NO_DEVICE.
+ *
+ * Node numbering everywhere is the reference's nlist (infix) order — leaves at even indices,
+ * internal nodes at odd indices (cafe/cafe_commands.cpp:1985-2051).  "Leaf order" means leaf k is
+ * node 2k.  Only binary trees (cafe/cafe_tree.c:248-249).
+ */
+#ifndef CAFE_GPU_H
+#define CAFE_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cafe_gpu_ctx cafe_gpu_ctx;
+
+enum cafe_gpu_status {
+    CAFE_GPU_OK = 0,
+    CAFE_GPU_ZERO_LIKELIHOOD = 1,
+    CAFE_GPU_ERR_NO_DEVICE = -1,
+    CAFE_GPU_ERR_CUDA = -2,
+    CAFE_GPU_ERR_ARG = -3,
+    CAFE_GPU_ERR_STATE = -4,
+    CAFE_GPU_ERR_UNSUPPORTED = -5
+};
+
+/* ABI version of this header (bumped on incompatible change). */
+#define CAFE_GPU_ABI_VERSION 1
+int cafe_gpu_abi_version(void);
+
+/* device < 0 selects the current CUDA device.  Fails (no CPU fallback) when there is none. */
+int cafe_gpu_create(cafe_gpu_ctx** out, int device);
+void cafe_gpu_destroy(cafe_gpu_ctx* ctx);
+const char* cafe_gpu_last_error(const cafe_gpu_ctx* ctx);
+
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*), e.g. the
+ * caller's framework stream; NULL restores the context's own stream. */
+int cafe_gpu_set_stream(cafe_gpu_ctx* ctx, void* cuda_stream);
+int cafe_gpu_synchronize(cafe_gpu_ctx* ctx);
+
+/* Tree topology.  left/right = children->head / children->tail (cafe/cafe_tree.c:248-249), -1 at
+ * leaves.  branchlength as parsed (double); the (int) truncation of the matrix key
+ * (cafe/cafe_tree.c:376, libtree/birthdeath.h:26-31) is applied inside. */
+int cafe_gpu_set_tree(cafe_gpu_ctx* ctx, int n_nodes, const int32_t* left, const int32_t* right,
+                      const double* branchlength);
+
+/* family_size_range (libtree/family.h:10-15) as copied to the tree by copy_range_to_tree
+ * (cafe/cafe_main.c:52-60).  range_min must be 0 (init_family_size, cafe/cafe_family.c:357-364).
+ * Matrix dimension S = max(range_max, root_max) + 1 (cafe/cafe_main.c:325). */
+int cafe_gpu_set_ranges(cafe_gpu_ctx* ctx, int range_min, int range_max, int root_min, int root_max);
+
+/* lnC table built ON THE HOST with the reference's Lanczos gammaln (libcommon/mathfunc.c:87-119,
+ * 224-229; libtree/chooseln_cache.h:27-41): row-major [rows][cols], rows >= 2*(S-1), cols >= S,
+ * table[n*cols + x] = chooseln(n, x). */
+int cafe_gpu_set_lnc_table(cafe_gpu_ctx* ctx, const double* lnc, int rows, int cols);
+
+/* Unique family count patterns: counts[f*n_leaves + k] = size of family f in leaf k (leaf order).
+ * multiplicity (NULL => 1): how many families of the original list share the pattern (the `ref`
+ * short-cut of cafe/lambda.cpp:702-714, cafe/cafe_family.c:9-34).  first_index (NULL => f): index
+ * of the first such family in the original list, reported by cafe_gpu_score on zero likelihood. */
+int cafe_gpu_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, const int32_t* counts,
+                          const int32_t* multiplicity, const int32_t* first_index);
+
+/* Root prior, prior[i] for root size root_min+i (cafe/lambda.cpp:841-852); len >= root_max-root_min+1. */
+int cafe_gpu_set_prior(cafe_gpu_ctx* ctx, const double* prior, int len);
+
+/* Dense error matrix errormatrix[observed][true], row-major dim x dim (libtree/family.h:31-38,
+ * cafe/error_model.cpp:145-259), attached to leaf `leaf` (leaf order) or to all leaves when
+ * leaf < 0.  errormatrix == NULL detaches.  dim must be >= range_max+1. */
+int cafe_gpu_set_error_model(cafe_gpu_ctx* ctx, int leaf, const double* errormatrix, int dim);
+
+/* Per-node (lambda, mu) as cafe_shell_set_lambdas leaves them in
+ * pcnode->birth_death_probabilities (cafe/cafe_shell.c:148-244); mu < 0 selects the lambda-only
+ * formulas (libtree/birthdeath.c:250-254,272-273).  Root entries are ignored.  Distinct
+ * (int t, lambda, mu) keys are found as gather_keys/add_key do (cafe/cafe_tree.c:374-446). */
+int cafe_gpu_set_rates(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node);
+
+/* K1: build one S x S transition matrix per distinct key (reset_birthdeath_cache,
+ * cafe/cafe_main.c:319; compute_birthdeath_rates, libtree/birthdeath.c:238-286). */
+int cafe_gpu_build_matrices(cafe_gpu_ctx* ctx);
+int cafe_gpu_num_keys(const cafe_gpu_ctx* ctx);
+/* Copy back the matrix used by the branch above `node`, row-major S x S. */
+int cafe_gpu_get_matrix(cafe_gpu_ctx* ctx, int node, double* out, int out_dim);
+
+/* K2+K3: pruning over all families, root posterior, score = sum_f mult_f * log(max_j L_f[j]*prior[j])
+ * (cafe/lambda.cpp:657-724).  first_zero_family may be NULL. */
+int cafe_gpu_score(cafe_gpu_ctx* ctx, double* score_out, int32_t* first_zero_family);
+/* cafe_gpu_set_rates + cafe_gpu_build_matrices + cafe_gpu_score: one objective evaluation. */
+int cafe_gpu_objective(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node,
+                       double* score_out, int32_t* first_zero_family);
+/* Same, asynchronous and device-resident: out_device[0] = partial score of this context's families,
+ * out_device[1] = (double) smallest first_index with zero likelihood, or +inf.  No host
+ * synchronisation; meant to be followed by one all-reduce (sum, min) across ranks. */
+int cafe_gpu_objective_device(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node,
+                              double* out_device /* device pointer, 2 doubles */);
+
+/* Per-family results of the last score: log(max posterior), max likelihood, argmax_j L[j]
+ * (the `maxlh` side effect, cafe/lambda.cpp:672-676).  Any pointer may be NULL. */
+int cafe_gpu_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, double* max_likelihood,
+                            int32_t* argmax_likelihood);
+/* Root likelihood vectors of all families, row-major [n_families][root_max-root_min+1]
+ * (get_likelihoods, cafe/cafe_tree.c:325-329).  Recomputes with the current matrices. */
+int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out);
+
+/* K4: conditional distribution (cafe/conditional_distribution.cpp:10-120): for every root size
+ * s = root_min..root_max, n_samples simulated families (cafe/cafe_tree.c:533-569), each pruned with
+ * root range {s} and the range.max ratchet of conditional_distribution.cpp:29; rows sorted ascending.
+ * cd_out is row-major [root_max-root_min+1][n_samples].
+ *   uniforms != NULL : "replay" — the stream of unifrnd() draws the single-threaded reference would
+ *                      consume, [(root_max-root_min+1) * n_samples * (n_nodes-1)] doubles, in order
+ *                      (s, trial, prefix-order non-root node); results match the reference draw for draw.
+ *   uniforms == NULL : counter-based device RNG keyed by (seed, s, trial, node). */
+int cafe_gpu_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms,
+                                      uint64_t seed, double* cd_out);
+
+/* K5: family-wide p-values (cafe/viterbi.cpp:88-97,32-39; cafe/pvalue.cpp:143-154;
+ * libcommon/mathfunc.c:663-689): per family the forced range of cafe/cafe_family.c:236-255, prune,
+ * p[s] = pvalue(L[s], cd[s]), result = max_s (0 when the family's root range is empty).
+ * cd is [cd_rows][n_samples] ascending rows, row r = root size 1+r. */
+int cafe_gpu_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
+                     double* max_pvalue_out);
+
+/* Bookkeeping for measurement: kernels launched by this context since creation / last reset, and
+ * CUDA-event time (ms) of the last K1 and K2 launches (events recorded on the context's stream). */
+int64_t cafe_gpu_launch_count(const cafe_gpu_ctx* ctx);
+void cafe_gpu_reset_launch_count(cafe_gpu_ctx* ctx);
+int cafe_gpu_enable_timing(cafe_gpu_ctx* ctx, int on);
+int cafe_gpu_last_kernel_ms(cafe_gpu_ctx* ctx, float* k1_ms, float* k2_ms);
+/* Algorithmic fp64 flops of one cafe_gpu_score over the current families:
+ * sum over internal edges of 2*W*W (2*R*W at the root), leaf edges excluded. */
+double cafe_gpu_score_flops(const cafe_gpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAFE_GPU_H */

@@ -1,0 +1,359 @@
+"""ctypes loaders for the CPU oracle — TEST INFRASTRUCTURE ONLY.
+
+`oracle.lib()`   -> oracle/libcafe_oracle.so  (our C restatement, oracle/cafe_oracle.c)
+`oracle.ref()`   -> oracle/_ref/libcafe_ref.so (the unmodified reference + oracle/ref_shim.cpp), or None
+                    when it has not been built (it needs /root/reference at build time; the built .so
+                    travels to the GPU box, the sources do not).
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this
+package.  The product (cafe_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from functools import lru_cache
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_lp = C.POINTER(C.c_long)
+_dpp = C.POINTER(_dp)
+
+
+def build(ref: bool = True) -> None:
+    """Compile the oracle (always) and the reference (when /root/reference is present)."""
+    subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+    if ref and os.path.isdir("/root/reference/cafe"):
+        subprocess.run(["make", "-s", "-j8", "-C", HERE, "ref"], check=True)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _iptr(a):
+    return a.ctypes.data_as(_ip)
+
+
+@lru_cache(maxsize=None)
+def lib():
+    path = os.path.join(HERE, "libcafe_oracle.so")
+    if not os.path.exists(path):
+        build(ref=False)
+    L = C.CDLL(path)
+    L.orc_gammaln.restype = C.c_double
+    L.orc_gammaln.argtypes = [C.c_double]
+    L.orc_chooseln.restype = C.c_double
+    L.orc_chooseln.argtypes = [C.c_double, C.c_double]
+    L.orc_poisspdf.restype = C.c_double
+    L.orc_poisspdf.argtypes = [C.c_int, C.c_double]
+    L.orc_unifrnd.restype = C.c_double
+    L.orc_lnc_table.argtypes = [C.c_int, _dp]
+    L.orc_bd_matrix.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, _dp]
+    L.orc_key_branchlength.restype = C.c_int
+    L.orc_key_branchlength.argtypes = [C.c_double]
+    L.orc_matvec.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+    L.orc_prune.restype = C.c_int
+    L.orc_prune.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _ip, _dpp, C.c_int,
+                            C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+    L.orc_posterior.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _ip]
+    L.orc_score.restype = C.c_double
+    L.orc_score.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _dpp, C.c_int,
+                            C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip, _ip,
+                            _dp, _dp, _ip, _dp, _ip]
+    L.orc_random_familysize.restype = C.c_int
+    L.orc_random_familysize.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, C.c_int, C.c_int, _dp, _lp, _ip]
+    L.orc_random_probabilities.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.c_int, _dp, _lp, _dp, _dp, _ip, _ip]
+    L.orc_pvalue.restype = C.c_double
+    L.orc_pvalue.argtypes = [C.c_double, _dp, C.c_int]
+    L.orc_init_family_size.argtypes = [C.c_int, _ip, _ip, _ip, _ip]
+    L.orc_family_pvalue.restype = C.c_double
+    L.orc_family_pvalue.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _dpp, C.c_int, _ip,
+                                    _dp, C.c_int, C.c_int, _dp, _ip]
+    return L
+
+
+@lru_cache(maxsize=None)
+def ref():
+    path = os.path.join(HERE, "_ref", "libcafe_ref.so")
+    if not os.path.exists(path):
+        return None
+    R = C.CDLL(path)
+    R.refshim_gammaln.restype = C.c_double
+    R.refshim_gammaln.argtypes = [C.c_double]
+    R.refshim_chooseln.restype = C.c_double
+    R.refshim_chooseln.argtypes = [C.c_double, C.c_double]
+    R.refshim_poisspdf.restype = C.c_double
+    R.refshim_poisspdf.argtypes = [C.c_int, C.c_double]
+    R.refshim_pvalue.restype = C.c_double
+    R.refshim_pvalue.argtypes = [C.c_double, _dp, C.c_int]
+    R.refshim_srand.argtypes = [C.c_uint]
+    R.refshim_unifrnd.restype = C.c_double
+    R.refshim_init_family_size.argtypes = [C.c_int, _ip]
+    R.refshim_bd_matrix.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, _dp]
+    R.refshim_bd_rate_log_alpha.restype = C.c_double
+    R.refshim_bd_rate_log_alpha.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+    R.refshim_bd_likelihood_s_c.restype = C.c_double
+    R.refshim_bd_likelihood_s_c.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+    R.refshim_matvec.argtypes = [_dp, C.c_int, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp]
+    R.refshim_session_new.restype = C.c_void_p
+    R.refshim_session_new.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    R.refshim_n_nodes.restype = C.c_int
+    R.refshim_n_nodes.argtypes = [C.c_void_p]
+    R.refshim_describe.argtypes = [C.c_void_p, _ip, _ip, _ip, _dp, C.c_char_p, C.c_int]
+    R.refshim_set_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    R.refshim_set_rates.argtypes = [C.c_void_p, _dp, _dp]
+    R.refshim_reset_cache.argtypes = [C.c_void_p]
+    R.refshim_get_matrix.restype = C.c_int
+    R.refshim_get_matrix.argtypes = [C.c_void_p, C.c_int, _dp]
+    R.refshim_set_errormodel.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int, C.c_int]
+    R.refshim_read_errormodel.restype = C.c_int
+    R.refshim_read_errormodel.argtypes = [C.c_char_p, C.c_int, _dp, _ip, _ip]
+    R.refshim_likelihoods.restype = C.c_int
+    R.refshim_likelihoods.argtypes = [C.c_void_p, _ip, _dp]
+    R.refshim_set_families.argtypes = [C.c_void_p, C.c_int, _ip, C.c_int]
+    R.refshim_get_refs.argtypes = [C.c_void_p, _ip]
+    R.refshim_get_posterior.restype = C.c_double
+    R.refshim_get_posterior.argtypes = [C.c_void_p, _dp, _ip, C.c_char_p, C.c_int]
+    R.refshim_get_maxlh.argtypes = [C.c_void_p, _ip]
+    R.refshim_prior_poisson.argtypes = [C.c_int, C.c_double, _dp]
+    R.refshim_find_poisson_lambda.restype = C.c_double
+    R.refshim_find_poisson_lambda.argtypes = [C.c_void_p, _ip, _dp]
+    R.refshim_cond_dist.restype = C.c_int
+    R.refshim_cond_dist.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+    R.refshim_random_probabilities.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp]
+    R.refshim_random_familysize.restype = C.c_int
+    R.refshim_random_familysize.argtypes = [C.c_void_p, C.c_int, C.c_int, _ip]
+    R.refshim_family_pvalue.restype = C.c_double
+    R.refshim_family_pvalue.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int, _dp, _ip]
+    R.refshim_load_families.restype = C.c_int
+    R.refshim_load_families.argtypes = [C.c_char_p, C.c_int, _ip, _ip, _ip, C.c_int, _ip, _ip]
+    R.refshim_session_free.argtypes = [C.c_void_p]
+    return R
+
+
+def ref_binary():
+    p = os.path.join(HERE, "_ref", "cafe_ref")
+    return p if os.path.exists(p) else None
+
+
+# --------------------------------------------------------------------------- flat trees
+
+class FlatTree:
+    """Binary tree in the reference's nlist (infix) numbering: leaves even, internal odd
+    (cafe/cafe_commands.cpp:1985-2051)."""
+
+    def __init__(self, left, right, parent, branchlength, names):
+        self.left = np.ascontiguousarray(left, dtype=np.int32)
+        self.right = np.ascontiguousarray(right, dtype=np.int32)
+        self.parent = np.ascontiguousarray(parent, dtype=np.int32)
+        self.branchlength = np.ascontiguousarray(branchlength, dtype=np.float64)
+        self.names = list(names)
+        self.n_nodes = len(self.left)
+        self.n_leaves = (self.n_nodes + 1) // 2
+        self.root = int(np.where(self.parent < 0)[0][0])
+
+    @property
+    def leaf_names(self):
+        return [self.names[i] for i in range(0, self.n_nodes, 2)]
+
+
+def parse_newick(s: str) -> FlatTree:
+    """Minimal Newick reader (names + ':length', binary only) producing the nlist numbering.
+    Test-side convenience; the product's parser is cafe_b200/host (C++)."""
+    s = s.strip().rstrip(";")
+    pos = 0
+
+    def node():
+        nonlocal pos
+        kids = []
+        if s[pos] == "(":
+            pos += 1
+            while True:
+                kids.append(node())
+                if s[pos] == ",":
+                    pos += 1
+                    continue
+                assert s[pos] == ")", f"bad newick at {pos}"
+                pos += 1
+                break
+        start = pos
+        while pos < len(s) and s[pos] not in ",():;":
+            pos += 1
+        name = s[start:pos]
+        bl = -1.0
+        if pos < len(s) and s[pos] == ":":
+            pos += 1
+            start = pos
+            while pos < len(s) and s[pos] not in ",()":
+                pos += 1
+            bl = float(s[start:pos])
+        return {"kids": kids, "name": name, "bl": bl}
+
+    rootn = node()
+    order = []
+
+    def infix(n):
+        if n["kids"]:
+            assert len(n["kids"]) == 2, "Tree must be binary"
+            infix(n["kids"][0])
+            order.append(n)
+            infix(n["kids"][1])
+        else:
+            order.append(n)
+
+    infix(rootn)
+    for i, n in enumerate(order):
+        n["id"] = i
+    N = len(order)
+    left = [-1] * N
+    right = [-1] * N
+    parent = [-1] * N
+    for n in order:
+        if n["kids"]:
+            left[n["id"]] = n["kids"][0]["id"]
+            right[n["id"]] = n["kids"][1]["id"]
+            parent[n["kids"][0]["id"]] = n["id"]
+            parent[n["kids"][1]["id"]] = n["id"]
+    return FlatTree(left, right, parent, [n["bl"] for n in order], [n["name"] for n in order])
+
+
+# --------------------------------------------------------------------------- numpy-level helpers
+
+def bd_matrix(t, lam, mu, maxfs):
+    M = np.zeros((maxfs + 1, maxfs + 1))
+    lib().orc_bd_matrix(float(t), float(lam), float(mu), int(maxfs), _dptr(M))
+    return M
+
+
+def lnc_table(size):
+    T = np.zeros((2 * size, size + 1))
+    lib().orc_lnc_table(int(size), _dptr(T))
+    return T
+
+
+def _matrix_ptrs(mats):
+    """mats: list (per node) of 2-D arrays or None -> (ctypes array of double*, keepalive)."""
+    arr = (_dp * len(mats))()
+    keep = []
+    for i, m in enumerate(mats):
+        if m is None:
+            arr[i] = None
+        else:
+            m = np.ascontiguousarray(m, dtype=np.float64)
+            keep.append(m)
+            arr[i] = _dptr(m)
+    return arr, keep
+
+
+def node_matrices(tree: FlatTree, lam_per_node, mu_per_node, maxfs):
+    """One matrix per non-root node keyed on (int t, lambda, mu) — cafe/cafe_tree.c:374-391,461-483."""
+    cache = {}
+    mats = []
+    for i in range(tree.n_nodes):
+        if i == tree.root:
+            mats.append(None)
+            continue
+        key = (int(tree.branchlength[i]), float(lam_per_node[i]), float(mu_per_node[i]))
+        if key not in cache:
+            cache[key] = bd_matrix(key[0], key[1], key[2], maxfs)
+        mats.append(cache[key])
+    return mats
+
+
+def prune(tree: FlatTree, mats, counts_by_leaf, rng, leaf_err=None):
+    """rng = (min, max, root_min, root_max).  counts_by_leaf in leaf order (even nlist indices)."""
+    S = next(m for m in mats if m is not None).shape[0]
+    lc = np.full(tree.n_nodes, -1, dtype=np.int32)
+    lc[0::2] = counts_by_leaf
+    mp, keep = _matrix_ptrs(mats)
+    E = 0
+    ep = None
+    if leaf_err is not None:
+        ep, keep2 = _matrix_ptrs(leaf_err)
+        E = next(m for m in leaf_err if m is not None).shape[0]
+    out = np.zeros(rng[3] - rng[2] + 1)
+    rc = lib().orc_prune(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S, _iptr(lc),
+                         ep, E, rng[0], rng[1], rng[2], rng[3], _dptr(out))
+    if rc != 0:
+        raise ValueError("leaf count outside the likelihood vector")
+    return out
+
+
+def score(tree: FlatTree, mats, counts, rng, prior, ref_idx=None, leaf_err=None, want_L=False):
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    F = counts.shape[0]
+    S = next(m for m in mats if m is not None).shape[0]
+    mp, keep = _matrix_ptrs(mats)
+    E = 0
+    ep = None
+    if leaf_err is not None:
+        ep, keep2 = _matrix_ptrs(leaf_err)
+        E = next(m for m in leaf_err if m is not None).shape[0]
+    prior = np.ascontiguousarray(prior, dtype=np.float64)
+    logpost = np.zeros(F)
+    maxlik = np.zeros(F)
+    argmax = np.zeros(F, dtype=np.int32)
+    rf = rng[3] - rng[2] + 1
+    L_all = np.zeros((F, rf)) if want_L else None
+    fz = C.c_int(-1)
+    refp = None
+    if ref_idx is not None:
+        ref_idx = np.ascontiguousarray(ref_idx, dtype=np.int32)
+        refp = _iptr(ref_idx)
+    sc = lib().orc_score(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S, ep, E,
+                         rng[0], rng[1], rng[2], rng[3], _dptr(prior), F, _iptr(counts), refp,
+                         _dptr(logpost), _dptr(maxlik), _iptr(argmax),
+                         _dptr(L_all) if want_L else None, C.byref(fz))
+    return {"score": sc, "logpost": logpost, "maxlik": maxlik, "argmax": argmax, "L": L_all,
+            "first_zero": fz.value}
+
+
+def prior_poisson(shift, lam, n=1000):
+    return np.array([lib().orc_poisspdf(shift - 1 + i, lam) for i in range(n)])
+
+
+def random_probabilities(tree, mats, rng_min, rng_max, root_size, trials, uniforms=None):
+    S = next(m for m in mats if m is not None).shape[0]
+    mp, keep = _matrix_ptrs(mats)
+    used = C.c_long(0)
+    srt = np.zeros(trials)
+    uns = np.zeros(trials)
+    sizes = np.zeros((trials, tree.n_nodes), dtype=np.int32)
+    caps = np.zeros(trials, dtype=np.int32)
+    up = None
+    if uniforms is not None:
+        uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+        up = _dptr(uniforms)
+    lib().orc_random_probabilities(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S,
+                                   rng_min, rng_max, root_size, trials, up, C.byref(used),
+                                   _dptr(srt), _dptr(uns), _iptr(sizes), _iptr(caps))
+    return {"sorted": srt, "unsorted": uns, "sizes": sizes, "caps": caps, "used": used.value}
+
+
+def pvalue(v, cd):
+    cd = np.ascontiguousarray(cd, dtype=np.float64)
+    return lib().orc_pvalue(float(v), _dptr(cd), len(cd))
+
+
+def family_pvalue(tree, mats, counts_by_leaf, cd, leaf_err=None):
+    S = next(m for m in mats if m is not None).shape[0]
+    mp, keep = _matrix_ptrs(mats)
+    lc = np.full(tree.n_nodes, -1, dtype=np.int32)
+    lc[0::2] = counts_by_leaf
+    cd = np.ascontiguousarray(cd, dtype=np.float64)
+    E = 0
+    ep = None
+    if leaf_err is not None:
+        ep, keep2 = _matrix_ptrs(leaf_err)
+        E = next(m for m in leaf_err if m is not None).shape[0]
+    pv = np.zeros(max(1, cd.shape[0] + 8))
+    rf = C.c_int(0)
+    p = lib().orc_family_pvalue(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S, ep, E,
+                                _iptr(lc), _dptr(cd), cd.shape[0], cd.shape[1], _dptr(pv), C.byref(rf))
+    return p, pv[:max(0, min(rf.value, cd.shape[0]))]

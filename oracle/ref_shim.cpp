@@ -1,0 +1,317 @@
+// oracle/ref_shim.cpp — TEST INFRASTRUCTURE ONLY.
+//
+// Thin extern "C" doors into the UNMODIFIED reference objects (compiled by oracle/Makefile from the
+// sources under /root/reference into oracle/_ref/).  This file is OUR code: it only calls the
+// reference's public functions so that tests/ and tests/golden/make_golden.py can drive the reference
+// through ctypes and pin the oracle (oracle/cafe_oracle.c) and the CUDA path against it.
+// It is linked into oracle/_ref/libcafe_ref.so, never into the product.
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+extern "C" {
+#include "cafe.h"
+#include "cafe_shell.h"
+#include <family.h>
+#include <mathfunc.h>
+#include <chooseln_cache.h>
+extern pBirthDeathCacheArray probability_cache;
+extern struct chooseln_cache cache;
+int __check_error_model_columnsums(pErrorStruct errormodel);
+void __cafe_famliy_check_the_pattern(pCafeFamily pcf);
+}
+#include "gene_family.h"
+#include "lambda.h"
+#include "conditional_distribution.h"
+#include "pvalue.h"
+#include "error_model.h"
+
+namespace {
+struct Session {
+    pCafeTree tree = nullptr;
+    family_size_range range;
+    pCafeFamily family = nullptr;
+    std::vector<pErrorStruct> errs;
+};
+family_size_range make_range(int rmin, int rmax, int root_min, int root_max) {
+    family_size_range r; r.min = rmin; r.max = rmax; r.root_min = root_min; r.root_max = root_max; return r;
+}
+// The reference's chooseln_cache_resize2 keeps rows allocated at the OLD width (chooseln_cache.c:36-56 vs
+// chooseln_cache.h:33-37), so growing the cache reads past them.  The shim never grows: it frees and
+// re-initialises, which is what a fresh reference process sees.
+void ensure_lnc(int size) {
+    if (chooseln_is_init2(&cache) && get_chooseln_cache_size2(&cache) >= size) return;
+    if (chooseln_is_init2(&cache)) chooseln_cache_free2(&cache);
+    chooseln_cache_init2(&cache, size);
+}
+pCafeNode node_at(Session* s, int i) { return (pCafeNode)s->tree->super.nlist->array[i]; }
+}  // namespace
+
+extern "C" {
+
+double refshim_gammaln(double a) { return gammaln(a); }
+double refshim_chooseln(double n, double r) { return chooseln(n, r); }
+double refshim_poisspdf(int x, double l) { return poisspdf(x, l); }
+double refshim_pvalue(double v, const double* cd, int n) { return pvalue(v, cd, n); }
+void refshim_srand(unsigned seed) { srand(seed); }
+double refshim_unifrnd() { return unifrnd(); }
+
+void refshim_init_family_size(int max, int* out4) {
+    family_size_range r; init_family_size(&r, max);
+    out4[0] = r.root_min; out4[1] = r.root_max; out4[2] = r.min; out4[3] = r.max;
+}
+
+// compute_birthdeath_rates (libtree/birthdeath.c:238) with the global lnC cache sized as the
+// reference does in birthdeath_cache_init (birthdeath.c:331-343).
+void refshim_bd_matrix(double t, double lambda, double mu, int maxfs, double* out) {
+    ensure_lnc(maxfs);
+    struct square_matrix* m = compute_birthdeath_rates(t, lambda, mu, maxfs);
+    memcpy(out, m->values, sizeof(double) * (size_t)m->size * m->size);
+    free(m->values); free(m);
+}
+
+double refshim_bd_rate_log_alpha(int s, int c, double log_alpha, double coeff, int cache_size) {
+    ensure_lnc(cache_size);
+    return birthdeath_rate_with_log_alpha(s, c, log_alpha, coeff, &cache);
+}
+double refshim_bd_likelihood_s_c(int s, int c, double t, double lambda, double mu, int cache_size) {
+    ensure_lnc(cache_size);
+    return birthdeath_likelihood_with_s_c(s, c, t, lambda, mu, &cache);
+}
+
+void refshim_matvec(const double* M, int S, const double* vec, int r0, int r1, int c0, int c1, double* out) {
+    struct square_matrix m; m.values = const_cast<double*>(M); m.size = S;
+    square_matrix_multiply(&m, const_cast<double*>(vec), r0, r1, c0, c1, out);
+}
+
+// ---------------------------------------------------------------- tree sessions
+void* refshim_session_new(const char* newick, int rmin, int rmax, int root_min, int root_max) {
+    Session* s = new Session();
+    s->range = make_range(rmin, rmax, root_min, root_max);
+    s->tree = cafe_tree_new(newick, &s->range, 0, 0);
+    if (!s->tree) { delete s; return nullptr; }
+    return s;
+}
+int refshim_n_nodes(void* h) { return ((Session*)h)->tree->super.nlist->size; }
+
+// nlist-order description: children (head/tail), parent, branch length, '\n'-joined names
+void refshim_describe(void* h, int* left, int* right, int* parent, double* bl, char* names, int names_len) {
+    Session* s = (Session*)h;
+    int n = refshim_n_nodes(h);
+    std::string all;
+    for (int i = 0; i < n; i++) {
+        pTreeNode tn = (pTreeNode)s->tree->super.nlist->array[i];
+        left[i] = right[i] = parent[i] = -1;
+        if (tn->children && tn->children->head) {
+            left[i] = ((pTreeNode)tn->children->head->data)->id;
+            right[i] = ((pTreeNode)tn->children->tail->data)->id;
+        }
+        if (tn->parent) parent[i] = tn->parent->id;
+        bl[i] = ((pPhylogenyNode)tn)->branchlength;
+        const char* nm = ((pPhylogenyNode)tn)->name;
+        all += (nm ? nm : "");
+        all += "\n";
+    }
+    strncpy(names, all.c_str(), names_len - 1);
+    names[names_len - 1] = 0;
+}
+
+void refshim_set_range(void* h, int rmin, int rmax, int root_min, int root_max) {
+    Session* s = (Session*)h;
+    s->range = make_range(rmin, rmax, root_min, root_max);
+    cafe_tree_set_parameters(s->tree, &s->range, 0);
+}
+
+void refshim_set_rates(void* h, const double* lambda, const double* mu) {
+    Session* s = (Session*)h;
+    int n = refshim_n_nodes(h);
+    for (int i = 0; i < n; i++) {
+        node_at(s, i)->birth_death_probabilities.lambda = lambda[i];
+        node_at(s, i)->birth_death_probabilities.mu = mu[i];
+    }
+}
+// reset_birthdeath_cache (cafe/cafe_main.c:319): rebuilds every (int t, lambda, mu) matrix
+void refshim_reset_cache(void* h) {
+    Session* s = (Session*)h;
+    reset_birthdeath_cache(s->tree, 0, &s->range);
+}
+int refshim_get_matrix(void* h, int node, double* out) {
+    Session* s = (Session*)h;
+    struct square_matrix* m = node_at(s, node)->birthdeath_matrix;
+    if (!m) return 0;
+    if (out) memcpy(out, m->values, sizeof(double) * (size_t)m->size * m->size);
+    return m->size;
+}
+
+// dense errormatrix[observed][true] (dim x dim) attached to leaf `node` (nlist index); dim==0 clears
+void refshim_set_errormodel(void* h, int node, const double* matrix, int dim, int fromdiff, int todiff) {
+    Session* s = (Session*)h;
+    if (dim == 0) { node_at(s, node)->errormodel = nullptr; return; }
+    pErrorStruct e = (pErrorStruct)calloc(1, sizeof(ErrorStruct));
+    e->maxfamilysize = dim - 1; e->fromdiff = fromdiff; e->todiff = todiff;
+    e->errormatrix = (double**)calloc(dim, sizeof(double*));
+    for (int i = 0; i < dim; i++) {
+        e->errormatrix[i] = (double*)calloc(dim + 2048, sizeof(double));  // slack: the reference may read past dim
+        memcpy(e->errormatrix[i], matrix + (size_t)i * dim, sizeof(double) * dim);
+    }
+    s->errs.push_back(e);
+    node_at(s, node)->errormodel = e;
+}
+
+// error-model file -> dense matrix via the reference's reader + column-sum fix (error_model.cpp:145-204,
+// cafe_shell.c:585-622).  Returns dim; out may be NULL to query.
+int refshim_read_errormodel(const char* path, int range_max, double* out, int* fromdiff, int* todiff) {
+    ErrorStruct e; memset(&e, 0, sizeof(e));
+    e.maxfamilysize = range_max;
+    std::ifstream ifs(path);
+    if (!ifs) return -1;
+    ifs >> e;
+    __check_error_model_columnsums(&e);
+    int dim = e.maxfamilysize + 1;
+    if (out) for (int i = 0; i < dim; i++) memcpy(out + (size_t)i * dim, e.errormatrix[i], sizeof(double) * dim);
+    if (fromdiff) *fromdiff = e.fromdiff;
+    if (todiff) *todiff = e.todiff;
+    return dim;
+}
+
+// compute_tree_likelihoods for one family; counts in leaf order (even nlist indices)
+int refshim_likelihoods(void* h, const int* counts, double* L_out) {
+    Session* s = (Session*)h;
+    int n = refshim_n_nodes(h);
+    for (int i = 0; i < n; i++) node_at(s, i)->familysize = -1;
+    for (int i = 0, k = 0; i < n; i += 2, k++) node_at(s, i)->familysize = counts[k];
+    compute_tree_likelihoods(s->tree);
+    memcpy(L_out, get_likelihoods(s->tree), sizeof(double) * s->tree->rfsize);
+    return s->tree->rfsize;
+}
+
+// families attached to the session; species order = leaf order
+void refshim_set_families(void* h, int F, const int* counts, int dedup) {
+    Session* s = (Session*)h;
+    int n = refshim_n_nodes(h);
+    int nl = (n + 1) / 2;
+    std::vector<std::string> species;
+    for (int i = 0; i < n; i += 2) species.push_back(((pPhylogenyNode)s->tree->super.nlist->array[i])->name);
+    if (s->family) cafe_family_free(s->family);
+    s->family = cafe_family_init(species);
+    for (int f = 0; f < F; f++) {
+        std::ostringstream id; id << "F" << f;
+        std::vector<int> v(counts + (size_t)f * nl, counts + (size_t)(f + 1) * nl);
+        cafe_family_add_item(s->family, gene_family(id.str(), "d", v));
+    }
+    cafe_family_set_species_index(s->family, s->tree);
+    if (dedup) __cafe_famliy_check_the_pattern(s->family);
+}
+void refshim_get_refs(void* h, int* ref_out) {
+    Session* s = (Session*)h;
+    for (int i = 0; i < s->family->flist->size; i++) ref_out[i] = ((pCafeFamilyItem)s->family->flist->array[i])->ref;
+}
+
+// get_posterior (cafe/lambda.cpp:691); *threw = 1 when the zero-likelihood exception fired
+double refshim_get_posterior(void* h, const double* prior1000, int* threw, char* msg, int msg_len) {
+    Session* s = (Session*)h;
+    std::vector<double> pr(prior1000, prior1000 + FAMILYSIZEMAX);
+    *threw = 0;
+    try { return get_posterior(s->family, s->tree, pr); }
+    catch (std::runtime_error& e) {
+        *threw = 1;
+        if (msg) { strncpy(msg, e.what(), msg_len - 1); msg[msg_len - 1] = 0; }
+        return log(0);
+    }
+}
+void refshim_get_maxlh(void* h, int* out) {
+    Session* s = (Session*)h;
+    for (int i = 0; i < s->family->flist->size; i++) out[i] = ((pCafeFamilyItem)s->family->flist->array[i])->maxlh;
+}
+
+void refshim_prior_poisson(int shift, double lambda, double* out1000) {
+    std::vector<double> pr;
+    cafe_set_prior_rfsize_poisson_lambda(pr, shift, &lambda);
+    memcpy(out1000, pr.data(), sizeof(double) * FAMILYSIZEMAX);
+}
+// find_poisson_lambda (lambda.cpp:808) — consumes one rand()
+double refshim_find_poisson_lambda(void* h, int* iters, double* score) {
+    Session* s = (Session*)h;
+    poisson_lambda pl = find_poisson_lambda(s->family);
+    double v = pl.parameters[0];
+    if (iters) *iters = pl.num_iterations;
+    if (score) *score = pl.score;
+    free(pl.parameters);
+    return v;
+}
+
+// cafe_conditional_distribution (conditional_distribution.cpp:86); out [rfsize][n_samples]
+int refshim_cond_dist(void* h, int nthreads, int n_samples, double* out) {
+    Session* s = (Session*)h;
+    matrix cd = cafe_conditional_distribution(s->tree, &s->range, nthreads, n_samples);
+    for (size_t r = 0; r < cd.size(); r++) memcpy(out + r * n_samples, cd[r].data(), sizeof(double) * n_samples);
+    return (int)cd.size();
+}
+// one row, unsorted copy too is not available from the reference; sorted only
+void refshim_random_probabilities(void* h, int root_size, int trials, double* out_sorted) {
+    Session* s = (Session*)h;
+    std::vector<double> p = get_random_probabilities(s->tree, root_size, trials);
+    memcpy(out_sorted, p.data(), sizeof(double) * trials);
+}
+int refshim_random_familysize(void* h, int root_size, int max_family_size, int* sizes_out) {
+    Session* s = (Session*)h;
+    int m = cafe_tree_random_familysize(s->tree, root_size, max_family_size);
+    int n = refshim_n_nodes(h);
+    for (int i = 0; i < n; i++) sizes_out[i] = node_at(s, i)->familysize;
+    return m;
+}
+
+// family p-value exactly as viterbi_section does it (viterbi.cpp:88-97): forced per-family range,
+// cafe_tree_p_values, max.  cd is [cd_rows][n_samples].
+double refshim_family_pvalue(void* h, int idx, const double* cd, int cd_rows, int n_samples, double* pvals_out, int* rfsize_out) {
+    Session* s = (Session*)h;
+    std::vector<std::vector<double> > cdv(cd_rows);
+    for (int r = 0; r < cd_rows; r++) cdv[r].assign(cd + (size_t)r * n_samples, cd + (size_t)(r + 1) * n_samples);
+    cafe_family_set_size_with_family_forced(s->family, idx, s->tree);
+    int rf = s->tree->rfsize;
+    if (rfsize_out) *rfsize_out = rf;
+    double best = 0;
+    if (rf > 0) {
+        std::vector<double> p1(rf);
+        cafe_tree_p_values(s->tree, p1, cdv, n_samples);
+        best = p1[0];
+        for (int i = 0; i < rf; i++) { if (pvals_out) pvals_out[i] = p1[i]; if (p1[i] > best) best = p1[i]; }
+    }
+    copy_range_to_tree(s->tree, &s->range);
+    return best;
+}
+
+// reference family-table reader + dedup (gene_family.cpp:186-225, cafe_family.c:9-34)
+int refshim_load_families(const char* path, int max_size, int* n_species, int* F_out, int* counts_out, int cap, int* ref_out, int* max_size_out) {
+    std::ifstream ifs(path);
+    if (!ifs) return -1;
+    std::string p(path);
+    char sep = (p.size() >= 3 && p.substr(p.size() - 3) == "csv") ? ',' : '\t';
+    pCafeFamily f = load_gene_families(ifs, sep, max_size);
+    if (!f) return -2;
+    *n_species = f->num_species; *F_out = f->flist->size;
+    if (max_size_out) *max_size_out = f->max_size;
+    if (counts_out) {
+        if ((long)f->flist->size * f->num_species > cap) return -3;
+        for (int i = 0; i < f->flist->size; i++) {
+            pCafeFamilyItem it = (pCafeFamilyItem)f->flist->array[i];
+            memcpy(counts_out + (size_t)i * f->num_species, it->count, sizeof(int) * f->num_species);
+            if (ref_out) ref_out[i] = it->ref;
+        }
+    }
+    cafe_family_free(f);
+    return 0;
+}
+
+void refshim_session_free(void* h) {
+    Session* s = (Session*)h;
+    if (s->family) cafe_family_free(s->family);
+    // tree and error structs intentionally leaked (test process lifetime)
+    delete s;
+}
+
+}  // extern "C"

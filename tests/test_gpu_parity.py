@@ -1,0 +1,198 @@
+"""-m gpu: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (fp64 path): transition-matrix entries 1e-12 relative (entries > 1e-300);
+per-family root likelihoods 1e-11 relative; per-family log max-posterior 1e-9 absolute; total score
+max(1e-6, 1e-12*|score|) absolute.  The GEMM sums in a different order than the reference's serial
+j-loop, so results are not bit-identical by construction.
+"""
+import numpy as np
+import pytest
+
+import oracle
+from cafe_b200 import host as chost
+
+from util import EXAMPLE_TREE, Problem, random_tree, rel_err, simulate_families
+
+pytestmark = pytest.mark.gpu
+
+TOL_MATRIX = 1e-12
+TOL_L = 1e-11
+TOL_LOGPOST = 1e-9
+
+
+def score_tol(s):
+    return max(1e-6, 1e-12 * abs(s))
+
+
+def small_counts(n_leaves, F, hi, seed):
+    rng = np.random.RandomState(seed)
+    base = rng.randint(1, hi, size=(F, 1))
+    return np.maximum(0, base + rng.randint(-2, 3, size=(F, n_leaves))).astype(np.int32)
+
+
+@pytest.mark.parametrize("t,lam,mu,maxfs", [
+    (10, 0.02, 0.01, 3), (1, 0.01, -1, 20), (68, 0.006335, -1, 140), (93, 0.005, -1, 250),
+    (17, 0.004, 0.003, 250), (6, 0.002, 0.002, 84), (93, 0.02, -1, 30), (0.9, 0.1, -1, 10),
+    (40, 0.001, 0.0015, 500),
+])
+def test_k1_matrix_vs_oracle(t, lam, mu, maxfs):
+    # a 2-leaf tree whose two branches carry the key under test
+    p = Problem(f"(A:{t},B:{t})", [[1, 1]], lam, mu=None if mu < 0 else mu, ranges=(0, maxfs, 1, maxfs))
+    g = p.make_gpu()
+    M = g.get_matrix(0)
+    ref = oracle.bd_matrix(int(t), lam, mu, maxfs)
+    assert M.shape == ref.shape
+    big = ref > 1e-300
+    assert rel_err(M[big], ref[big]).max() <= TOL_MATRIX
+    assert np.abs(M[~big] - ref[~big]).max() <= 1e-300
+    g.close()
+
+
+def test_k1_reference_kat_row_sums():
+    # Appendix E of SURVEY.md: t=68, lambda=0.006335 -> M[1][0], M[1][1], M[5][5]
+    p = Problem("(A:68,B:68)", [[1, 1]], 0.006335, ranges=(0, 140, 1, 140))
+    g = p.make_gpu()
+    M = g.get_matrix(0)
+    assert abs(M[1, 0] - 0.30108052950139091) < 1e-13
+    assert abs(M[1, 1] - 0.48848842624205624) < 1e-13
+    assert abs(M[5, 5] - 0.19579137469510913) < 1e-13
+    g.close()
+
+
+def check_problem(p, expect_zero=False):
+    g = p.make_gpu()
+    o = p.oracle_score(want_L=True)
+    s, fz = g.score()
+    L = g.family_likelihoods()
+    lp, ml, am = g.family_results()
+    if expect_zero:
+        assert fz == o["first_zero"] and fz >= 0
+        assert s == -np.inf
+    else:
+        assert fz == -1 and o["first_zero"] == -1
+        assert abs(s - o["score"]) <= score_tol(o["score"]), (s, o["score"])
+        assert np.abs(lp - o["logpost"]).max() <= TOL_LOGPOST
+    big = o["L"] > 1e-290
+    assert rel_err(L[big], o["L"][big]).max() <= TOL_L
+    assert np.abs(L[~big] - o["L"][~big]).max() <= 1e-290
+    assert rel_err(ml, o["maxlik"], 1e-290).max() <= TOL_L
+    # argmax may legitimately differ only where two root sizes tie to within rounding
+    diff = am != o["argmax"]
+    if diff.any():
+        rows = np.where(diff)[0]
+        assert rel_err(o["L"][rows, am[rows]], o["L"][rows, o["argmax"][rows]]).max() < 1e-10
+    g.close()
+    return s
+
+
+def test_k2_reference_kat_small_tree():
+    # tests/test.cpp:441-474 of the reference: ((A:1,B:1):1,(C:1,D:1):1), lambda=.01, leaves 5,3,2,4
+    p = Problem("((A:1,B:1):1,(C:1,D:1):1);", [[5, 3, 2, 4]], 0.01, ranges=(0, 7, 0, 7), prior_lambda=3.0)
+    g = p.make_gpu()
+    L = g.family_likelihoods()[0]
+    kat = [0, 1.4213810941710317e-13, 2.8750146893173634e-09, 4.1190257854799189e-07, 6.7380816658820656e-07,
+           2.0604688982933231e-08, 3.5778191226909485e-11, 2.9103694791175412e-14]
+    assert L[0] == 0
+    assert rel_err(L[1:], kat[1:]).max() < 1e-12
+    g.close()
+
+
+def test_k2_example_tree_single_lambda():
+    p = Problem(EXAMPLE_TREE, small_counts(5, 59, 30, 3), 0.005)
+    check_problem(p)
+
+
+def test_k2_two_lambda_classes():
+    p = Problem(EXAMPLE_TREE, small_counts(5, 40, 25, 4), [0.002, 0.006], lambda_tree="(((2,2)1,(1,1)1)1,1)")
+    check_problem(p)
+
+
+def test_k2_lambda_mu():
+    p = Problem(EXAMPLE_TREE, small_counts(5, 40, 25, 5), 0.004, mu=0.006)
+    check_problem(p)
+
+
+def test_k2_zero_likelihood_family_reported():
+    # lambda*t >= 1 on the dog branch zeroes its matrix (fact 9): every family scores 0
+    p = Problem(EXAMPLE_TREE, small_counts(5, 8, 20, 6), 0.011, first=np.arange(8, dtype=np.int32) + 100)
+    g = p.make_gpu()
+    s, fz = g.score()
+    assert s == -np.inf and fz == 100
+    g.close()
+
+
+def test_k2_fractional_branch_is_identity():
+    # branch length 0.9 truncates to t=0 -> identity matrix (fact 2)
+    p = Problem("((A:0.9,B:3):2,C:5)", small_counts(3, 16, 12, 7), 0.01)
+    check_problem(p)
+
+
+@pytest.mark.parametrize("n_leaves,seed", [(2, 1), (3, 2), (8, 3), (13, 4), (20, 5)])
+def test_k2_random_trees(n_leaves, seed):
+    nw = random_tree(n_leaves, seed)
+    ot = oracle.parse_newick(nw)
+    depth = 0
+    v = 0
+    while ot.parent[v] >= 0:
+        depth += ot.branchlength[v]
+        v = ot.parent[v]
+    lam = 0.25 / depth
+    n = ot.n_nodes
+    counts = simulate_families(ot, [lam] * n, [-1] * n, 90, 96, np.arange(1, 40), seed)
+    p = Problem(nw, counts, lam)
+    check_problem(p)
+
+
+def test_k2_error_model_band():
+    # errormatrix[observed][true], band -1..1 (tests/integration/errormodel.txt shape)
+    rg = chost.init_family_size(30)
+    dim = rg["max"] + 1
+    E = np.zeros((dim, dim))
+    eps = 0.02744140625
+    for j in range(dim):
+        for d, v in ((-1, eps), (0, 1 - 2 * eps), (1, eps)):
+            if 0 <= j + d < dim:
+                E[j + d, j] = v
+    E[0, 0] = 1 - eps
+    E[dim - 1, dim - 1] = 1 - eps
+    counts = small_counts(5, 48, 28, 8)
+    counts = np.minimum(counts, 30)
+    p = Problem(EXAMPLE_TREE, counts, 0.004, err={k: E for k in range(5)},
+                ranges=(rg["min"], rg["max"], rg["root_min"], rg["root_max"]))
+    check_problem(p)
+
+
+def test_k2_multiplicity_and_first_index():
+    counts = small_counts(5, 20, 20, 9)
+    mult = np.arange(1, 21, dtype=np.int32)
+    p1 = Problem(EXAMPLE_TREE, counts, 0.006, mult=mult)
+    g = p1.make_gpu()
+    s, _ = g.score()
+    lp, _, _ = g.family_results()
+    assert abs(s - float((lp * mult).sum())) <= score_tol(s)
+    g.close()
+
+
+def test_k2_ragged_family_count_not_multiple_of_tile():
+    for F in (1, 7, 129, 257):
+        p = Problem(EXAMPLE_TREE, small_counts(5, F, 22, 10 + F), 0.005)
+        check_problem(p)
+
+
+def test_k2_large_ranges_config2_shape_sample():
+    # config-2 geometry (max size 200 -> W=251, R=250, S=251) on a small family sample
+    nw = random_tree(20, 1)
+    ot = oracle.parse_newick(nw)
+    depth = 0
+    v = 0
+    while ot.parent[v] >= 0:
+        depth += ot.branchlength[v]
+        v = ot.parent[v]
+    lam = 0.25 / depth
+    n = ot.n_nodes
+    counts = simulate_families(ot, [lam] * n, [-1] * n, 250, 40, np.r_[np.arange(1, 60), 150, 180, 199], 11)
+    counts = np.minimum(counts, 200)
+    counts[0, 0] = 200
+    p = Problem(nw, counts, lam)
+    assert p.ranges == (0, 250, 1, 250)
+    check_problem(p)
