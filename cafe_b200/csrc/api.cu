@@ -41,7 +41,6 @@ int cafe_gpu_create(cafe_gpu_ctx** out, int device) {
     ctx->stream = ctx->own_stream;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaMalloc(&ctx->d_score, 2 * sizeof(double));
     cudaMallocHost(&ctx->h_score, 2 * sizeof(double));
     *out = ctx;
@@ -62,7 +61,7 @@ void cafe_gpu_destroy(cafe_gpu_ctx* ctx) {
     cudaFree(ctx->d_logpost); cudaFree(ctx->d_maxlik); cudaFree(ctx->d_argmax); cudaFree(ctx->d_score);
     cudaFreeHost(ctx->h_score);
     free_err_models(ctx);
-    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->ring) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -477,15 +476,26 @@ int64_t cafe_gpu_launch_count(const cafe_gpu_ctx* ctx) { return ctx ? ctx->launc
 void cafe_gpu_reset_launch_count(cafe_gpu_ctx* ctx) { if (ctx) ctx->launches = 0; }
 int cafe_gpu_enable_timing(cafe_gpu_ctx* ctx, int on) {
     if (!ctx) return CAFE_GPU_ERR_ARG;
-    ctx->timing = on != 0; ctx->ev_k1 = ctx->ev_k2 = false;
+    if (on && ctx->ring.empty()) {
+        ctx->ring.resize(4 * cafe_gpu_ctx::kRing);
+        for (auto& e : ctx->ring) CAFE_CK(ctx, cudaEventCreate(&e));
+    }
+    ctx->timing = on != 0;
+    ctx->ring_k1 = ctx->ring_k2 = 0;
     return CAFE_GPU_OK;
 }
-int cafe_gpu_last_kernel_ms(cafe_gpu_ctx* ctx, float* k1_ms, float* k2_ms) {
-    if (!ctx) return CAFE_GPU_ERR_ARG;
+int cafe_gpu_timing_collect(cafe_gpu_ctx* ctx, float* k1_ms, float* k2_ms, int cap) {
+    if (!ctx || cap < 0) return CAFE_GPU_ERR_ARG;
     CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (k1_ms) { *k1_ms = -1.f; if (ctx->ev_k1) CAFE_CK(ctx, cudaEventElapsedTime(k1_ms, ctx->ev[0], ctx->ev[1])); }
-    if (k2_ms) { *k2_ms = -1.f; if (ctx->ev_k2) CAFE_CK(ctx, cudaEventElapsedTime(k2_ms, ctx->ev[2], ctx->ev[3])); }
-    return CAFE_GPU_OK;
+    int n = std::min(std::min(ctx->ring_k1, ctx->ring_k2), std::min(cap, (int)cafe_gpu_ctx::kRing));
+    int first = std::min(ctx->ring_k1, ctx->ring_k2) - n;
+    for (int i = 0; i < n; ++i) {
+        cudaEvent_t* q = ctx->quad(first + i);
+        if (k1_ms) CAFE_CK(ctx, cudaEventElapsedTime(&k1_ms[i], q[0], q[1]));
+        if (k2_ms) CAFE_CK(ctx, cudaEventElapsedTime(&k2_ms[i], q[2], q[3]));
+    }
+    ctx->ring_k1 = ctx->ring_k2 = 0;
+    return n;
 }
 
 double cafe_gpu_score_flops(const cafe_gpu_ctx* ctx) {

@@ -136,8 +136,11 @@ struct cafe_gpu_ctx {
     // bookkeeping
     int64_t launches = 0;
     bool timing = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    bool ev_k1 = false, ev_k2 = false;
+    // ring of CUDA-event quads {K1 begin, K1 end, K2 begin, K2 end}, one quad per objective evaluation
+    static constexpr int kRing = 256;
+    std::vector<cudaEvent_t> ring;   // 4 * kRing events, created on enable_timing
+    int ring_k1 = 0, ring_k2 = 0;    // evaluations recorded since the last collect
+    cudaEvent_t* quad(int i) { return &ring[4 * (i % kRing)]; }
 };
 
 // kernels (defined in the .cu files of this directory); all launch on ctx->stream

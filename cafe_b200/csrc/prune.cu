@@ -298,7 +298,7 @@ int launch_prune_ops(cafe_gpu_ctx* ctx, const int* d_counts_override, int F, int
                      int root_r0, int root_rows, int* root_slot_out);
 
 int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
-    if (ctx->timing) CAFE_CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (ctx->timing) CAFE_CK(ctx, cudaEventRecord(ctx->quad(ctx->ring_k2)[2], ctx->stream));
     int root_slot = -1;
     int rc = launch_prune_ops(ctx, nullptr, ctx->F, ctx->F_pad, nullptr, ctx->root_min, ctx->R, &root_slot);
     if (rc) return rc;
@@ -307,7 +307,7 @@ int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     k_root_posterior<<<(ctx->F + warps_per_block - 1) / warps_per_block, 256, 0, ctx->stream>>>(
         Lroot, ctx->Vp, ctx->F, ctx->R, ctx->d_logprior, ctx->d_logpost, ctx->d_maxlik, ctx->d_argmax);
     ctx->launches++;
-    if (ctx->timing) { CAFE_CK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->ev_k2 = true; }
+    if (ctx->timing) { CAFE_CK(ctx, cudaEventRecord(ctx->quad(ctx->ring_k2)[3], ctx->stream)); ctx->ring_k2++; }
     if (d_Lroot_out) {
         CAFE_CK(ctx, cudaMemcpy2DAsync(d_Lroot_out, (size_t)ctx->R * sizeof(double), Lroot,
                                        (size_t)ctx->Vp * sizeof(double), (size_t)ctx->R * sizeof(double), ctx->F,

@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "cafe_gpu_build_matrices", "cafe_gpu_num_keys", "cafe_gpu_get_matrix", "cafe_gpu_score", "cafe_gpu_objective",
     "cafe_gpu_objective_device", "cafe_gpu_family_results", "cafe_gpu_family_likelihoods",
     "cafe_gpu_conditional_distribution", "cafe_gpu_pvalues", "cafe_gpu_launch_count",
-    "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_last_kernel_ms", "cafe_gpu_score_flops",
+    "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_timing_collect", "cafe_gpu_score_flops",
 ]
 
 
@@ -67,7 +67,7 @@ def load_library():
     L.cafe_gpu_launch_count.argtypes = [vp]
     L.cafe_gpu_reset_launch_count.argtypes = [vp]
     L.cafe_gpu_enable_timing.argtypes = [vp, C.c_int]
-    L.cafe_gpu_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.cafe_gpu_timing_collect.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
     L.cafe_gpu_score_flops.restype = C.c_double
     L.cafe_gpu_score_flops.argtypes = [vp]
     return L
@@ -231,11 +231,12 @@ class CafeGpu:
     def enable_timing(self, on=True):
         self._ck(self.L.cafe_gpu_enable_timing(self.h, 1 if on else 0), "enable_timing")
 
-    def last_kernel_ms(self):
-        a = C.c_float()
-        b = C.c_float()
-        self._ck(self.L.cafe_gpu_last_kernel_ms(self.h, C.byref(a), C.byref(b)), "last_kernel_ms")
-        return a.value, b.value
+    def timing_collect(self, cap=256):
+        k1 = np.zeros(cap, dtype=np.float32)
+        k2 = np.zeros(cap, dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        n = self._ck(self.L.cafe_gpu_timing_collect(self.h, k1.ctypes.data_as(fp), k2.ctypes.data_as(fp), cap), "timing_collect")
+        return k1[:n].copy(), k2[:n].copy()
 
     def score_flops(self):
         return float(self.L.cafe_gpu_score_flops(self.h))

@@ -152,12 +152,15 @@ int cafe_gpu_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const do
 int cafe_gpu_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
                      double* max_pvalue_out);
 
-/* Bookkeeping for measurement: kernels launched by this context since creation / last reset, and
- * CUDA-event time (ms) of the last K1 and K2 launches (events recorded on the context's stream). */
+/* Bookkeeping for measurement: kernels launched by this context since creation / last reset; and,
+ * when timing is enabled, one CUDA-event quad per objective evaluation recorded on the context's
+ * stream around K1 (matrix build) and K2 (pruning + root reduction).  cafe_gpu_timing_collect
+ * synchronises, writes the per-evaluation device times (ms) of the evaluations recorded since the
+ * last collect (at most `cap`, at most the last 256) and returns how many it wrote. */
 int64_t cafe_gpu_launch_count(const cafe_gpu_ctx* ctx);
 void cafe_gpu_reset_launch_count(cafe_gpu_ctx* ctx);
 int cafe_gpu_enable_timing(cafe_gpu_ctx* ctx, int on);
-int cafe_gpu_last_kernel_ms(cafe_gpu_ctx* ctx, float* k1_ms, float* k2_ms);
+int cafe_gpu_timing_collect(cafe_gpu_ctx* ctx, float* k1_ms, float* k2_ms, int cap);
 /* Algorithmic fp64 flops of one cafe_gpu_score over the current families:
  * sum over internal edges of 2*W*W (2*R*W at the root), leaf edges excluded. */
 double cafe_gpu_score_flops(const cafe_gpu_ctx* ctx);

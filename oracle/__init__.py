@@ -357,3 +357,47 @@ def family_pvalue(tree, mats, counts_by_leaf, cd, leaf_err=None):
     p = lib().orc_family_pvalue(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S, ep, E,
                                 _iptr(lc), _dptr(cd), cd.shape[0], cd.shape[1], _dptr(pv), C.byref(rf))
     return p, pv[:max(0, min(rf.value, cd.shape[0]))]
+
+
+# --------------------------------------------------------------------------- test-side data generation
+
+def random_tree(n_leaves: int, seed: int = 1, max_gap: int = 3) -> str:
+    """Random ultrametric binary tree with integer branch lengths >= 1 (SURVEY.md 8d recipe)."""
+    rng = np.random.RandomState(seed)
+    nodes = [(f"s{i}", 0) for i in range(n_leaves)]
+    h = 0
+    while len(nodes) > 1:
+        h += int(rng.randint(1, max_gap + 1))
+        i, j = sorted(rng.choice(len(nodes), 2, replace=False))
+        a, b = nodes[i], nodes[j]
+        new = (f"({a[0]}:{h - a[1]},{b[0]}:{h - b[1]})", h)
+        nodes = [x for k, x in enumerate(nodes) if k not in (i, j)] + [new]
+    return nodes[0][0]
+
+
+def simulate_families(tree: FlatTree, lam_per_node, mu_per_node, maxfs, n_families, root_sizes, seed=0):
+    """Draw family tables from the model with the ORACLE's matrices (CPU only)."""
+    rng = np.random.RandomState(seed)
+    mats = node_matrices(tree, lam_per_node, mu_per_node, maxfs)
+    cdfs = {id(m): np.cumsum(m, axis=1) for m in mats if m is not None}
+    order, st = [], [tree.root]
+    while st:
+        v = st.pop()
+        order.append(v)
+        if tree.left[v] >= 0:
+            st.append(tree.right[v])
+            st.append(tree.left[v])
+    sizes = np.zeros((n_families, tree.n_nodes), dtype=np.int64)
+    sizes[:, tree.root] = rng.choice(root_sizes, size=n_families)
+    for v in order:
+        if v == tree.root:
+            continue
+        cdf = cdfs[id(mats[v])]
+        u = rng.random_sample(n_families)
+        par = sizes[:, tree.parent[v]]
+        child = np.empty(n_families, dtype=np.int64)
+        for p in np.unique(par):
+            idx = np.where(par == p)[0]
+            child[idx] = np.searchsorted(cdf[p], u[idx], side="left")
+        sizes[:, v] = np.minimum(child, maxfs)
+    return sizes[:, 0::2].astype(np.int32)

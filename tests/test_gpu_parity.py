@@ -44,7 +44,8 @@ def test_k1_matrix_vs_oracle(t, lam, mu, maxfs):
     assert M.shape == ref.shape
     big = ref > 1e-300
     assert rel_err(M[big], ref[big]).max() <= TOL_MATRIX
-    assert np.abs(M[~big] - ref[~big]).max() <= 1e-300
+    if (~big).any():
+        assert np.abs(M[~big] - ref[~big]).max() <= 1e-300
     g.close()
 
 
@@ -74,7 +75,8 @@ def check_problem(p, expect_zero=False):
         assert np.abs(lp - o["logpost"]).max() <= TOL_LOGPOST
     big = o["L"] > 1e-290
     assert rel_err(L[big], o["L"][big]).max() <= TOL_L
-    assert np.abs(L[~big] - o["L"][~big]).max() <= 1e-290
+    if (~big).any():
+        assert np.abs(L[~big] - o["L"][~big]).max() <= 1e-290
     assert rel_err(ml, o["maxlik"], 1e-290).max() <= TOL_L
     # argmax may legitimately differ only where two root sizes tie to within rounding
     diff = am != o["argmax"]

@@ -11,44 +11,8 @@ from cafe_b200 import host as chost
 EXAMPLE_TREE = "(((chimp:6,human:6):81,(mouse:17,rat:17):70):6,dog:93)"
 
 
-def random_tree(n_leaves: int, seed: int = 1, max_gap: int = 3) -> str:
-    """Random ultrametric binary tree with integer branch lengths >= 1 (SURVEY.md §8d recipe):
-    coalescent-style merging, inter-merge gaps uniform in {1..max_gap}."""
-    rng = np.random.RandomState(seed)
-    nodes = [(f"s{i}", 0) for i in range(n_leaves)]  # (newick, height)
-    h = 0
-    while len(nodes) > 1:
-        h += int(rng.randint(1, max_gap + 1))
-        i, j = sorted(rng.choice(len(nodes), 2, replace=False))
-        a, b = nodes[i], nodes[j]
-        new = (f"({a[0]}:{h - a[1]},{b[0]}:{h - b[1]})", h)
-        nodes = [x for k, x in enumerate(nodes) if k not in (i, j)] + [new]
-    return nodes[0][0]
-
-
-def simulate_families(tree, lam_per_node, mu_per_node, maxfs, n_families, root_sizes, seed=0):
-    """Draw family tables from the model with the ORACLE's matrices (test-side data generation)."""
-    rng = np.random.RandomState(seed)
-    mats = oracle.node_matrices(tree, lam_per_node, mu_per_node, maxfs)
-    cdfs = {id(m): np.cumsum(m, axis=1) for m in mats if m is not None}
-    order = []
-    st = [tree.root]
-    while st:
-        v = st.pop()
-        order.append(v)
-        if tree.left[v] >= 0:
-            st.append(tree.right[v])
-            st.append(tree.left[v])
-    sizes = np.zeros((n_families, tree.n_nodes), dtype=np.int64)
-    sizes[:, tree.root] = rng.choice(root_sizes, size=n_families)
-    for v in order:
-        if v == tree.root:
-            continue
-        cdf = cdfs[id(mats[v])]
-        u = rng.random_sample(n_families)
-        rows = cdf[sizes[:, tree.parent[v]]]
-        sizes[:, v] = np.minimum((rows < u[:, None]).sum(axis=1), maxfs)
-    return sizes[:, 0::2].astype(np.int32)
+random_tree = oracle.random_tree
+simulate_families = oracle.simulate_families
 
 
 class Problem:
