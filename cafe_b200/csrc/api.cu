@@ -61,6 +61,7 @@ void cafe_gpu_destroy(cafe_gpu_ctx* ctx) {
     cudaFree(ctx->d_logpost); cudaFree(ctx->d_maxlik); cudaFree(ctx->d_argmax); cudaFree(ctx->d_score);
     cudaFreeHost(ctx->h_score);
     free_err_models(ctx);
+    fused_release(ctx);
     for (cudaEvent_t e : ctx->ring) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

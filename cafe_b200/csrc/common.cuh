@@ -133,6 +133,8 @@ struct cafe_gpu_ctx {
     double* h_score = nullptr;    // pinned [2]
     bool results_valid = false;
 
+    void* fused_state = nullptr;  // prune_fused.cu private state (device schedule, scratch)
+
     // bookkeeping
     int64_t launches = 0;
     bool timing = false;
@@ -148,6 +150,9 @@ int launch_bd_matrices(cafe_gpu_ctx* ctx);                              // bd_ma
 int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out /*nullable*/);  // prune.cu       (K2)
 int launch_score_reduce(cafe_gpu_ctx* ctx, double* d_out2);             // reduce.cu      (K3)
 int build_schedule(cafe_gpu_ctx* ctx);                                  // prune.cu (host)
+bool fused_supported(const cafe_gpu_ctx* ctx);                          // prune_fused.cu
+int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out);         // prune_fused.cu (K2, fused persistent kernel)
+void fused_release(cafe_gpu_ctx* ctx);
 int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed,
                                  double* cd_out);                       // conddist.cu    (K4)
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out);  // pvalue.cu (K5)

@@ -14,6 +14,7 @@
 // on the fp64 tensor pipe (DMMA.8x8x4); leaf edges are gathers fused into the epilogue together with
 // the child product.
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 
 #include "common.cuh"
@@ -299,20 +300,28 @@ int launch_prune_ops(cafe_gpu_ctx* ctx, const int* d_counts_override, int F, int
 
 int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     if (ctx->timing) CAFE_CK(ctx, cudaEventRecord(ctx->quad(ctx->ring_k2)[2], ctx->stream));
-    int root_slot = -1;
-    int rc = launch_prune_ops(ctx, nullptr, ctx->F, ctx->F_pad, nullptr, ctx->root_min, ctx->R, &root_slot);
-    if (rc) return rc;
-    const double* Lroot = ctx->d_vec + (size_t)root_slot * ctx->F_pad * ctx->Vp;
-    const int warps_per_block = 8;
-    k_root_posterior<<<(ctx->F + warps_per_block - 1) / warps_per_block, 256, 0, ctx->stream>>>(
-        Lroot, ctx->Vp, ctx->F, ctx->R, ctx->d_logprior, ctx->d_logpost, ctx->d_maxlik, ctx->d_argmax);
-    ctx->launches++;
-    if (ctx->timing) { CAFE_CK(ctx, cudaEventRecord(ctx->quad(ctx->ring_k2)[3], ctx->stream)); ctx->ring_k2++; }
-    if (d_Lroot_out) {
-        CAFE_CK(ctx, cudaMemcpy2DAsync(d_Lroot_out, (size_t)ctx->R * sizeof(double), Lroot,
-                                       (size_t)ctx->Vp * sizeof(double), (size_t)ctx->R * sizeof(double), ctx->F,
-                                       cudaMemcpyDeviceToDevice, ctx->stream));
+    static const bool no_fused = std::getenv("CAFE_GPU_NO_FUSED") != nullptr;  // A/B switch for tests and profiling
+    if (!no_fused && fused_supported(ctx)) {
+        // fused persistent kernel: whole tree + root reduction in one launch
+        int rc = launch_prune_fused(ctx, d_Lroot_out);
+        if (rc) return rc;
+    } else {
+        // per-node kernels (also the path for per-family column windows, see pvalue.cu / conddist.cu)
+        int root_slot = -1;
+        int rc = launch_prune_ops(ctx, nullptr, ctx->F, ctx->F_pad, nullptr, ctx->root_min, ctx->R, &root_slot);
+        if (rc) return rc;
+        const double* Lroot = ctx->d_vec + (size_t)root_slot * ctx->F_pad * ctx->Vp;
+        const int warps_per_block = 8;
+        k_root_posterior<<<(ctx->F + warps_per_block - 1) / warps_per_block, 256, 0, ctx->stream>>>(
+            Lroot, ctx->Vp, ctx->F, ctx->R, ctx->d_logprior, ctx->d_logpost, ctx->d_maxlik, ctx->d_argmax);
+        ctx->launches++;
+        if (d_Lroot_out) {
+            CAFE_CK(ctx, cudaMemcpy2DAsync(d_Lroot_out, (size_t)ctx->R * sizeof(double), Lroot,
+                                           (size_t)ctx->Vp * sizeof(double), (size_t)ctx->R * sizeof(double), ctx->F,
+                                           cudaMemcpyDeviceToDevice, ctx->stream));
+        }
     }
+    if (ctx->timing) { CAFE_CK(ctx, cudaEventRecord(ctx->quad(ctx->ring_k2)[3], ctx->stream)); ctx->ring_k2++; }
     CAFE_CK(ctx, cudaGetLastError());
     return CAFE_GPU_OK;
 }
