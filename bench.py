@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -67,14 +67,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        return len(self.lines)
+
+    def stop(self, lo=0, hi=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[lo:hi]:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -221,7 +223,9 @@ def run_ours(args, rank, local_rank, world):
     mu_node = np.full(n, -1.0)
 
     g = cgpu.CafeGpu(local_rank)
-    stream = torch.cuda.current_stream()
+    # everything (our kernels, the NCCL collective, the timing events) runs on one explicit torch stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     g.set_stream(stream.cuda_stream)
     g.set_tree(tree.left, tree.right, tree.branchlength)
     g.set_ranges(*ranges)
@@ -239,6 +243,9 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     # ---- warm-up ----
     for k in range(args.warmup):
         s, z = step_device(k)
@@ -248,21 +255,24 @@ def run_ours(args, rank, local_rank, world):
     # ---- device-timed region: K steps, inputs resident in HBM ----
     g.enable_timing(True)
     g.reset_launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    if rank == 0:  # wait for the first nvidia-smi sample so that the timed region is covered
+        t_wait = time.time()
+        while sampler.mark() == 0 and time.time() - t_wait < 3.0:
+            time.sleep(0.01)
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    mark0 = sampler.mark()
     e0.record(stream)
     for k in range(args.steps):
         s, z = step_device(args.warmup + k)
     e1.record(stream)
     barrier()
+    mark1 = sampler.mark() + 1
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(max(0, mark0 - 1), mark1) if rank == 0 else None
     launches = g.launch_count() + (args.steps if world > 1 else 0)  # + one NCCL all-gather per step
     k1_ms, k2_ms = g.timing_collect()
     g.enable_timing(False)
@@ -372,7 +382,7 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=1500)

@@ -202,6 +202,46 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
 }
 
 // ================================ DMMA consumers (8 warps) ================================
+// One k4-step of the warp tile: 4 B fragments, then per 8-family block one A fragment and 4 DMMAs.
+// No predicates inside: MBV is a compile-time count, so the DMMA stream is straight-line code.
+template <int MBV>
+__device__ __forceinline__ void kstep(double (&acc)[MB][NB][2], const unsigned char* sA, const unsigned char* sB, int off) {
+    double b[NB];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) b[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + off);
+#pragma unroll
+    for (int mb = 0; mb < MBV; ++mb) {
+        const double a = *reinterpret_cast<const double*>(sA + mb * 1024 + off);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], a, b[nb]);
+    }
+}
+
+// K loop of one N pass: consume n_kblocks ring stages.
+template <int MBV>
+__device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned char* stage_base, SharedCtl* ctl, uint32_t& stage,
+                                             uint32_t& phase, int n_kblocks, int tail_steps, int warp, int lane, int pg, int q,
+                                             bool warp_has_columns) {
+    const int off0 = pg * 128 + ((q & 1) << 3);
+    const int hi = q >> 1;
+    for (int kb = 0; kb < n_kblocks; ++kb) {
+        mbar_wait(&ctl->full[stage], phase);
+        const unsigned char* sA = stage_base + stage * STAGE_BYTES;
+        const unsigned char* sB = sA + A_BYTES + warp * 32 * 128;
+        if (warp_has_columns) {
+            if (kb + 1 < n_kblocks || tail_steps == 4) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) kstep<MBV>(acc, sA, sB, off0 + (((2 * kk + hi) ^ pg) << 4));
+            } else {
+                for (int kk = 0; kk < tail_steps; ++kk) kstep<MBV>(acc, sA, sB, off0 + (((2 * kk + hi) ^ pg) << 4));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[stage]);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+    }
+}
+
 __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* stage_base, SharedCtl* ctl) {
     const TilePlan plan(P);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -211,10 +251,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
     const size_t half_stride = (size_t)P.n_slots * HM * P.Vp;  // doubles per half-tile scratch
     double* my_scratch = P.scratch + (size_t)blockIdx.x * 2 * half_stride;
     const int n_kblocks = (P.W + BK - 1) / BK;
-    // byte offsets of this lane's fragment element inside an 8-row block for the 4 k4-steps of a stage
-    int frag_off[4];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) frag_off[kk] = pg * 128 + (((2 * kk + (q >> 1)) ^ pg) << 4) + ((q & 1) << 3);
+    const int tail_steps = ((P.W - (n_kblocks - 1) * BK) + 3) >> 2;  // k4-steps of the last K block (1..4)
 
     uint32_t stage = 0, phase = 0;
     int ops_done_base = 0;
@@ -232,8 +269,8 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
 
                 if (op.kind == 0) {
                     // ---- both children are leaves: product of two gathered columns, warp per family ----
-                    const double* MTa = P.MT + (size_t)op.key_a * P.Sp * P.Sp;
-                    const double* MTb = P.MT + (size_t)op.key_b * P.Sp * P.Sp;
+                    const double* __restrict__ MTa = P.MT + (size_t)op.key_a * P.Sp * P.Sp;
+                    const double* __restrict__ MTb = P.MT + (size_t)op.key_b * P.Sp * P.Sp;
                     const LeafErr Ea = P.leaf_err[op.leaf_a], Eb = P.leaf_err[op.leaf_b];
                     for (int row = warp; row < mb_valid * 8; row += N_CONSUMER_WARPS) {
                         const int f = f0 + row;
@@ -241,15 +278,28 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         if (f < P.F) {
                             const int ca = P.counts[(size_t)op.leaf_a * P.F_pad + f], cb = P.counts[(size_t)op.leaf_b * P.F_pad + f];
                             double ml = -1.0, mp = -INFINITY; int am = 0x7fffffff;
-                            for (int i = lane; i < P.Vp; i += 32) {
-                                double v = 0.0;
-                                if (i < nrows) v = leaf_factor(MTa, Ea, P.Sp, ca, P.W - 1, r0 + i) * leaf_factor(MTb, Eb, P.Sp, cb, P.W - 1, r0 + i);
-                                if (!op.is_root) o[i] = v;
-                                else if (i < nrows) {
-                                    if (P.Lroot_out) P.Lroot_out[(size_t)f * P.R + i] = v;
-                                    if (v > ml) { ml = v; am = i; }
-                                    const double x = log(v) + P.logprior[i];
-                                    if (x > mp) mp = x;
+                            for (int ib = 0; ib < P.Vp; ib += 256) {  // 8 independent column groups per batch
+                                double va[8], vb[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    const int i = ib + u * 32 + lane;
+                                    va[u] = 0.0; vb[u] = 0.0;
+                                    if (i < nrows) {
+                                        va[u] = leaf_factor(MTa, Ea, P.Sp, ca, P.W - 1, r0 + i);
+                                        vb[u] = leaf_factor(MTb, Eb, P.Sp, cb, P.W - 1, r0 + i);
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    const int i = ib + u * 32 + lane;
+                                    const double v = va[u] * vb[u];
+                                    if (!op.is_root) { if (i < P.Vp) o[i] = v; }
+                                    else if (i < nrows) {
+                                        if (P.Lroot_out) P.Lroot_out[(size_t)f * P.R + i] = v;
+                                        if (v > ml) { ml = v; am = i; }
+                                        const double x = log(v) + P.logprior[i];
+                                        if (x > mp) mp = x;
+                                    }
                                 }
                             }
                             if (op.is_root) {  // two-leaf tree: the root itself is a leaf pair
@@ -268,71 +318,102 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     }
                 } else {
                     // ---- GEMM over the internal child, the whole vector in passes of 256 sizes ----
-                    const double* MTl = P.MT + (size_t)(op.other_kind == 1 ? op.key_a : 0) * P.Sp * P.Sp;
+                    const double* __restrict__ MTl = P.MT + (size_t)(op.other_kind == 1 ? op.key_a : 0) * P.Sp * P.Sp;
                     LeafErr El{nullptr, nullptr, nullptr};
                     if (op.other_kind == 1) El = P.leaf_err[op.leaf_a];
                     const bool reduce_now = op.is_root && op.other_kind != 0;
                     if (reduce_now && threadIdx.x < HM) { ctl->run_ml[threadIdx.x] = -1.0; ctl->run_mp[threadIdx.x] = -INFINITY; ctl->run_am[threadIdx.x] = 0x7fffffff; }
+                    // observed sizes of the leaf sibling for this lane's 8 family rows (latency hidden by the K loop)
+                    int cnt[MB];
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) {
+                        const int f = f0 + mb * 8 + pg;
+                        cnt[mb] = (op.other_kind == 1 && mb < mb_valid && f < P.F) ? __ldg(P.counts + (size_t)op.leaf_a * P.F_pad + f) : 0;
+                    }
+                    const bool rows_full = f0 + mb_valid * 8 <= P.F;
 
                     for (int ch = 0; ch < n_chunks; ++ch) {
-                        const int n0 = ch * TN + warp * 32;   // first output size of this warp
-                        int nb_valid = (nrows - n0 + 7) >> 3; // n-blocks of this warp that exist
-                        nb_valid = nb_valid < 0 ? 0 : (nb_valid > NB ? NB : nb_valid);
+                        const int n0 = ch * TN + warp * 32;  // first output size of this warp
+                        const bool warp_has_columns = n0 < nrows;
                         double acc[MB][NB][2];
 #pragma unroll
                         for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
                             for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
 
-                        for (int kb = 0; kb < n_kblocks; ++kb) {
-                            mbar_wait(&ctl->full[stage], phase);
-                            const unsigned char* sA = stage_base + stage * STAGE_BYTES;
-                            const unsigned char* sB = sA + A_BYTES + warp * 32 * 128;
-                            const int ksteps = min(4, (P.W - kb * BK + 3) >> 2);
+                        switch (mb_valid) {
+                            case 8: gemm_kblocks<8>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
+                            case 7: gemm_kblocks<7>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
+                            case 6: gemm_kblocks<6>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
+                            case 5: gemm_kblocks<5>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
+                            case 4: gemm_kblocks<4>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
+                            case 3: gemm_kblocks<3>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
+                            case 2: gemm_kblocks<2>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
+                            default: gemm_kblocks<1>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
+                        }
+
+                        // ---------------- epilogue of this pass ----------------
+                        const bool fast = rows_full && (n0 + 32 <= nrows) && El.rowptr == nullptr;
+                        if (!reduce_now && fast) {
+                            // common case: every element of the warp tile exists; sibling factors are fetched in
+                            // batches of 16 independent loads (two 8-family blocks) before they are consumed
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                if (kk < ksteps) {
-                                    double b[NB];
+                            for (int mb = 0; mb < MB; mb += 2) {
+                                if (mb < mb_valid) {
+                                    double fac[2][NB][2];
 #pragma unroll
-                                    for (int nb = 0; nb < NB; ++nb) b[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + frag_off[kk]);
+                                    for (int u = 0; u < 2; ++u) {
+                                        const int row = (mb + u) * 8 + pg;
+                                        const double* src = (op.other_kind == 1) ? MTl + (size_t)cnt[mb + u] * P.Sp + r0 + n0
+                                                                                 : out + (size_t)row * P.Vp + n0;
 #pragma unroll
-                                    for (int mb = 0; mb < MB; ++mb) {
-                                        if (mb < mb_valid) {
-                                            const double a = *reinterpret_cast<const double*>(sA + mb * 1024 + frag_off[kk]);
+                                        for (int nb = 0; nb < NB; ++nb) {
+                                            fac[u][nb][0] = 1.0; fac[u][nb][1] = 1.0;
+                                            if (op.other_kind != 0 && mb + u < mb_valid) {
+                                                fac[u][nb][0] = src[nb * 8 + pc0];
+                                                fac[u][nb][1] = src[nb * 8 + pc1];
+                                            }
+                                        }
+                                    }
 #pragma unroll
-                                            for (int nb = 0; nb < NB; ++nb)
-                                                if (nb < nb_valid) dmma_884(acc[mb][nb][0], acc[mb][nb][1], a, b[nb]);
+                                    for (int u = 0; u < 2; ++u) {
+                                        if (mb + u < mb_valid) {
+                                            double* o = out + (size_t)((mb + u) * 8 + pg) * P.Vp + n0;
+#pragma unroll
+                                            for (int nb = 0; nb < NB; ++nb) {
+                                                o[nb * 8 + pc0] = acc[mb + u][nb][0] * fac[u][nb][0];
+                                                o[nb * 8 + pc1] = acc[mb + u][nb][1] * fac[u][nb][1];
+                                            }
                                         }
                                     }
                                 }
                             }
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&ctl->empty[stage]);
-                            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
-                        }
-
-                        // ---------------- epilogue of this pass ----------------
-                        if (!reduce_now) {  // store the vector (or the root's first partial product)
+                        } else if (!reduce_now) {  // edge tiles / error-model leaves: fully guarded, loads still batched
 #pragma unroll
                             for (int mb = 0; mb < MB; ++mb) {
                                 if (mb < mb_valid) {
                                     const int row = mb * 8 + pg, f = f0 + row;
-                                    const int cnt = (op.other_kind == 1 && f < P.F) ? P.counts[(size_t)op.leaf_a * P.F_pad + f] : 0;
                                     double* o = out + (size_t)row * P.Vp;
+                                    double fac[NB][2];
 #pragma unroll
                                     for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
                                         for (int hh = 0; hh < 2; ++hh) {
                                             const int i = n0 + nb * 8 + (hh ? pc1 : pc0);
-                                            if (i < P.Vp) {
-                                                double v = 0.0;
-                                                if (i < nrows && f < P.F) {
-                                                    v = acc[mb][nb][hh];
-                                                    if (op.other_kind == 1) v *= leaf_factor(MTl, El, P.Sp, cnt, P.W - 1, r0 + i);
-                                                    else if (op.other_kind == 2) v *= o[i];
-                                                }
-                                                o[i] = v;
+                                            fac[nb][hh] = 0.0;
+                                            if (i < nrows && f < P.F) {
+                                                fac[nb][hh] = 1.0;
+                                                if (op.other_kind == 1) fac[nb][hh] = leaf_factor(MTl, El, P.Sp, cnt[mb], P.W - 1, r0 + i);
+                                                else if (op.other_kind == 2) fac[nb][hh] = o[i];
                                             }
+                                        }
+                                    }
+#pragma unroll
+                                    for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+                                        for (int hh = 0; hh < 2; ++hh) {
+                                            const int i = n0 + nb * 8 + (hh ? pc1 : pc0);
+                                            if (i < P.Vp) o[i] = (i < nrows && f < P.F) ? acc[mb][nb][hh] * fac[nb][hh] : 0.0;
                                         }
                                     }
                                 }
@@ -344,17 +425,24 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                                 double ml = -1.0, mp = -INFINITY; int am = 0x7fffffff;
                                 const int row = mb * 8 + pg, f = f0 + row;
                                 if (mb < mb_valid && f < P.F) {
-                                    const int cnt = (op.other_kind == 1) ? P.counts[(size_t)op.leaf_a * P.F_pad + f] : 0;
                                     const double* o = out + (size_t)row * P.Vp;
+                                    double fac[NB][2];
+#pragma unroll
+                                    for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+                                        for (int hh = 0; hh < 2; ++hh) {
+                                            const int i = n0 + nb * 8 + (hh ? pc1 : pc0);
+                                            fac[nb][hh] = 0.0;
+                                            if (i < nrows) fac[nb][hh] = (op.other_kind == 1) ? leaf_factor(MTl, El, P.Sp, cnt[mb], P.W - 1, r0 + i) : o[i];
+                                        }
+                                    }
 #pragma unroll
                                     for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
                                         for (int hh = 0; hh < 2; ++hh) {
                                             const int i = n0 + nb * 8 + (hh ? pc1 : pc0);
                                             if (i < nrows) {
-                                                double v = acc[mb][nb][hh];
-                                                if (op.other_kind == 1) v *= leaf_factor(MTl, El, P.Sp, cnt, P.W - 1, r0 + i);
-                                                else v *= o[i];
+                                                const double v = acc[mb][nb][hh] * fac[nb][hh];
                                                 if (P.Lroot_out) P.Lroot_out[(size_t)f * P.R + i] = v;
                                                 if (v > ml || (v == ml && i < am)) { ml = v; am = i; }
                                                 const double x = log(v) + P.logprior[i];
