@@ -29,22 +29,31 @@
 // the fp64 pipe.
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fused {
 
-constexpr int HM = 64;            // families per half-tile
-constexpr int TN = 256;           // output sizes per N pass
+// Three CTAs per SM (3 DMMA warps per sub-partition: one warp alone reaches only ~73 % of the DMMA issue rate,
+// three reach ~97 %, tools/fp64_peak.cu): while one is in an epilogue (sibling-factor gathers from L2, stores) the other keeps the
+// DMMA pipe busy.  Each CTA: 1 DMMA warpgroup (4 warps, one per SM sub-partition) + 1 producer warpgroup.
+constexpr int HM = 32;            // families per half-tile
+constexpr int TN = 128;           // output sizes per N pass
 constexpr int BK = 16;            // sizes per K block (16 doubles = 128 B = one swizzle row)
-constexpr int NSTAGE = 4;
-constexpr int A_BYTES = HM * 128;   // 8 KB
-constexpr int B_BYTES = TN * 128;   // 32 KB
+constexpr int NSTAGE = 3;
+constexpr int A_BYTES = HM * 128;   // 4 KB
+constexpr int B_BYTES = TN * 128;   // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int N_CONSUMER_WARPS = 8;
-constexpr int THREADS = (N_CONSUMER_WARPS + 4) * 32;  // 2 consumer warpgroups + 1 producer warpgroup (only its first lane works)
-constexpr int REGS_PRODUCER = 40, REGS_CONSUMER = 232;  // setmaxnreg split of the 168 x 384 launch allocation
-constexpr int MB = HM / 8;        // 8 m-blocks per half-tile
+constexpr int N_CONSUMER_WARPS = 4;
+constexpr int THREADS = (N_CONSUMER_WARPS + 4) * 32;  // DMMA warpgroup + producer warpgroup (only its first lane works)
+constexpr int CTAS_PER_SM = 3;
+// setmaxnreg split of the launch allocation (80 regs x 256 threads): 4*136 + 4*24 = 8*80
+constexpr int REGS_PRODUCER = 24, REGS_CONSUMER = 136;
+constexpr int MB = HM / 8;        // 4 m-blocks per half-tile
 constexpr int NB = 4;             // n-blocks per warp (32 sizes)
+constexpr int WCOLS = NB * 8;     // sizes per warp
 constexpr int MAX_SLOTS = 16;
 
 struct Op {              // one node of the post-order schedule
@@ -80,6 +89,7 @@ struct Params {
     double* maxlik;
     int* argmax;
     double* Lroot_out;           // nullable, [F][R]
+    long long* trace;            // nullable debug trace of CTA 0: [event][warp][4] clock64 stamps (CAFE_GPU_TRACE)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -227,7 +237,7 @@ __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned 
     for (int kb = 0; kb < n_kblocks; ++kb) {
         mbar_wait(&ctl->full[stage], phase);
         const unsigned char* sA = stage_base + stage * STAGE_BYTES;
-        const unsigned char* sB = sA + A_BYTES + warp * 32 * 128;
+        const unsigned char* sB = sA + A_BYTES + warp * WCOLS * 128;
         if (warp_has_columns) {
             if (kb + 1 < n_kblocks || tail_steps == 4) {
 #pragma unroll
@@ -266,6 +276,9 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                 plan.half(pair, h, mb_valid, f0);
                 if (mb_valid == 0) continue;
                 double* out = my_scratch + h * half_stride + (size_t)op.out_slot * HM * P.Vp;
+                const bool tracing = P.trace != nullptr && blockIdx.x == 0 && lane == 0;
+                long long* tr = tracing ? P.trace + ((size_t)((pair * P.n_ops + oi) * 2 + h) * N_CONSUMER_WARPS + warp) * 4 : nullptr;
+                if (tracing) { tr[0] = clock64(); tr[1] = tr[0]; }
 
                 if (op.kind == 0) {
                     // ---- both children are leaves: product of two gathered columns, warp per family ----
@@ -330,10 +343,9 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         const int f = f0 + mb * 8 + pg;
                         cnt[mb] = (op.other_kind == 1 && mb < mb_valid && f < P.F) ? __ldg(P.counts + (size_t)op.leaf_a * P.F_pad + f) : 0;
                     }
-                    const bool rows_full = f0 + mb_valid * 8 <= P.F;
 
                     for (int ch = 0; ch < n_chunks; ++ch) {
-                        const int n0 = ch * TN + warp * 32;  // first output size of this warp
+                        const int n0 = ch * TN + warp * WCOLS;  // first output size of this warp
                         const bool warp_has_columns = n0 < nrows;
                         double acc[MB][NB][2];
 #pragma unroll
@@ -342,18 +354,17 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                             for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
 
                         switch (mb_valid) {
-                            case 8: gemm_kblocks<8>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
-                            case 7: gemm_kblocks<7>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
-                            case 6: gemm_kblocks<6>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
-                            case 5: gemm_kblocks<5>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
                             case 4: gemm_kblocks<4>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
                             case 3: gemm_kblocks<3>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
                             case 2: gemm_kblocks<2>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
                             default: gemm_kblocks<1>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, warp, lane, pg, q, warp_has_columns); break;
                         }
 
+                        if (tracing) tr[1] = clock64();
                         // ---------------- epilogue of this pass ----------------
-                        const bool fast = rows_full && (n0 + 32 <= nrows) && El.rowptr == nullptr;
+                        // Unguarded path: sizes in [nrows, Vp) come out as exact zeros by themselves (matrix rows/columns
+                        // beyond S are zero padding, stored partials there are zero), rows beyond F are private garbage.
+                        const bool fast = (n0 + WCOLS <= P.Vp) && El.rowptr == nullptr;
                         if (!reduce_now && fast) {
                             // common case: every element of the warp tile exists; sibling factors are fetched in
                             // batches of 16 independent loads (two 8-family blocks) before they are consumed
@@ -482,8 +493,10 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     }
                 }
                 // publish: this half-tile finished op `oi` (its vector may be streamed by TMA from now on)
+                if (tracing) tr[2] = clock64();
                 fence_proxy_async();
                 consumer_bar();
+                if (tracing) tr[3] = clock64();
                 if (threadIdx.x == 0) { __threadfence_block(); ctl->done[h] = ops_done_base + oi + 1; }
             }
         }
@@ -491,7 +504,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS, CTAS_PER_SM)
 k_prune_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window
@@ -597,7 +610,7 @@ int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
 
     // ---- geometry ----
     const int n_mblocks = (ctx->F + 7) / 8;
-    const int grid = std::max(1, std::min(ctx->sm_count, (n_mblocks + 2 * MB - 1) / (2 * MB)));
+    const int grid = std::max(1, std::min(CTAS_PER_SM * ctx->sm_count, (n_mblocks + 2 * MB - 1) / (2 * MB)));
     const size_t scratch_doubles = (size_t)grid * 2 * ctx->n_slots * HM * ctx->Vp;
     if (scratch_doubles > st.scratch_cap) {
         cudaFree(st.d_scratch); st.d_scratch = nullptr;
@@ -638,8 +651,32 @@ int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
         CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         st.attr_set = true;
     }
+    const char* trace_path = std::getenv("CAFE_GPU_TRACE");
+    long long* d_trace = nullptr;
+    size_t trace_n = 0;
+    if (trace_path) {
+        const int pairs_max = ((n_mblocks + grid - 1) / grid + 2 * MB - 1) / (2 * MB) + 1;
+        trace_n = (size_t)pairs_max * ops.size() * 2 * N_CONSUMER_WARPS * 4;
+        CAFE_CK(ctx, cudaMalloc(&d_trace, trace_n * sizeof(long long)));
+        CAFE_CK(ctx, cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), ctx->stream));
+        P.trace = d_trace;
+    }
     k_prune_fused<<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
     ctx->launches++;
     CAFE_CK(ctx, cudaGetLastError());
+    if (trace_path) {  // debug only: synchronous dump "event warp t0 t_kloop_end t_epilogue_end t_barrier_end kind"
+        std::vector<long long> h(trace_n);
+        CAFE_CK(ctx, cudaMemcpyAsync(h.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_trace);
+        if (FILE* fp = std::fopen(trace_path, "w")) {
+            for (size_t e = 0; e < trace_n / (N_CONSUMER_WARPS * 4); ++e)
+                for (int w = 0; w < N_CONSUMER_WARPS; ++w) {
+                    const long long* t = &h[(e * N_CONSUMER_WARPS + w) * 4];
+                    if (t[0]) std::fprintf(fp, "%zu %d %lld %lld %lld %lld %d\n", e, w, t[0], t[1], t[2], t[3], ops[(e / 2) % ops.size()].kind);
+                }
+            std::fclose(fp);
+        }
+    }
     return CAFE_GPU_OK;
 }

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) k_dfma(double* out, int iters, double a, 
 }
 
 template <int NACC>
-__global__ void __launch_bounds__(256) k_dmma(double* out, int iters, double a, double b) {
+__global__ void __launch_bounds__(512) k_dmma(double* out, int iters, double a, double b) {
     double c0[NACC], c1[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) { c0[i] = threadIdx.x * 1e-3 + i; c1[i] = i; }
@@ -109,6 +109,12 @@ int main() {
             double fl = 2.0 * (iters / 4) * grid * (256.0 * 8 * 8 + 64 * 256.0);
             printf("{\"variant\": \"mix_8dmma_64dfma\", \"warps_per_sm\": %d, \"ms\": %.4f, \"tflops\": %.3f}\n", bps * 8, ms, fl / ms * 1e-9);
         }
+    }
+    // warps per SM sweep for DMMA with 32 independent accumulators (1 warp per SM sub-partition = 4 warps/SM)
+    for (int wps : {4, 8, 12, 16}) {
+        float ms = time_it([&] { k_dmma<32><<<sms, wps * 32>>>(out, iters, 1.0000001, 1e-9); }, 5);
+        double fl = 2.0 * 256 * 32 * iters * (double)wps * sms;
+        printf("{\"variant\": \"dmma884x32_wps\", \"warps_per_sm\": %d, \"ms\": %.4f, \"tflops\": %.3f}\n", wps, ms, fl / ms * 1e-9);
     }
     // single-warp dependent-chain latency of DMMA
     {
