@@ -80,6 +80,7 @@ struct Params {
     int W, R, root_min;
     int Sp, Vp;
     int n_mblocks;               // ceil(F / 8)
+    int counts_in_window;        // every observed size < W (then a one-hot leaf never falls outside the matvec columns)
     const double* MT;            // [D][Sp][Sp] transposed matrices
     const int* counts;           // [n_leaves][F_pad]
     const LeafErr* leaf_err;     // [n_leaves]
@@ -90,6 +91,7 @@ struct Params {
     int* argmax;
     double* Lroot_out;           // nullable, [F][R]
     long long* trace;            // nullable debug trace of CTA 0: [event][warp][4] clock64 stamps (CAFE_GPU_TRACE)
+    long long* cta_times;        // nullable debug: [grid][4] = smid, start ns, end ns, 8-family blocks
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -133,14 +135,19 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(N_CONSUMER_WARPS * 32) : "memory"); }
 
-__device__ __forceinline__ double leaf_factor(const double* __restrict__ MT, const LeafErr& E, int Sp, int count, int colmax, int r) {
-    if (E.rowptr == nullptr) return (count <= colmax) ? MT[(size_t)count * Sp + r] : 0.0;
+// error-model leaf (cafe_tree.c:196-203): sparse combination of matrix columns, ascending true size.  Cold path.
+__device__ __noinline__ double leaf_factor_err(const double* __restrict__ MT, const int* rowptr, const int* col, const double* val,
+                                               int Sp, int count, int colmax, int r) {
     double s = 0.0;
-    for (int k = E.rowptr[count]; k < E.rowptr[count + 1]; ++k) {
-        int j = E.col[k];
-        if (j <= colmax) s = __dadd_rn(s, __dmul_rn(MT[(size_t)j * Sp + r], E.val[k]));
+    for (int k = rowptr[count]; k < rowptr[count + 1]; ++k) {
+        const int j = col[k];
+        if (j <= colmax) s = __dadd_rn(s, __dmul_rn(MT[(size_t)j * Sp + r], val[k]));
     }
     return s;
+}
+__device__ __forceinline__ double leaf_factor(const double* __restrict__ MT, const LeafErr& E, int Sp, int count, int colmax, int r) {
+    if (E.rowptr == nullptr) return (count <= colmax) ? MT[(size_t)count * Sp + r] : 0.0;
+    return leaf_factor_err(MT, E.rowptr, E.col, E.val, Sp, count, colmax, r);
 }
 
 struct SharedCtl {
@@ -285,6 +292,45 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     const double* __restrict__ MTa = P.MT + (size_t)op.key_a * P.Sp * P.Sp;
                     const double* __restrict__ MTb = P.MT + (size_t)op.key_b * P.Sp * P.Sp;
                     const LeafErr Ea = P.leaf_err[op.leaf_a], Eb = P.leaf_err[op.leaf_b];
+                    const bool lp_fast = !op.is_root && Ea.rowptr == nullptr && Eb.rowptr == nullptr && P.counts_in_window;
+                    if (lp_fast) {
+                        // common case (one-hot leaves): two gathered matrix columns per family, two families in flight per
+                        // warp => 32 independent 8-byte loads per lane before the first store
+                        const int n_rows = mb_valid * 8;
+                        for (int row = warp * 2; row < n_rows; row += 2 * N_CONSUMER_WARPS) {
+                            const double* pa[2]; const double* pb[2];
+#pragma unroll
+                            for (int u = 0; u < 2; ++u) {
+                                const int f = min(f0 + row + u, P.F - 1);
+                                const int ca = __ldg(P.counts + (size_t)op.leaf_a * P.F_pad + f), cb = __ldg(P.counts + (size_t)op.leaf_b * P.F_pad + f);
+                                pa[u] = MTa + (size_t)ca * P.Sp + lane;
+                                pb[u] = MTb + (size_t)cb * P.Sp + lane;
+                            }
+                            for (int ib = 0; ib < P.Vp; ib += 256) {
+                                double va[2][8], vb[2][8];
+#pragma unroll
+                                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                                    for (int c8 = 0; c8 < 8; ++c8) {
+                                        const int i = ib + c8 * 32;  // + lane folded into the pointers; Sp >= Vp, zero padded beyond W
+                                        const bool in = i + lane < P.Vp;
+                                        va[u][c8] = in ? __ldg(pa[u] + i) : 0.0;
+                                        vb[u][c8] = in ? __ldg(pb[u] + i) : 0.0;
+                                    }
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    if (row + u < n_rows) {
+                                        double* o = out + (size_t)(row + u) * P.Vp + lane;
+#pragma unroll
+                                        for (int c8 = 0; c8 < 8; ++c8) {
+                                            const int i = ib + c8 * 32;
+                                            if (i + lane < P.Vp) o[i] = va[u][c8] * vb[u][c8];
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    } else
                     for (int row = warp; row < mb_valid * 8; row += N_CONSUMER_WARPS) {
                         const int f = f0 + row;
                         double* o = out + (size_t)row * P.Vp;
@@ -364,7 +410,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         // ---------------- epilogue of this pass ----------------
                         // Unguarded path: sizes in [nrows, Vp) come out as exact zeros by themselves (matrix rows/columns
                         // beyond S are zero padding, stored partials there are zero), rows beyond F are private garbage.
-                        const bool fast = (n0 + WCOLS <= P.Vp) && El.rowptr == nullptr;
+                        const bool fast = (n0 + WCOLS <= P.Vp) && El.rowptr == nullptr && P.counts_in_window;
                         if (!reduce_now && fast) {
                             // common case: every element of the warp tile exists; sibling factors are fetched in
                             // batches of 16 independent loads (two 8-family blocks) before they are consumed
@@ -527,7 +573,17 @@ k_prune_fused(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (threadIdx.x == N_CONSUMER_WARPS * 32) producer_main(&tmA, &tmB, P, stage_base, ctl);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
+        long long t_start = 0;
+        if (P.cta_times && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         consumer_main(P, stage_base, ctl);
+        if (P.cta_times && threadIdx.x == 0) {
+            long long t_end; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const TilePlan plan(P);
+            long long* o = P.cta_times + (size_t)blockIdx.x * 4;
+            o[0] = smid; o[1] = t_start; o[2] = t_end; o[3] = plan.n_mb;
+        }
     }
 }
 
@@ -642,6 +698,7 @@ int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
 
     Params P{};
     P.ops = st.d_ops; P.n_ops = (int)ops.size(); P.n_slots = ctx->n_slots; P.F = ctx->F; P.F_pad = ctx->F_pad;
+    P.counts_in_window = ctx->max_count < ctx->W ? 1 : 0;
     P.W = ctx->W; P.R = ctx->R; P.root_min = ctx->root_min; P.Sp = ctx->Sp; P.Vp = ctx->Vp; P.n_mblocks = n_mblocks;
     P.MT = ctx->d_MT; P.counts = ctx->d_counts; P.leaf_err = st.d_leaf_err; P.logprior = ctx->d_logprior;
     P.scratch = st.d_scratch; P.logpost = ctx->d_logpost; P.maxlik = ctx->d_maxlik; P.argmax = ctx->d_argmax; P.Lroot_out = d_Lroot_out;
@@ -656,10 +713,11 @@ int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     size_t trace_n = 0;
     if (trace_path) {
         const int pairs_max = ((n_mblocks + grid - 1) / grid + 2 * MB - 1) / (2 * MB) + 1;
-        trace_n = (size_t)pairs_max * ops.size() * 2 * N_CONSUMER_WARPS * 4;
+        trace_n = (size_t)pairs_max * ops.size() * 2 * N_CONSUMER_WARPS * 4 + (size_t)grid * 4;
         CAFE_CK(ctx, cudaMalloc(&d_trace, trace_n * sizeof(long long)));
         CAFE_CK(ctx, cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), ctx->stream));
         P.trace = d_trace;
+        P.cta_times = d_trace + trace_n - (size_t)grid * 4;
     }
     k_prune_fused<<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
     ctx->launches++;
@@ -670,7 +728,11 @@ int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
         CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(d_trace);
         if (FILE* fp = std::fopen(trace_path, "w")) {
-            for (size_t e = 0; e < trace_n / (N_CONSUMER_WARPS * 4); ++e)
+            for (int c = 0; c < grid; ++c) {
+                const long long* t = &h[trace_n - (size_t)grid * 4 + (size_t)c * 4];
+                std::fprintf(fp, "cta %d %lld %lld %lld %lld\n", c, t[0], t[1], t[2], t[3]);
+            }
+            for (size_t e = 0; e < (trace_n - (size_t)grid * 4) / (N_CONSUMER_WARPS * 4); ++e)
                 for (int w = 0; w < N_CONSUMER_WARPS; ++w) {
                     const long long* t = &h[(e * N_CONSUMER_WARPS + w) * 4];
                     if (t[0]) std::fprintf(fp, "%zu %d %lld %lld %lld %lld %d\n", e, w, t[0], t[1], t[2], t[3], ops[(e / 2) % ops.size()].kind);

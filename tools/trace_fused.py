@@ -1,7 +1,21 @@
 """Summarise a CAFE_GPU_TRACE dump of the fused K2 kernel (CTA 0): per phase time per (op, half)."""
 import sys, collections
 import numpy as np
-rows = [list(map(int, l.split())) for l in open(sys.argv[1])]
+lines = open(sys.argv[1]).read().split('\n')
+cta = np.array([list(map(int, l.split()[1:])) for l in lines if l.startswith('cta')])
+if len(cta):
+    t0 = cta[:,2].min()
+    dur = (cta[:,3]-cta[:,2])/1e3
+    print("CTAs", len(cta), "duration us: min %.0f mean %.0f max %.0f; kernel span %.0f us" % (dur.min(), dur.mean(), dur.max(), (cta[:,3].max()-t0)/1e3))
+    print("start skew us max", (cta[:,2].max()-t0)/1e3)
+    per_sm = collections.defaultdict(list)
+    for c,(smid,a,b,nmb) in zip(cta[:,0],cta[:,1:]): per_sm[smid].append(((a-t0)/1e3,(b-t0)/1e3,nmb,c))
+    ends = {k: max(x[1] for x in v) for k,v in per_sm.items()}
+    worst = max(ends, key=ends.get); best = min(ends, key=ends.get)
+    print("SM count", len(per_sm), "CTAs per SM", collections.Counter(len(v) for v in per_sm.values()))
+    print("worst SM", worst, sorted(per_sm[worst])); print("best SM", best, sorted(per_sm[best]))
+    print("m-blocks per SM:", collections.Counter(sum(x[2] for x in v) for v in per_sm.values()))
+rows = [list(map(int, l.split())) for l in lines if l and not l.startswith('cta')]
 a = np.array(rows)
 ev, w, t0, t1, t2, t3, kind = a.T
 clk = 1.965e3  # cycles per us
