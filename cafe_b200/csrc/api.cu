@@ -358,7 +358,9 @@ int cafe_gpu_get_matrix(cafe_gpu_ctx* ctx, int node, double* out, int out_dim) {
 }
 
 // ------------------------------------------------------------------------------------------- K2 + K3
-static int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad) {
+}  // extern "C"
+
+int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad) {
     size_t need = (size_t)ctx->n_slots * F_pad * ctx->Vp;
     if (need > ctx->vec_cap) {
         cudaFree(ctx->d_vec); ctx->d_vec = nullptr;
@@ -368,6 +370,8 @@ static int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad) {
     }
     return CAFE_GPU_OK;
 }
+
+extern "C" {
 
 static int check_ready(cafe_gpu_ctx* ctx, const char* who) {
     if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + ": build_matrices first");

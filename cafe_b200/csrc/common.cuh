@@ -150,6 +150,9 @@ int launch_bd_matrices(cafe_gpu_ctx* ctx);                              // bd_ma
 int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out /*nullable*/);  // prune.cu       (K2)
 int launch_score_reduce(cafe_gpu_ctx* ctx, double* d_out2);             // reduce.cu      (K3)
 int build_schedule(cafe_gpu_ctx* ctx);                                  // prune.cu (host)
+int launch_prune_ops(cafe_gpu_ctx* ctx, const int* counts_base, size_t leaf_stride, int F, int F_pad, const int* d_colmax,
+                     int root_r0, int root_rows, bool skip_root, int* root_slot_out);  // prune.cu (per-node kernels)
+int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad);                // api.cu
 bool fused_supported(const cafe_gpu_ctx* ctx);                          // prune_fused.cu
 int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out);         // prune_fused.cu (K2, fused persistent kernel)
 void fused_release(cafe_gpu_ctx* ctx);

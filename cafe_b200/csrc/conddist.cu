@@ -1,5 +1,241 @@
-// conddist.cu — K4 (placeholder until the simulate-and-prune kernels land).
+// conddist.cu — K4: Monte-Carlo conditional distribution.
+//
+// Replaces cafe_conditional_distribution / get_random_probabilities
+// (cafe/conditional_distribution.cpp:10-120) and cafe_tree_random_familysize (cafe/cafe_tree.c:533-569):
+// for every root size s in [root_min, root_max], n_samples simulated families are drawn down the tree
+// (child size = first c with cumsum_{c'<=c} M[parent][c'] >= u, c < maxFamilySize-1), each is pruned with
+// root range {s} and the shrinking column window of conditional_distribution.cpp:29, and the n_samples
+// root likelihoods of every s are sorted ascending.
+//
+// Parallel restatement of the reference's serial loops:
+//   * the reference's running `cumul +=` sums are reproduced as per-row prefix sums computed serially in
+//     the same order (k_row_cdf), so a binary search finds exactly the size the serial scan would;
+//   * trials are independent: the simulation uses the maxFamilySize captured before the loop (:20,:26);
+//     the range.max ratchet is a prefix-min over the trials of one root size (k_ratchet);
+//   * "replay" mode consumes the caller's uniform stream in the reference's order (s, trial, prefix-order
+//     non-root node) and is draw-for-draw comparable with the single-threaded reference; otherwise a
+//     counter-based generator keyed by (seed, s, trial, node) is used.
+#include <cub/device/device_segmented_sort.cuh>
+
+#include <algorithm>
+
 #include "common.cuh"
-int run_conditional_distribution(cafe_gpu_ctx* ctx, int, const double*, uint64_t, double*) {
-    CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "conditional_distribution: not built yet");
+
+namespace {
+
+// prefix sums of every matrix row, in the reference's summation order (cafe_tree.c:549-553)
+__global__ void k_row_cdf(const double* __restrict__ M, double* __restrict__ CDF, int S, int Sp, int D) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = blockIdx.y;
+    if (row >= S || d >= D) return;
+    const double* m = M + ((size_t)d * Sp + row) * Sp;
+    double* c = CDF + ((size_t)d * Sp + row) * Sp;
+    double cumul = 0.0;
+    for (int j = 0; j < S; ++j) { cumul += m[j]; c[j] = cumul; }
+}
+
+__device__ __forceinline__ double counter_uniform(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
+    // splitmix64-style mixing of (seed, root size, trial, node) -> [0,1) with 53 random bits
+    uint64_t x = seed ^ (a * 0x9E3779B97F4A7C15ull) ^ (b * 0xBF58476D1CE4E5B9ull) ^ (c * 0x94D049BB133111EBull);
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x = x ^ (x >> 31);
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// one thread per (root size, trial): walk the tree in prefix order (libtree/tree.c:101-124)
+__global__ void k_simulate(const double* __restrict__ CDF, int Sp, const int* __restrict__ prefix_nodes,
+                           const int* __restrict__ parent, const int* __restrict__ node_key, int n_nonroot, int root,
+                           int s_lo, int n_samples, int Fc, int Fc_pad, int range_max,
+                           const double* __restrict__ uniforms /* nullable, chunk-local */, uint64_t seed,
+                           int* __restrict__ sizes /* [n_nodes][Fc_pad] */, int* __restrict__ trial_max) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Fc) return;
+    const int s = s_lo + f / n_samples, trial = f % n_samples;
+    const int max_family_size = max(s, range_max);  // conditional_distribution.cpp:20
+    sizes[(size_t)root * Fc_pad + f] = s;
+    int mx = 0;
+    for (int k = 0; k < n_nonroot; ++k) {
+        const int v = prefix_nodes[k];
+        const int ps = sizes[(size_t)parent[v] * Fc_pad + f];
+        const double rnd = uniforms ? uniforms[(size_t)f * n_nonroot + k] : counter_uniform(seed, (uint64_t)s, (uint64_t)trial, (uint64_t)k);
+        const double* cdf = CDF + ((size_t)node_key[v] * Sp + ps) * Sp;
+        // first c in [0, max_family_size-2] with cdf[c] >= rnd, else max_family_size-1
+        int lo = 0, hi = max_family_size - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cdf[mid] >= rnd) hi = mid; else lo = mid + 1;
+        }
+        sizes[(size_t)v * Fc_pad + f] = lo;
+        mx = max(mx, lo);
+    }
+    trial_max[f] = mx;
+}
+
+// range.max = MIN(max + MAX(50, max/5), range.max), carried from trial to trial within one root size
+__global__ void k_ratchet(const int* __restrict__ trial_max, int n_root_sizes, int n_samples, int range_max, int* __restrict__ colmax) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_root_sizes) return;
+    int cap = range_max;
+    for (int t = 0; t < n_samples; ++t) {
+        const int m = trial_max[(size_t)r * n_samples + t];
+        cap = min(m + max(50, m / 5), cap);
+        colmax[(size_t)r * n_samples + t] = cap;
+    }
+}
+
+struct RootChild {
+    int is_leaf;
+    int key;
+    int leaf;           // leaf ordinal when is_leaf
+    int slot;           // vector slot when internal
+    const int* err_rowptr; const int* err_col; const double* err_val;
+};
+
+// root with the single row s: L0 = prod over the two children of (row s of M_child) . (child vector)
+// one warp per simulated family
+__global__ void __launch_bounds__(256)
+k_root_single_row(RootChild c0, RootChild c1, const double* __restrict__ M, const double* __restrict__ vec, int Sp, int Vp,
+                  size_t slot_stride, const int* __restrict__ sizes, int Fc, int Fc_pad, int s_lo, int n_samples,
+                  const int* __restrict__ colmax, double* __restrict__ L0) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= Fc) return;
+    const int s = s_lo + f / n_samples;
+    const int cm = colmax[f];
+    double prod = 1.0;
+    for (int w = 0; w < 2; ++w) {
+        const RootChild c = w ? c1 : c0;
+        const double* row = M + ((size_t)c.key * Sp + s) * Sp;
+        double fac;
+        if (c.is_leaf) {
+            const int cnt = sizes[(size_t)(2 * c.leaf) * Fc_pad + f];
+            if (c.err_rowptr == nullptr) {
+                fac = (cnt <= cm) ? row[cnt] : 0.0;
+            } else {
+                fac = 0.0;
+                for (int k = c.err_rowptr[cnt]; k < c.err_rowptr[cnt + 1]; ++k) {
+                    const int j = c.err_col[k];
+                    if (j <= cm) fac = __dadd_rn(fac, __dmul_rn(row[j], c.err_val[k]));
+                }
+            }
+        } else {
+            const double* L = vec + (size_t)c.slot * slot_stride + (size_t)f * Vp;
+            double acc = 0.0;
+            for (int j = lane; j <= cm; j += 32) acc += row[j] * L[j];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            fac = acc;
+        }
+        prod *= fac;
+    }
+    if (lane == 0) L0[f] = prod;
+}
+
+}  // namespace
+
+int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, double* cd_out) {
+    const int R = ctx->R, n = ctx->n_nodes, n_nonroot = n - 1, D = (int)ctx->keys.size();
+    const size_t mat_bytes = (size_t)D * ctx->Sp * ctx->Sp * sizeof(double);
+    double* d_cdf = nullptr;
+    int *d_prefix = nullptr, *d_parent = nullptr, *d_node_key = nullptr;
+    int *d_sizes = nullptr, *d_trial_max = nullptr, *d_colmax = nullptr;
+    double *d_uniforms = nullptr, *d_L0 = nullptr, *d_sorted = nullptr;
+    void* d_tmp = nullptr;
+    int* d_offsets = nullptr;
+    int rc = CAFE_GPU_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_cdf); cudaFree(d_prefix); cudaFree(d_parent); cudaFree(d_node_key); cudaFree(d_sizes); cudaFree(d_trial_max);
+        cudaFree(d_colmax); cudaFree(d_uniforms); cudaFree(d_L0); cudaFree(d_sorted); cudaFree(d_tmp); cudaFree(d_offsets);
+    };
+#define CD_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
+
+    // root children (the root node itself is evaluated by k_root_single_row)
+    RootChild rc_child[2];
+    {
+        const int kids[2] = {ctx->left[ctx->root], ctx->right[ctx->root]};
+        for (int w = 0; w < 2; ++w) {
+            RootChild c{};
+            const int v = kids[w];
+            c.is_leaf = ctx->left[v] < 0;
+            c.key = ctx->node_key[v];
+            c.leaf = v / 2;
+            c.slot = -1;
+            if (c.is_leaf) {
+                int e = ctx->leaf_err.empty() ? -1 : ctx->leaf_err[c.leaf];
+                if (e >= 0) { c.err_rowptr = ctx->errs[e].d_rowptr; c.err_col = ctx->errs[e].d_col; c.err_val = ctx->errs[e].d_val; }
+            } else {
+                for (const PruneOp& op : ctx->ops)
+                    if (op.is_root && op.gemm_child == v) c.slot = op.in_slot;
+                if (c.slot < 0) { ctx->err = "conditional_distribution: schedule has no slot for a root child"; return CAFE_GPU_ERR_STATE; }
+            }
+            rc_child[w] = c;
+        }
+    }
+
+    CD_CK(cudaMalloc(&d_cdf, mat_bytes));
+    {
+        dim3 grid((ctx->S + 127) / 128, D);
+        k_row_cdf<<<grid, 128, 0, ctx->stream>>>(ctx->d_M, d_cdf, ctx->S, ctx->Sp, D);
+        ctx->launches++;
+    }
+    CD_CK(cudaMalloc(&d_prefix, n_nonroot * sizeof(int)));
+    CD_CK(cudaMalloc(&d_parent, n * sizeof(int)));
+    CD_CK(cudaMalloc(&d_node_key, n * sizeof(int)));
+    CD_CK(cudaMemcpyAsync(d_prefix, ctx->prefix_nonroot.data(), n_nonroot * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CD_CK(cudaMemcpyAsync(d_parent, ctx->parent.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CD_CK(cudaMemcpyAsync(d_node_key, ctx->node_key.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+
+    // root sizes are processed in chunks that bound the vector-slot memory
+    const int rows_per_chunk = std::max(1, std::min(R, (1 << 16) / std::max(1, n_samples)));
+    const int Fc_max = rows_per_chunk * n_samples, Fc_pad = round_up(Fc_max, 128);
+    CD_CK(cudaMalloc(&d_sizes, (size_t)n * Fc_pad * sizeof(int)));
+    CD_CK(cudaMemsetAsync(d_sizes, 0, (size_t)n * Fc_pad * sizeof(int), ctx->stream));
+    CD_CK(cudaMalloc(&d_trial_max, (size_t)Fc_pad * sizeof(int)));
+    CD_CK(cudaMalloc(&d_colmax, (size_t)Fc_pad * sizeof(int)));
+    CD_CK(cudaMemsetAsync(d_colmax, 0, (size_t)Fc_pad * sizeof(int), ctx->stream));
+    CD_CK(cudaMalloc(&d_L0, (size_t)R * n_samples * sizeof(double)));
+    CD_CK(cudaMalloc(&d_sorted, (size_t)R * n_samples * sizeof(double)));
+    if (uniforms) CD_CK(cudaMalloc(&d_uniforms, (size_t)Fc_max * n_nonroot * sizeof(double)));
+    rc = ensure_vec_buffers(ctx, Fc_pad);
+    if (rc) { cleanup(); return rc; }
+    const size_t slot_stride = (size_t)Fc_pad * ctx->Vp;
+
+    for (int r_lo = 0; r_lo < R; r_lo += rows_per_chunk) {
+        const int rows = std::min(rows_per_chunk, R - r_lo), Fc = rows * n_samples, s_lo = ctx->root_min + r_lo;
+        if (uniforms)
+            CD_CK(cudaMemcpyAsync(d_uniforms, uniforms + (size_t)r_lo * n_samples * n_nonroot, (size_t)Fc * n_nonroot * sizeof(double),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        k_simulate<<<(Fc + 127) / 128, 128, 0, ctx->stream>>>(d_cdf, ctx->Sp, d_prefix, d_parent, d_node_key, n_nonroot, ctx->root, s_lo,
+                                                              n_samples, Fc, Fc_pad, ctx->rmax, d_uniforms, seed, d_sizes, d_trial_max);
+        k_ratchet<<<(rows + 127) / 128, 128, 0, ctx->stream>>>(d_trial_max, rows, n_samples, ctx->rmax, d_colmax);
+        ctx->launches += 2;
+        // all non-root nodes with the per-trial column window; leaf k is node 2k of the size table
+        rc = launch_prune_ops(ctx, d_sizes, (size_t)2 * Fc_pad, Fc, Fc_pad, d_colmax, 0, 0, /*skip_root=*/true, nullptr);
+        if (rc) { cleanup(); return rc; }
+        k_root_single_row<<<(Fc + 7) / 8, 256, 0, ctx->stream>>>(rc_child[0], rc_child[1], ctx->d_M, ctx->d_vec, ctx->Sp, ctx->Vp, slot_stride,
+                                                                 d_sizes, Fc, Fc_pad, s_lo, n_samples, d_colmax,
+                                                                 d_L0 + (size_t)r_lo * n_samples);
+        ctx->launches++;
+        CD_CK(cudaGetLastError());
+    }
+
+    // ascending sort of every row (std::sort, conditional_distribution.cpp:41)
+    {
+        std::vector<int> off(R + 1);
+        for (int r = 0; r <= R; ++r) off[r] = r * n_samples;
+        CD_CK(cudaMalloc(&d_offsets, (R + 1) * sizeof(int)));
+        CD_CK(cudaMemcpyAsync(d_offsets, off.data(), (R + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        size_t tmp_bytes = 0;
+        CD_CK(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_L0, d_sorted, R * n_samples, R, d_offsets, d_offsets + 1, ctx->stream));
+        CD_CK(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        CD_CK(cub::DeviceSegmentedSort::SortKeys(d_tmp, tmp_bytes, d_L0, d_sorted, R * n_samples, R, d_offsets, d_offsets + 1, ctx->stream));
+        ctx->launches++;
+    }
+    CD_CK(cudaMemcpyAsync(cd_out, d_sorted, (size_t)R * n_samples * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CD_CK(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+    ctx->results_valid = false;  // the vector slots were reused
+#undef CD_CK
+    return CAFE_GPU_OK;
 }

@@ -295,8 +295,6 @@ static LeafSrc make_leaf_src(cafe_gpu_ctx* ctx, int leaf, int key) {
     return L;
 }
 
-int launch_prune_ops(cafe_gpu_ctx* ctx, const int* d_counts_override, int F, int F_pad, const int* d_colmax,
-                     int root_r0, int root_rows, int* root_slot_out);
 
 int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     if (ctx->timing) CAFE_CK(ctx, cudaEventRecord(ctx->quad(ctx->ring_k2)[2], ctx->stream));
@@ -308,7 +306,7 @@ int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     } else {
         // per-node kernels (also the path for per-family column windows, see pvalue.cu / conddist.cu)
         int root_slot = -1;
-        int rc = launch_prune_ops(ctx, nullptr, ctx->F, ctx->F_pad, nullptr, ctx->root_min, ctx->R, &root_slot);
+        int rc = launch_prune_ops(ctx, ctx->d_counts, ctx->F_pad, ctx->F, ctx->F_pad, nullptr, ctx->root_min, ctx->R, false, &root_slot);
         if (rc) return rc;
         const double* Lroot = ctx->d_vec + (size_t)root_slot * ctx->F_pad * ctx->Vp;
         const int warps_per_block = 8;
@@ -326,22 +324,25 @@ int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     return CAFE_GPU_OK;
 }
 
-// Runs the schedule over F families whose counts live in ctx->d_counts (or an override with the same
-// [leaf][F_pad] layout).  d_colmax (nullable) gives a per-family column window; the root rows are
-// root_r0 .. root_r0+root_rows-1.  The caller guarantees ctx->d_vec holds n_slots*F_pad*Vp doubles.
-int launch_prune_ops(cafe_gpu_ctx* ctx, const int* d_counts_override, int F, int F_pad, const int* d_colmax,
-                     int root_r0, int root_rows, int* root_slot_out) {
+// Runs the schedule with the per-node kernels over F families.  counts_base[leaf * leaf_stride + f] is the
+// observed (or simulated) size of family f at leaf `leaf`; d_colmax (nullable) gives a per-family column
+// window (cafe_family.c:250-254, conditional_distribution.cpp:29); the root rows are root_r0..root_r0+root_rows-1.
+// With skip_root the root node is left to the caller (single-row roots of the conditional distribution).
+// The caller guarantees ctx->d_vec holds n_slots*F_pad*Vp doubles.
+int launch_prune_ops(cafe_gpu_ctx* ctx, const int* counts_base, size_t leaf_stride, int F, int F_pad, const int* d_colmax,
+                     int root_r0, int root_rows, bool skip_root, int* root_slot_out) {
     const size_t slot_stride = (size_t)F_pad * ctx->Vp;
     const size_t mat_stride = (size_t)ctx->Sp * ctx->Sp;
     const int K = ctx->W;  // columns min..max of the matvec (cafe_tree.c:223)
     for (const PruneOp& op : ctx->ops) {
+        if (op.is_root && skip_root) continue;
         const int r0 = op.is_root ? root_r0 : 0;
         const int nrows = op.is_root ? root_rows : ctx->W;
         const int mask_rows = op.is_root ? 0 : 1;
         double* out = ctx->d_vec + (size_t)op.out_slot * slot_stride;
         auto leaf_src = [&](int leaf, int key) {
             LeafSrc L = make_leaf_src(ctx, leaf, key);
-            if (d_counts_override) L.counts = d_counts_override + (size_t)leaf * F_pad;
+            L.counts = counts_base + (size_t)leaf * leaf_stride;
             return L;
         };
         if (op.gemm_child < 0) {

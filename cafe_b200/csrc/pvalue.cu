@@ -1,5 +1,98 @@
-// pvalue.cu — K5 (placeholder until the p-value kernels land).
+// pvalue.cu — K5: family-wide p-values.
+//
+// Replaces, for every family at once, viterbi_section's p-value part (cafe/viterbi.cpp:88-97):
+//   cafe_family_set_size_with_family_forced (cafe/cafe_family.c:236-255): per-family range
+//       root 1..rint(1.25*max_f), columns 0..max_f + max(50, max_f/5)
+//   cafe_tree_p_values (cafe/pvalue.cpp:143-154): prune, p[s] = pvalue(L[s], cd[s], n_samples)
+//   pvalue (libcommon/mathfunc.c:663-689): rank of L[s] in the ascending row, ties at their midpoint
+//   viterbi_set_max_pvalue (cafe/viterbi.cpp:32-39): max over s, 0 for an empty root range
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
-int run_pvalues(cafe_gpu_ctx* ctx, const double*, int, int, double*) {
-    CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "pvalues: not built yet");
+
+namespace {
+
+// Ties: the reference compares with == (mathfunc.c:674-681) and an observed family that coincides with a simulated
+// one gives a bit-identical likelihood there, so the tie midpoint matters.  Here the two values come from
+// differently ordered sums (GEMM vs row dot product) and agree only to ~1e-15 relative; values within
+// TIE_RTOL of each other are therefore treated as the tie the reference would see.
+constexpr double TIE_RTOL = 1e-11;
+
+__device__ __forceinline__ double pvalue_dev(double v, const double* __restrict__ cd, int size) {
+    const double lo_v = v * (1.0 - TIE_RTOL), hi_v = v * (1.0 + TIE_RTOL);
+    int from = 0, to = size - 1;
+    while (from < to) {
+        const int mi = from + (to - from) / 2;
+        const double c = cd[mi];
+        if (c > hi_v) to = mi - 1;
+        else if (c < lo_v) from = mi + 1;
+        else {
+            from = mi; while (from > 0 && cd[from - 1] >= lo_v) --from;
+            to = mi; while (to + 1 < size && cd[to + 1] <= hi_v) ++to;
+            break;
+        }
+    }
+    if (from > to) to = from;
+    return ((double)from + (cd[from] <= hi_v ? 1.0 : 0.0) + (double)(to - from) / 2.0) / (double)size;
+}
+
+// one warp per family: lanes take root sizes s, warp-max of the p-values
+__global__ void __launch_bounds__(256)
+k_family_pvalue(const double* __restrict__ Lroot, int Vp, int F, const int* __restrict__ rfsize, const double* __restrict__ cd,
+                int cd_rows, int n_samples, double* __restrict__ out) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= F) return;
+    const int rf = min(rfsize[f], cd_rows);
+    double best = -1.0;
+    for (int s = lane; s < rf; s += 32) best = fmax(best, pvalue_dev(Lroot[(size_t)f * Vp + s], cd + (size_t)s * n_samples, n_samples));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if (lane == 0) out[f] = (rf > 0) ? best : 0.0;
+}
+
+}  // namespace
+
+int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out) {
+    const int F = ctx->F, nl = ctx->n_leaves;
+    // per-family forced range (host: n_leaves ints per family)
+    std::vector<int> colmax(ctx->F_pad, 0), rfsize(ctx->F_pad, 0);
+    int rf_max = 0;
+    for (int f = 0; f < F; ++f) {
+        int mx = 0;
+        for (int k = 0; k < nl; ++k) mx = std::max(mx, ctx->h_counts[(size_t)f * nl + k]);
+        const int root_max = (int)std::rint(mx * 1.25);
+        colmax[f] = std::min(mx + std::max(50, mx / 5), ctx->W - 1);
+        rfsize[f] = root_max;  // root_min is 1 in the forced range
+        rf_max = std::max(rf_max, root_max);
+    }
+    if (rf_max > ctx->Vp || 1 + rf_max > ctx->S)
+        CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "pvalues: a family's root range rint(1.25*max) exceeds the matrices (set_ranges from the table's max first)");
+    int *d_colmax = nullptr, *d_rf = nullptr;
+    double *d_cd = nullptr, *d_out = nullptr;
+    auto cleanup = [&]() { cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_cd); cudaFree(d_out); };
+#define PV_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
+    PV_CK(cudaMalloc(&d_colmax, ctx->F_pad * sizeof(int)));
+    PV_CK(cudaMalloc(&d_rf, ctx->F_pad * sizeof(int)));
+    PV_CK(cudaMalloc(&d_cd, (size_t)cd_rows * n_samples * sizeof(double)));
+    PV_CK(cudaMalloc(&d_out, ctx->F_pad * sizeof(double)));
+    PV_CK(cudaMemcpyAsync(d_colmax, colmax.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    PV_CK(cudaMemcpyAsync(d_rf, rfsize.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    PV_CK(cudaMemcpyAsync(d_cd, cd, (size_t)cd_rows * n_samples * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = ensure_vec_buffers(ctx, ctx->F_pad);
+    if (rc) { cleanup(); return rc; }
+    int root_slot = -1;
+    // root rows 1..rf_max for everybody (rows beyond a family's own range are ignored by k_family_pvalue)
+    rc = launch_prune_ops(ctx, ctx->d_counts, ctx->F_pad, F, ctx->F_pad, d_colmax, 1, std::min(rf_max, ctx->S - 1), false, &root_slot);
+    if (rc) { cleanup(); return rc; }
+    const double* Lroot = ctx->d_vec + (size_t)root_slot * ctx->F_pad * ctx->Vp;
+    k_family_pvalue<<<(F + 7) / 8, 256, 0, ctx->stream>>>(Lroot, ctx->Vp, F, d_rf, d_cd, cd_rows, n_samples, d_out);
+    ctx->launches++;
+    PV_CK(cudaGetLastError());
+    PV_CK(cudaMemcpyAsync(out, d_out, F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PV_CK(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+    ctx->results_valid = false;
+#undef PV_CK
+    return CAFE_GPU_OK;
 }

@@ -401,3 +401,22 @@ def simulate_families(tree: FlatTree, lam_per_node, mu_per_node, maxfs, n_famili
             child[idx] = np.searchsorted(cdf[p], u[idx], side="left")
         sizes[:, v] = np.minimum(child, maxfs)
     return sizes[:, 0::2].astype(np.int32)
+
+
+def conditional_distribution(tree: FlatTree, mats, ranges, n_samples, uniforms=None):
+    """cafe/conditional_distribution.cpp:48-57 single-threaded: rows for s = root_min..root_max.
+    uniforms (optional): the unifrnd() stream in the reference's order; None draws from glibc rand()."""
+    rmin, rmax, root_min, root_max = ranges
+    rows = []
+    off = 0
+    per_row = n_samples * (tree.n_nodes - 1)
+    for s in range(root_min, root_max + 1):
+        u = None if uniforms is None else uniforms[off:off + per_row]
+        r = random_probabilities(tree, mats, rmin, rmax, s, n_samples, u)
+        rows.append(r["sorted"])
+        off += per_row
+    return np.array(rows)
+
+
+def srand(seed: int):
+    C.CDLL(None).srand(C.c_uint(seed))

@@ -1,0 +1,121 @@
+"""-m gpu: K4 (conditional distribution) and K5 (family p-values) through the C-ABI against the oracle."""
+import numpy as np
+import pytest
+
+import oracle
+
+from util import EXAMPLE_TREE, Problem, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def small_counts(n_leaves, F, hi, seed):
+    rng = np.random.RandomState(seed)
+    base = rng.randint(1, hi, size=(F, 1))
+    return np.maximum(0, base + rng.randint(-2, 3, size=(F, n_leaves))).astype(np.int32)
+
+
+def make(newick=EXAMPLE_TREE, lam=0.004, F=24, hi=12, ranges=(0, 62, 1, 15), seed=1, **kw):
+    n_leaves = newick.count(",") + 1
+    return Problem(newick, small_counts(n_leaves, F, hi, seed), lam, ranges=ranges, **kw)
+
+
+@pytest.mark.parametrize("newick,lam", [
+    (EXAMPLE_TREE, 0.004),
+    ("((A:10,B:10):5,(C:7,D:7):8)", 0.01),
+    ("(A:12,B:12)", 0.02),
+    ("(((A:3,B:3):4,C:7):6,(D:5,(E:2,F:2):3):8)", 0.015),
+])
+def test_k4_replay_matches_oracle_draw_for_draw(newick, lam):
+    p = make(newick, lam)
+    g = p.make_gpu()
+    n = 200
+    R = p.ranges[3] - p.ranges[2] + 1
+    u = np.random.RandomState(7).random_sample(R * n * (p.tree.n_nodes - 1))
+    cd = g.conditional_distribution(n, uniforms=u)
+    ref = oracle.conditional_distribution(p.otree, p.oracle_mats(), p.ranges, n, uniforms=u)
+    assert cd.shape == ref.shape
+    assert np.all(np.diff(cd, axis=1) >= 0)
+    big = ref > 1e-290
+    assert rel_err(cd[big], ref[big]).max() < 1e-11
+    assert np.abs(cd[~big] - ref[~big]).max() <= 1e-290 if (~big).any() else True
+    g.close()
+
+
+def test_k4_replay_with_lambda_mu_and_ratchet():
+    # larger lambda: simulated sizes spread, the range.max ratchet (conditional_distribution.cpp:29) bites
+    p = make(EXAMPLE_TREE, 0.008, mu=0.009, ranges=(0, 90, 1, 30))
+    g = p.make_gpu()
+    n = 150
+    R = 30
+    u = np.random.RandomState(11).random_sample(R * n * (p.tree.n_nodes - 1))
+    cd = g.conditional_distribution(n, uniforms=u)
+    ref = oracle.conditional_distribution(p.otree, p.oracle_mats(), p.ranges, n, uniforms=u)
+    big = ref > 1e-290
+    assert rel_err(cd[big], ref[big]).max() < 1e-11
+    g.close()
+
+
+def test_k4_device_rng_is_statistically_equivalent():
+    from scipy import stats
+    p = make(EXAMPLE_TREE, 0.004)
+    g = p.make_gpu()
+    n = 2000
+    cd = g.conditional_distribution(n, uniforms=None, seed=12345)
+    assert np.all(np.diff(cd, axis=1) >= 0)
+    oracle.srand(99)
+    ref = oracle.conditional_distribution(p.otree, p.oracle_mats(), p.ranges, n)
+    pv = []
+    for r in (0, 3, 7, 14):
+        a = np.log(np.maximum(cd[r], 1e-300))
+        b = np.log(np.maximum(ref[r], 1e-300))
+        pv.append(stats.ks_2samp(a, b).pvalue)
+    assert min(pv) > 1e-4, pv
+    # a different seed gives a different sample
+    cd2 = g.conditional_distribution(n, uniforms=None, seed=54321)
+    assert not np.array_equal(cd, cd2)
+    g.close()
+
+
+@pytest.mark.parametrize("with_err", [False, True])
+def test_k5_family_pvalues_match_oracle(with_err):
+    err = None
+    ranges = (0, 62, 1, 15)
+    if with_err:
+        dim = 63
+        E = np.zeros((dim, dim))
+        eps = 0.03
+        for j in range(dim):
+            for d, v in ((-1, eps), (0, 1 - 2 * eps), (1, eps)):
+                if 0 <= j + d < dim:
+                    E[j + d, j] = v
+        E[0, 0] = 1 - eps
+        E[dim - 1, dim - 1] = 1 - eps
+        err = {k: E for k in range(5)}
+    p = make(EXAMPLE_TREE, 0.004, F=40, err=err, ranges=ranges)
+    p.counts[0, :] = 0  # an all-zero family: empty root range -> p-value 0 (viterbi.cpp:32-39)
+    g = p.make_gpu()
+    n = 400
+    R = ranges[3] - ranges[2] + 1
+    u = np.random.RandomState(3).random_sample(R * n * (p.tree.n_nodes - 1))
+    cd = oracle.conditional_distribution(p.otree, p.oracle_mats(), p.ranges, n, uniforms=u)
+    pv = g.pvalues(cd)
+    ref = np.array([oracle.family_pvalue(p.otree, p.oracle_mats(), p.counts[f], cd, leaf_err=p.oracle_leaf_err())[0]
+                    for f in range(len(p.counts))])
+    assert pv[0] == 0.0 and ref[0] == 0.0
+    assert np.abs(pv - ref).max() <= 1.0 / n + 1e-12
+    assert (pv == ref).mean() > 0.97
+    g.close()
+
+
+def test_k4_then_score_still_correct():
+    # the conditional distribution reuses the vector slots; a following score must be unaffected
+    p = make(EXAMPLE_TREE, 0.004, F=33)
+    g = p.make_gpu()
+    s0, _ = g.score()
+    g.conditional_distribution(50, uniforms=None, seed=1)
+    s1, _ = g.score()
+    assert s0 == s1
+    o = p.oracle_score(want_L=False)
+    assert abs(s1 - o["score"]) < 1e-6
+    g.close()
