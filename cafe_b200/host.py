@@ -46,6 +46,9 @@ def load_library():
     H.cafe_host_free.argtypes = [vp]
     H.cafe_host_command.argtypes = [vp, C.c_char_p]
     H.cafe_host_num_params.argtypes = [vp]
+    H.cafe_host_srand.argtypes = [C.c_uint]
+    H.cafe_host_find_poisson_lambda.argtypes = [vp, _dp, _ip, _dp]
+    H.cafe_host_get_family_table.argtypes = [vp, _ip, C.c_long, _ip, _ip]
     H.cafe_host_get_parameters.argtypes = [vp, _dp, C.c_int]
     H.cafe_host_objective_calls.argtypes = [vp]
     H.cafe_host_get_ranges.argtypes = [vp, _ip]
@@ -199,6 +202,24 @@ class Session:
             raise CafeHostError("prior not set")
         return out
 
+    def find_poisson_lambda(self):
+        lam = C.c_double()
+        it = C.c_int()
+        sc = C.c_double()
+        if self.H.cafe_host_find_poisson_lambda(self.h, C.byref(lam), C.byref(it), C.byref(sc)) != 0:
+            raise CafeHostError(self.H.cafe_host_last_error().decode())
+        return lam.value, it.value, sc.value
+
+    def family_table(self, n_species):
+        F = self.num_families()
+        counts = np.zeros((F, n_species), dtype=np.int32)
+        ref = np.zeros(F, dtype=np.int32)
+        index = np.zeros(n_species, dtype=np.int32)
+        ns = self.H.cafe_host_get_family_table(self.h, _i(counts), counts.size, _i(ref), _i(index))
+        if ns != n_species:
+            raise CafeHostError("species count mismatch")
+        return counts, ref, index
+
     def num_families(self):
         return self.H.cafe_host_num_families(self.h)
 
@@ -234,6 +255,10 @@ class Session:
         out = np.zeros(F)
         n = self.H.cafe_host_get_max_pvalues(self.h, _d(out), F)
         return out[:n]
+
+
+def srand(seed: int):
+    load_library().cafe_host_srand(seed)
 
 
 def release_gpu():

@@ -1,6 +1,7 @@
 // capi.cpp — extern "C" doors into the host library for the Python tests / bench (ctypes).
 // No torch types, plain pointers and sizes.  Errors are returned as negative codes; the text of the
 // last one is available from cafe_host_last_error().
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -139,6 +140,30 @@ void cafe_host_free(void* h) { delete static_cast<Globals*>(h); }
 void cafe_host_release_gpu() { cafe_gpu_engine_release(); }
 
 int cafe_host_command(void* h, const char* line) { return cafe_shell_dispatch_command(*static_cast<Globals*>(h), line); }
+
+void cafe_host_srand(unsigned seed) { std::srand(seed); }
+// find_poisson_lambda on the loaded table (consumes one rand()), cafe/lambda.cpp:808-838
+int cafe_host_find_poisson_lambda(void* h, double* lambda, int* iters, double* score) {
+    HOST_TRY
+    CafeParam& p = static_cast<Globals*>(h)->param;
+    if (!p.pfamily) { g_host_err = "no family table loaded"; return -1; }
+    poisson_lambda r = find_poisson_lambda(p.pfamily);
+    *lambda = r.parameters[0]; *iters = r.num_iterations; *score = r.score;
+    return 0;
+    HOST_CATCH(-1)
+}
+int cafe_host_get_family_table(void* h, int* counts_out, long cap, int* ref_out, int* index_out) {
+    CafeParam& p = static_cast<Globals*>(h)->param;
+    if (!p.pfamily) return -1;
+    const int ns = p.pfamily->num_species;
+    if ((long)p.pfamily->flist.size() * ns > cap) return -1;
+    for (size_t i = 0; i < p.pfamily->flist.size(); ++i) {
+        std::copy(p.pfamily->flist[i].count.begin(), p.pfamily->flist[i].count.end(), counts_out + i * ns);
+        if (ref_out) ref_out[i] = p.pfamily->flist[i].ref;
+    }
+    if (index_out) std::copy(p.pfamily->index.begin(), p.pfamily->index.end(), index_out);
+    return ns;
+}
 
 int cafe_host_num_params(void* h) { return static_cast<Globals*>(h)->param.num_params; }
 int cafe_host_get_parameters(void* h, double* out, int cap) {

@@ -22,6 +22,7 @@ _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
 _lp = C.POINTER(C.c_long)
 _dpp = C.POINTER(_dp)
+MATH_FUNC = C.CFUNCTYPE(C.c_double, _dp, C.c_void_p)
 
 
 def build(ref: bool = True) -> None:
@@ -134,6 +135,7 @@ def ref():
     R.refshim_load_families.restype = C.c_int
     R.refshim_load_families.argtypes = [C.c_char_p, C.c_int, _ip, _ip, _ip, C.c_int, _ip, _ip]
     R.refshim_session_free.argtypes = [C.c_void_p]
+    R.refshim_fminsearch.argtypes = [MATH_FUNC, C.c_void_p, C.c_int, _dp, C.c_double, C.c_double, _dp, _dp, _ip]
     return R
 
 

@@ -307,6 +307,19 @@ int refshim_load_families(const char* path, int max_size, int* n_species, int* F
     return 0;
 }
 
+// the reference's Nelder-Mead (libcommon/fminsearch.cpp) on a caller-supplied function
+int refshim_fminsearch(math_func f, void* args, int n, const double* x0, double tolx, double tolf, double* x_out, double* f_out, int* iters_out) {
+    pFMinSearch pfm = fminsearch_new_with_eq(f, n, args);
+    pfm->tolx = tolx; pfm->tolf = tolf;
+    std::vector<double> start(x0, x0 + n);
+    fminsearch_min(pfm, &start[0]);
+    memcpy(x_out, fminsearch_get_minX(pfm), n * sizeof(double));
+    *f_out = fminsearch_get_minF(pfm);
+    *iters_out = pfm->iters;
+    fminsearch_free(pfm);
+    return 0;
+}
+
 void refshim_session_free(void* h) {
     Session* s = (Session*)h;
     if (s->family) cafe_family_free(s->family);

@@ -1,0 +1,82 @@
+"""CPU, world_size 2, gloo: the multi-rank plumbing of one objective evaluation — contiguous family
+shards, one collective on {partial score, first zero family}, identical result on every rank."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from cafe_b200 import sharding
+
+EX_TREE = "(((chimp:6,human:6):81,(mouse:17,rat:17):70):6,dog:93)"
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 100, 50000, 200001):
+        for ws in (1, 2, 3, 8):
+            cuts = [sharding.shard_bounds(n, ws, r) for r in range(ws)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(ws - 1))
+            sizes = [b - a for a, b in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _problem(lam):
+    t = oracle.parse_newick(EX_TREE)
+    rng = np.random.RandomState(4)
+    base = rng.randint(1, 20, size=(41, 1))
+    counts = np.maximum(0, base + rng.randint(-2, 3, size=(41, 5))).astype(np.int32)
+    ranges = (0, 72, 1, 30)
+    mats = oracle.node_matrices(t, [lam] * t.n_nodes, [-1.0] * t.n_nodes, 72)
+    prior = oracle.prior_poisson(1, 8.0, 1000)[:30]
+    return t, counts, ranges, mats, prior
+
+
+def _worker(rank, world, port, lam, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t, counts, ranges, mats, prior = _problem(lam)
+    first = np.arange(len(counts), dtype=np.int32) + 1000
+    c, m, f = sharding.shard_families(counts, None, first, world, rank)
+    # the per-rank partial a GPU context would leave in its 2-double device buffer (cafe_gpu_objective_device)
+    o = oracle.score(t, mats, c, ranges, prior)
+    zero = o["maxlik"] == 0
+    partial = float(o["logpost"][~zero].sum())
+    zidx = float(f[zero].min()) if zero.any() else float("inf")
+    s, z = sharding.reduce_score(torch.tensor([partial, zidx], dtype=torch.float64))
+    out[rank] = sharding.finish_score(s, z)
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("lam,expect_zero", [(0.005, False), (0.011, True)])
+def test_two_rank_reduction_matches_single_rank(lam, expect_zero):
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), lam, out), nprocs=world, join=True)
+    t, counts, ranges, mats, prior = _problem(lam)
+    full = oracle.score(t, mats, counts, ranges, prior)
+    assert out[0] == out[1]
+    score, fz = out[0]
+    if expect_zero:
+        assert score == -np.inf and fz == 1000 + full["first_zero"]
+    else:
+        assert fz == -1 and abs(score - full["score"]) < 1e-9
+
+
+def test_reduce_score_without_process_group():
+    s, z = sharding.reduce_score(torch.tensor([-12.5, float("inf")], dtype=torch.float64))
+    assert sharding.finish_score(s, z) == (-12.5, -1)
+    s, z = sharding.reduce_score(torch.tensor([-12.5, 7.0], dtype=torch.float64))
+    assert sharding.finish_score(s, z) == (-np.inf, 7)
