@@ -62,6 +62,7 @@ void cafe_gpu_destroy(cafe_gpu_ctx* ctx) {
     cudaFreeHost(ctx->h_score);
     free_err_models(ctx);
     fused_release(ctx);
+    fused2_release(ctx);
     for (cudaEvent_t e : ctx->ring) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

@@ -133,7 +133,8 @@ struct cafe_gpu_ctx {
     double* h_score = nullptr;    // pinned [2]
     bool results_valid = false;
 
-    void* fused_state = nullptr;  // prune_fused.cu private state (device schedule, scratch)
+    void* fused_state = nullptr;   // prune_fused.cu private state (device schedule, scratch)
+    void* fused2_state = nullptr;  // prune_fused2.cu private state
 
     // bookkeeping
     int64_t launches = 0;
@@ -156,6 +157,9 @@ int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad);                // api.c
 bool fused_supported(const cafe_gpu_ctx* ctx);                          // prune_fused.cu
 int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out);         // prune_fused.cu (K2, fused persistent kernel)
 void fused_release(cafe_gpu_ctx* ctx);
+bool fused2_supported(const cafe_gpu_ctx* ctx);                         // prune_fused2.cu
+int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out);        // prune_fused2.cu (K2, one CTA per SM, default)
+void fused2_release(cafe_gpu_ctx* ctx);
 int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed,
                                  double* cd_out);                       // conddist.cu    (K4)
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out);  // pvalue.cu (K5)

@@ -299,8 +299,13 @@ static LeafSrc make_leaf_src(cafe_gpu_ctx* ctx, int leaf, int key) {
 int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     if (ctx->timing) CAFE_CK(ctx, cudaEventRecord(ctx->quad(ctx->ring_k2)[2], ctx->stream));
     static const bool no_fused = std::getenv("CAFE_GPU_NO_FUSED") != nullptr;  // A/B switch for tests and profiling
-    if (!no_fused && fused_supported(ctx)) {
-        // fused persistent kernel: whole tree + root reduction in one launch
+    static const bool fused_v1 = std::getenv("CAFE_GPU_FUSED_V1") != nullptr;  // A/B switch: first-generation fused kernel
+    if (!no_fused && !fused_v1 && fused2_supported(ctx)) {
+        // fused persistent kernel, one CTA per SM: whole tree + root reduction in one launch
+        int rc = launch_prune_fused2(ctx, d_Lroot_out);
+        if (rc) return rc;
+    } else if (!no_fused && fused_supported(ctx)) {
+        // first-generation fused kernel: error-model leaves, leaf counts outside the vector, two-leaf trees
         int rc = launch_prune_fused(ctx, d_Lroot_out);
         if (rc) return rc;
     } else {

@@ -324,7 +324,8 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
 #pragma unroll
                                         for (int c8 = 0; c8 < 8; ++c8) {
                                             const int i = ib + c8 * 32;
-                                            if (i + lane < P.Vp) o[i] = va[u][c8] * vb[u][c8];
+                                            // sizes >= W must stay exact zeros (the matrices are wider than W when S > W)
+                                            if (i + lane < P.Vp) o[i] = (i + lane < P.W) ? va[u][c8] * vb[u][c8] : 0.0;
                                         }
                                     }
                                 }
@@ -438,8 +439,9 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                                             double* o = out + (size_t)((mb + u) * 8 + pg) * P.Vp + n0;
 #pragma unroll
                                             for (int nb = 0; nb < NB; ++nb) {
-                                                o[nb * 8 + pc0] = acc[mb + u][nb][0] * fac[u][nb][0];
-                                                o[nb * 8 + pc1] = acc[mb + u][nb][1] * fac[u][nb][1];
+                                                // sizes >= nrows must stay exact zeros: matrix rows in [W, S) are not zero when S > W
+                                                o[nb * 8 + pc0] = (n0 + nb * 8 + pc0 < nrows) ? acc[mb + u][nb][0] * fac[u][nb][0] : 0.0;
+                                                o[nb * 8 + pc1] = (n0 + nb * 8 + pc1 < nrows) ? acc[mb + u][nb][1] * fac[u][nb][1] : 0.0;
                                             }
                                         }
                                     }

@@ -1,0 +1,870 @@
+// prune_fused2.cu — K2, second generation of the fused persistent pruning kernel (the default path when no
+// leaf carries an error model).
+//
+// Replaces, per objective evaluation, the reference's F x (2n-2) calls of square_matrix_multiply
+// (libtree/birthdeath.c:163-182) under compute_internal_node_likelihood (cafe/cafe_tree.c:226-271),
+// initialize_leaf_likelihoods (:191-211) and compute_posterior's root reduction (cafe/lambda.cpp:657-689).
+//
+// Why a second kernel: prune_fused.cu runs 3 independent CTAs per SM.  The SM's warp arbiter serves the
+// highest warp slot first, so one of the three CTAs is starved of the DMMA pipe and finishes ~20 % after the
+// other two (profiles/r1_fused_v1_cta_timeline.txt), and every CTA leaves the pipe for its epilogues (global
+// gathers), leaf-pair products and proxy fences.  Here ONE CTA per SM owns the SM:
+//
+//   warps 0..11  DMMA consumers, 3 M-groups x 4 N-warps, CTA tile 96 families x 128 sizes.  All twelve consume the
+//                same shared-memory ring, so they advance in lockstep (a starved warp stalls the ring and thereby
+//                gets the pipe) and the matrix tile (B) is fetched once for all three groups.  Consumers touch shared
+//                memory only: no global loads, no global stores, no membar.
+//   warp 12      TMA producer: child vectors (A, 96 x 16 sizes) and matrix K-blocks (B, 128 rows x 16 sizes).
+//   warp 13      cherry gatherer: when the GEMM child is a node whose two children are leaves, its vector is the
+//                product of two gathered matrix columns (cafe_tree.c:204-210); the rows are copied with cp.async
+//                straight into the ring (A1, A2) and multiplied by the consumers in registers — a leaf-pair
+//                vector never exists in memory.
+//   warp 14      epilogue manager: stages the sibling factor of the next pass in the 96 KB C tile (TMA for a stored
+//                partial product, cp.async row gathers for a leaf sibling), and writes the finished tile back with
+//                a TMA store.  Consumers multiply in place (C = acc * C).  All fences live in this warp.
+//
+// Bit-for-bit the same arithmetic as prune_fused.cu / prune.cu (same DMMA order over K, one rounding per product).
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+
+#include "common.cuh"
+
+namespace fused2 {
+
+constexpr int GM = 2;                  // M-groups (consumer warpgroups): exactly two DMMA warps per SM sub-partition
+constexpr int HM = 48;                 // families per group
+constexpr int TILE_M = GM * HM;        // 96 families per CTA tile
+constexpr int TN = 128;                // output sizes per pass
+constexpr int BK = 16;                 // sizes per K block (16 doubles = 128 B = one swizzle row)
+constexpr int NSTAGE = 3;
+constexpr int A_BYTES = TILE_M * 128;  // 12 KB
+constexpr int B_BYTES = TN * 128;      // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;  // A1 | A2 | B
+constexpr int C_BOX_BYTES = TILE_M * 128;           // one box: 96 families x 16 sizes
+constexpr int C_BOXES = TN / BK;                    // 8
+constexpr int C_BYTES = C_BOXES * C_BOX_BYTES;      // 96 KB
+constexpr int N_CONSUMER_WARPS = 4 * GM;
+constexpr int THREADS = (N_CONSUMER_WARPS + 4) * 32;
+constexpr int MB = HM / 8, NB = 4, WCOLS = NB * 8;
+constexpr int N_GATHER_WARPS = 2;
+// register re-partition of the 384 x 168 launch allocation: 8*32*200 + 4*32*104 = 64512
+constexpr int REGS_CONSUMER = 200, REGS_AUX = 104;
+
+struct Op {              // one GEMM of the post-order schedule (a tree edge below an internal node)
+    int is_root;
+    int key;             // matrix of the GEMM child's branch
+    int a_kind;          // 0: child vector in in_slot, 1: child is a leaf pair (a1, a2)
+    int in_slot, out_slot;
+    int leaf_a1, key_a1, leaf_a2, key_a2;
+    int other_kind;      // 0 none, 1 leaf sibling, 2 multiply into out_slot
+    int leaf_o, key_o;
+};
+
+struct Params {
+    const Op* ops;
+    int n_ops, n_slots;
+    int F, F_pad;
+    int W, R, root_min;
+    int Sp, Vp;
+    int n_mblocks;               // ceil(F / 8)
+    const double* MT;            // [D][Sp][Sp] transposed matrices
+    const int* counts;           // [n_leaves][F_pad]
+    const double* logprior;      // [R]
+    double* logpost;             // [F_pad]
+    double* maxlik;
+    int* argmax;
+    double* Lroot_out;           // nullable, [F][R]
+    long long* cta_times;        // nullable debug: [grid][4] = smid, start ns, end ns, 8-family blocks
+    long long* warp_prof;        // nullable debug: CTA 0, [16 warps][8] cycle sums (see consumer_main / producer_main)
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy accesses <-> async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16-byte / 8-byte asynchronous copies with zero fill of the bytes beyond src_bytes
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+struct Ctl {
+    uint64_t full[NSTAGE];       // producer expect_tx + 32 gatherer lanes
+    uint64_t empty[NSTAGE];      // 12 consumer warps
+    uint64_t c_ready;            // 32 lanes of the epilogue manager (+ TMA bytes)
+    uint64_t c_done;             // 12 consumer warps
+    volatile int done[2];        // finished (stored, visible) ops per tile of the pair
+    int rowoff_o[TILE_M];                    // epilogue manager: count * Sp of the leaf sibling
+    double red_ml[GM][4][HM];    // root reduction across the 4 N-warps of a group
+    double red_mp[GM][4][HM];
+    int red_am[GM][4][HM];
+};
+
+// This CTA's families: a contiguous range of 8-family blocks cut into an even number of tiles of <= 12 blocks;
+// tiles are processed two at a time (the op sequence of one interleaved with the other's) so that a vector is never
+// streamed right after it was stored.  Inside a tile, group g owns mbv(g) consecutive blocks.
+struct TilePlan {
+    int mb_lo, n_mb, n_tiles, n_pairs;
+    __device__ TilePlan(const Params& P) {
+        const int G = gridDim.x, c = blockIdx.x;
+        mb_lo = (int)((long long)P.n_mblocks * c / G);
+        n_mb = (int)((long long)P.n_mblocks * (c + 1) / G) - mb_lo;
+        n_tiles = (n_mb + TILE_M / 8 - 1) / (TILE_M / 8);
+        if (n_mb >= 2 && (n_tiles & 1)) ++n_tiles;
+        n_pairs = (n_tiles + 1) / 2;
+    }
+    __device__ bool tile(int t, int& mb0, int& m) const {
+        if (t >= n_tiles) return false;
+        mb0 = mb_lo + (int)((long long)n_mb * t / n_tiles);
+        m = mb_lo + (int)((long long)n_mb * (t + 1) / n_tiles) - mb0;
+        return true;
+    }
+    __device__ static int mbv(int m, int g) { return (m + GM - 1 - g) / GM; }
+    __device__ static int pre(int m, int g) { return g == 0 ? 0 : mbv(m, 0); }
+    // family of tile row r (clamped into [0, F) so that gathers of unused rows stay in bounds)
+    __device__ static int family(int mb0, int m, int r, int F) {
+        const int g = r / HM, lr = r - g * HM;
+        const int f = (mb0 + pre(m, g)) * 8 + lr;
+        return (lr < mbv(m, g) * 8 && f < F) ? f : (F - 1);
+    }
+};
+
+__device__ __forceinline__ void advance(uint32_t& stage, uint32_t& phase) {
+    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+}
+
+// ================================ TMA producer (one lane) ================================ ================================
+template <bool PROF>
+__device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUtensorMap* tmB, const Params& P,
+                                              unsigned char* stage_base, Ctl* ctl) {
+    const TilePlan plan(P);
+    const int scratch_row0 = blockIdx.x * 2 * P.n_slots * TILE_M;
+    const int n_kblocks = (P.W + BK - 1) / BK;
+    uint32_t stage = 0, phase = 0;
+    int ops_done_base = 0;
+    const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
+    long long t_wait_done = 0, t_wait_empty = 0;
+    const long long t_begin = prof ? clock64() : 0;
+    for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        for (int oi = 0; oi < P.n_ops; ++oi) {
+            const Op op = P.ops[oi];
+            const int r0 = op.is_root ? P.root_min : 0;
+            const int nrows = op.is_root ? P.R : P.W;
+            const int n_chunks = (nrows + TN - 1) / TN;
+            for (int h = 0; h < 2; ++h) {
+                if (2 * pair + h >= plan.n_tiles) continue;
+                if (op.a_kind == 0) {
+                    // the vector to stream was stored by an earlier op of this tile: wait until it is visible
+                    const long long t0 = prof ? clock64() : 0;
+                    while (ctl->done[h] < ops_done_base + oi) { __nanosleep(20); }
+                    __threadfence_block();
+                    fence_proxy_async();
+                    if (prof) t_wait_done += clock64() - t0;
+                }
+                const int a_row = scratch_row0 + (h * P.n_slots + op.in_slot) * TILE_M;
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    for (int kb = 0; kb < n_kblocks; ++kb) {
+                        const long long t0 = prof ? clock64() : 0;
+                        mbar_wait(&ctl->empty[stage], phase ^ 1);
+                        if (prof) t_wait_empty += clock64() - t0;
+                        unsigned char* sA = stage_base + stage * STAGE_BYTES;
+                        mbar_arrive_expect_tx(&ctl->full[stage], op.a_kind == 0 ? A_BYTES + B_BYTES : B_BYTES);
+                        if (op.a_kind == 0) tma_load_2d(sA, tmA, kb * BK, a_row, &ctl->full[stage]);
+                        tma_load_3d(sA + 2 * A_BYTES, tmB, kb * BK, r0 + ch * TN, op.key, &ctl->full[stage]);
+                        advance(stage, phase);
+                    }
+                }
+            }
+        }
+        ops_done_base += P.n_ops;
+    }
+    if (prof) {
+        long long* o = P.warp_prof + N_CONSUMER_WARPS * 8;
+        o[0] = clock64() - t_begin; o[1] = t_wait_done; o[2] = t_wait_empty;
+    }
+}
+
+// ================================ cherry gatherers (2 warps) ================================
+// Wait for every ring slot (so that they can never run ahead of the ring) and, when the GEMM child is a leaf pair, fill A1/A2
+// with the gathered rows MT_a[count_a][k..k+16), MT_b[count_b][k..k+16) in the TMA's 128B-swizzle layout.  Gatherer gi owns the
+// tile rows rs + 4*i, i in [12*gi, 12*gi + 12): 8 lanes copy one 128-byte row segment, 4 rows per instruction.
+__device__ __forceinline__ void gatherer_main(const Params& P, unsigned char* stage_base, Ctl* ctl, int gi) {
+    const TilePlan plan(P);
+    const int lane = threadIdx.x & 31;
+    const int n_kblocks = (P.W + BK - 1) / BK;
+    const int c = lane & 7, rs = lane >> 3;
+    constexpr int ROWS = TILE_M / 4 / N_GATHER_WARPS;  // 12 rows per lane
+    uint32_t stage = 0, phase = 0;
+    for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        for (int oi = 0; oi < P.n_ops; ++oi) {
+            const Op op = P.ops[oi];
+            const int nrows = op.is_root ? P.R : P.W;
+            const int n_chunks = (nrows + TN - 1) / TN;
+            const double* __restrict__ MTa = P.MT + (size_t)op.key_a1 * P.Sp * P.Sp;
+            const double* __restrict__ MTb = P.MT + (size_t)op.key_a2 * P.Sp * P.Sp;
+            for (int h = 0; h < 2; ++h) {
+                int mb0, m;
+                if (!plan.tile(2 * pair + h, mb0, m)) continue;
+                int offa[ROWS], offb[ROWS];
+                if (op.a_kind == 1) {
+#pragma unroll
+                    for (int i = 0; i < ROWS; ++i) {
+                        const int f = TilePlan::family(mb0, m, rs + 4 * (ROWS * gi + i), P.F);
+                        offa[i] = __ldg(P.counts + (size_t)op.leaf_a1 * P.F_pad + f) * P.Sp;
+                        offb[i] = __ldg(P.counts + (size_t)op.leaf_a2 * P.F_pad + f) * P.Sp;
+                    }
+                }
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    for (int kb = 0; kb < n_kblocks; ++kb) {
+                        mbar_wait(&ctl->empty[stage], phase ^ 1);
+                        if (op.a_kind == 1) {
+                            const uint32_t sA1 = smem_u32(stage_base + stage * STAGE_BYTES), sA2 = sA1 + A_BYTES;
+                            const int col0 = kb * BK + 2 * c;
+                            // sizes >= W are zero filled: the child vector has length W although the matrices are wider when S > W
+                            const int nbytes = max(0, min(16, (P.W - col0) * 8));
+#pragma unroll
+                            for (int i = 0; i < ROWS; ++i) {
+                                const int r = rs + 4 * (ROWS * gi + i);
+                                const uint32_t dst = r * 128 + ((c ^ (r & 7)) << 4);
+                                cp_async16(sA1 + dst, MTa + offa[i] + col0, nbytes);
+                                cp_async16(sA2 + dst, MTb + offb[i] + col0, nbytes);
+                            }
+                            cp_async_arrive_noinc(&ctl->full[stage]);
+                        } else {
+                            mbar_arrive(&ctl->full[stage]);
+                        }
+                        advance(stage, phase);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ================================ epilogue manager (1 warp) ================================ ================================
+template <bool PROF>
+__device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Params& P, unsigned char* Cbuf, Ctl* ctl) {
+    const TilePlan plan(P);
+    const int lane = threadIdx.x & 31;
+    const int scratch_row0 = blockIdx.x * 2 * P.n_slots * TILE_M;
+    const uint32_t sC = smem_u32(Cbuf);
+    uint32_t item = 0;
+    int ops_done_base = 0;
+    const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
+    long long t_prep = 0, t_wait_cdone = 0, t_store = 0;
+    const long long t_begin = prof ? clock64() : 0;
+    for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        for (int oi = 0; oi < P.n_ops; ++oi) {
+            const Op op = P.ops[oi];
+            const int r0 = op.is_root ? P.root_min : 0;
+            const int nrows = op.is_root ? P.R : P.W;
+            const int n_chunks = (nrows + TN - 1) / TN;
+            const bool reduce_now = op.is_root && op.other_kind != 0;
+            const double* __restrict__ MTo = P.MT + (size_t)op.key_o * P.Sp * P.Sp;
+            for (int h = 0; h < 2; ++h) {
+                int mb0, m;
+                if (!plan.tile(2 * pair + h, mb0, m)) continue;
+                if (op.other_kind == 1) {
+                    __syncwarp();
+                    for (int r = lane; r < TILE_M; r += 32) {
+                        const int f = TilePlan::family(mb0, m, r, P.F);
+                        ctl->rowoff_o[r] = __ldg(P.counts + (size_t)op.leaf_o * P.F_pad + f) * P.Sp;
+                    }
+                    __syncwarp();
+                }
+                const int out_row = scratch_row0 + (h * P.n_slots + op.out_slot) * TILE_M;
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    const int nbx = min(C_BOXES, (P.Vp - ch * TN) / BK);  // boxes of this pass inside the vector
+                    const long long tc0 = prof ? clock64() : 0;
+                    // ---- stage the sibling factor of this pass in the C tile ----
+                    if (op.other_kind == 2) {
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(&ctl->c_ready, nbx * C_BOX_BYTES);
+                            for (int b = 0; b < nbx; ++b)
+                                tma_load_2d(Cbuf + b * C_BOX_BYTES, tmA, ch * TN + b * BK, out_row, &ctl->c_ready);
+                        } else {
+                            mbar_arrive(&ctl->c_ready);
+                        }
+                    } else if (op.other_kind == 1) {
+                        // leaf sibling (cafe_tree.c:204-210): row `count` of the transposed matrix, sizes r0 + pass
+                        const int gc0 = r0 + ch * TN;
+                        if ((r0 & 1) == 0) {
+                            const int cj = lane & 7, rs = lane >> 3;
+                            for (int b = 0; b < nbx; ++b) {
+                                const int col = gc0 + b * BK + 2 * cj;
+                                const bool in = col < P.Sp;
+                                const double* src0 = MTo + (in ? col : 0);
+#pragma unroll 4
+                                for (int i = 0; i < TILE_M / 4; ++i) {
+                                    const int r = rs + 4 * i;
+                                    cp_async16(sC + b * C_BOX_BYTES + r * 128 + ((cj ^ (r & 7)) << 4), src0 + ctl->rowoff_o[r], in ? 16 : 0);
+                                }
+                            }
+                        } else {  // odd first size (the root range starts at 1): rows are only 8-byte aligned
+                            const int cl = lane & 15, rs = lane >> 4;
+                            for (int b = 0; b < nbx; ++b) {
+                                const int col = gc0 + b * BK + cl;
+                                const bool in = col < P.Sp;
+                                const double* src0 = MTo + (in ? col : 0);
+#pragma unroll 4
+                                for (int i = 0; i < TILE_M / 2; ++i) {
+                                    const int r = rs + 2 * i;
+                                    cp_async8(sC + b * C_BOX_BYTES + r * 128 + (((cl >> 1) ^ (r & 7)) << 4) + ((cl & 1) << 3),
+                                              src0 + ctl->rowoff_o[r], in ? 8 : 0);
+                                }
+                            }
+                        }
+                        cp_async_arrive_noinc(&ctl->c_ready);
+                    } else {
+                        mbar_arrive(&ctl->c_ready);
+                    }
+                    // ---- the consumers multiply in place; then the tile goes back to the scratch slot ----
+                    const long long tc1 = prof ? clock64() : 0;
+                    mbar_wait(&ctl->c_done, item & 1);
+                    const long long tc2 = prof ? clock64() : 0;
+                    if (!reduce_now && lane == 0) {
+                        fence_proxy_async_smem();  // consumer writes (generic proxy, acquired above) -> TMA store (async proxy)
+                        for (int b = 0; b < nbx; ++b) tma_store_2d(tmA, ch * TN + b * BK, out_row, Cbuf + b * C_BOX_BYTES);
+                        bulk_commit();
+                        bulk_wait_all();  // the C tile is free again and the slot is written
+                    }
+                    __syncwarp();
+                    if (ch == n_chunks - 1 && lane == 0) {
+                        __threadfence();
+                        ctl->done[h] = ops_done_base + oi + 1;
+                    }
+                    ++item;
+                    if (prof) { const long long tc3 = clock64(); t_prep += tc1 - tc0; t_wait_cdone += tc2 - tc1; t_store += tc3 - tc2; }
+                }
+            }
+        }
+        ops_done_base += P.n_ops;
+    }
+    if (prof && lane == 0) {
+        long long* o = P.warp_prof + (N_CONSUMER_WARPS + 3) * 8;
+        o[0] = clock64() - t_begin; o[1] = t_prep; o[2] = t_wait_cdone; o[3] = t_store; o[4] = item;
+    }
+}
+
+// ================================ warps 0..7: DMMA consumers ================================
+// One k4-step of the warp tile: 4 B fragments, then per 8-family block one A fragment and 4 DMMAs.
+template <int MBV, bool CHERRY>
+__device__ __forceinline__ void kstep(double (&acc)[MB][NB][2], const unsigned char* sA, const unsigned char* sB, int off) {
+    double b[NB];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) b[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + off);
+#pragma unroll
+    for (int mb = 0; mb < MBV; ++mb) {
+        double a = *reinterpret_cast<const double*>(sA + mb * 1024 + off);
+        if (CHERRY) a = __dmul_rn(a, *reinterpret_cast<const double*>(sA + A_BYTES + mb * 1024 + off));
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], a, b[nb]);
+    }
+}
+
+// K loop of one pass: consume n_kblocks ring stages.  MBV == 0: this warp has no work in the tile, it only keeps the ring moving.
+template <int MBV, bool CHERRY>
+__device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned char* stage_base, Ctl* ctl, uint32_t& stage,
+                                             uint32_t& phase, int n_kblocks, int tail_steps, int grp, int nw, int lane, int pg, int q,
+                                             bool prof, long long& t_wait_full) {
+    const int off0 = pg * 128 + ((q & 1) << 3);
+    const int hi = q >> 1;
+    for (int kb = 0; kb < n_kblocks; ++kb) {
+        if (prof) {
+            const long long t0 = clock64();
+            mbar_wait(&ctl->full[stage], phase);
+            t_wait_full += clock64() - t0;
+        } else {
+            mbar_wait(&ctl->full[stage], phase);
+        }
+        if (MBV > 0) {
+            const unsigned char* sA = stage_base + stage * STAGE_BYTES + grp * (HM * 128);
+            const unsigned char* sB = stage_base + stage * STAGE_BYTES + 2 * A_BYTES + nw * WCOLS * 128;
+            if (kb + 1 < n_kblocks || tail_steps == 4) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) kstep<MBV, CHERRY>(acc, sA, sB, off0 + (((2 * kk + hi) ^ pg) << 4));
+            } else {
+                for (int kk = 0; kk < tail_steps; ++kk) kstep<MBV, CHERRY>(acc, sA, sB, off0 + (((2 * kk + hi) ^ pg) << 4));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl->empty[stage]);
+        advance(stage, phase);
+    }
+}
+
+template <bool PROF>
+__device__ __forceinline__ void consumer_main(const Params& P, unsigned char* stage_base, unsigned char* Cbuf, Ctl* ctl) {
+    const TilePlan plan(P);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = warp >> 2, nw = warp & 3;
+    const int g = lane >> 2, q = lane & 3;
+    const int pg = mma_row_perm(g);
+    const int pc0 = mma_row_perm(2 * q), pc1 = mma_row_perm(2 * q + 1);
+    const int n_kblocks = (P.W + BK - 1) / BK;
+    const int tail_steps = ((P.W - (n_kblocks - 1) * BK) + 3) >> 2;  // k4-steps of the last K block (1..4)
+
+    // Byte offsets of this lane's two accumulator columns inside a C box, for even / odd 8-size blocks (128B swizzle).
+    // Lanes with odd g touch their columns in the opposite order: per instruction a half-warp then covers all eight
+    // 16-byte bank groups (rows 0,2,4,6 x columns {0,4,1,5} alone would hit only four of them).
+    const bool swp = (g & 1) != 0;
+    const int pcA = swp ? pc1 : pc0, pcB = swp ? pc0 : pc1;  // column of the first / second access
+    int coff[2][2];
+#pragma unroll
+    for (int par = 0; par < 2; ++par) {
+        coff[0][par] = pg * 128 + ((pcA & 1) << 3) + ((((par << 2) | (pcA >> 1)) ^ pg) << 4);
+        coff[1][par] = pg * 128 + ((pcB & 1) << 3) + ((((par << 2) | (pcB >> 1)) ^ pg) << 4);
+    }
+    unsigned char* cwarp = Cbuf + (nw * 2) * C_BOX_BYTES + (grp * HM) * 128;
+
+    // debug profile (CTA 0): cycles waiting for ring stages / in K loops / waiting for the C tile / in epilogues
+    const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
+    long long t_wait_full = 0, t_kloop = 0, t_wait_c = 0, t_epi = 0, t_epi_root = 0, t_epi_k0 = 0, t_sync = 0;
+    const long long t_begin = prof ? clock64() : 0;
+
+    uint32_t stage = 0, phase = 0, item = 0;
+    for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        for (int oi = 0; oi < P.n_ops; ++oi) {
+            const Op op = P.ops[oi];
+            const int nrows = op.is_root ? P.R : P.W;
+            const int n_chunks = (nrows + TN - 1) / TN;
+            const bool reduce_now = op.is_root && op.other_kind != 0;
+            for (int h = 0; h < 2; ++h) {
+                int mb0, m;
+                if (!plan.tile(2 * pair + h, mb0, m)) continue;
+                const int mbv = TilePlan::mbv(m, grp);
+                const int f0 = (mb0 + TilePlan::pre(m, grp)) * 8;
+                // running root reduction of one family row of this group, owned by the group's first HM threads
+                double run_ml = -1.0, run_mp = -INFINITY; int run_am = 0x7fffffff;
+
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    const int n0 = ch * TN + nw * WCOLS;  // first output size of this warp
+                    const int mbw = (n0 < nrows) ? mbv : 0;
+                    double acc[MB][NB][2];
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+
+ const long long tk0 = prof ? clock64() : 0;
+#define CAFE_K(MBV_)                                                                                                   \
+    if (op.a_kind == 1) gemm_kblocks<MBV_, true>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full); \
+    else gemm_kblocks<MBV_, false>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full);
+                    switch (mbw) {
+                        case 6: CAFE_K(6) break;
+                        case 5: CAFE_K(5) break;
+                        case 4: CAFE_K(4) break;
+                        case 3: CAFE_K(3) break;
+                        case 2: CAFE_K(2) break;
+                        case 1: CAFE_K(1) break;
+                        default: gemm_kblocks<0, false>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full); break;
+                    }
+#undef CAFE_K
+                    const long long tk1 = prof ? clock64() : 0;
+
+                    // ---------------- epilogue of this pass: C = acc * C in shared memory ----------------
+                    mbar_wait(&ctl->c_ready, item & 1);
+                    const long long tk2 = prof ? clock64() : 0;
+                    if (!reduce_now) {
+#pragma unroll
+                        for (int mb = 0; mb < MB; ++mb) {
+                            if (mb < mbw) {
+                                // all eight factors of this 8-family block first, then the products, then the stores
+                                // (shared-memory pointers may alias for the compiler: written out explicitly)
+                                double fac[NB][2];
+#pragma unroll
+                                for (int nb = 0; nb < NB; ++nb) {
+                                    fac[nb][0] = 1.0; fac[nb][1] = 1.0;
+                                    if (op.other_kind != 0) {
+                                        fac[nb][0] = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[0][nb & 1]);
+                                        fac[nb][1] = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[1][nb & 1]);
+                                    }
+                                }
+                                double out[NB][2];
+#pragma unroll
+                                for (int nb = 0; nb < NB; ++nb) {
+                                    const double v0 = swp ? acc[mb][nb][1] : acc[mb][nb][0], v1 = swp ? acc[mb][nb][0] : acc[mb][nb][1];
+                                    // sizes >= nrows stay exact zeros: matrix rows in [W, S) are not zero when S > W
+                                    out[nb][0] = (n0 + nb * 8 + pcA < nrows) ? __dmul_rn(v0, fac[nb][0]) : 0.0;
+                                    out[nb][1] = (n0 + nb * 8 + pcB < nrows) ? __dmul_rn(v1, fac[nb][1]) : 0.0;
+                                }
+#pragma unroll
+                                for (int nb = 0; nb < NB; ++nb) {
+                                    *reinterpret_cast<volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[0][nb & 1]) = out[nb][0];
+                                    *reinterpret_cast<volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[1][nb & 1]) = out[nb][1];
+                                }
+                            }
+                        }
+                        // no proxy fence here (MEMBAR.ALL.CTA drains every store of the warp, ~2k cycles with the DMMA pipe idle):
+                        // the arrive below releases the writes, the epilogue manager acquires them and fences before its TMA store
+                    } else {
+                        // root: L[i] = acc * other; max/argmax of L and max of log L + log prior (lambda.cpp:670-686)
+#pragma unroll
+                        for (int mb = 0; mb < MB; ++mb) {
+                            double ml = -1.0, mp = -INFINITY; int am = 0x7fffffff;
+                            const int row = mb * 8 + pg, f = f0 + row;
+                            if (mb < mbw && f < P.F) {
+#pragma unroll
+                                for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+                                    for (int hh = 0; hh < 2; ++hh) {
+                                        const int i = n0 + nb * 8 + (hh ? pcB : pcA);
+                                        if (i < nrows) {
+                                            const double fac = *reinterpret_cast<const double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[hh][nb & 1]);
+                                            const double v = __dmul_rn((hh != 0) != swp ? acc[mb][nb][1] : acc[mb][nb][0], fac);
+                                            if (P.Lroot_out) P.Lroot_out[(size_t)f * P.R + i] = v;
+                                            if (v > ml || (v == ml && i < am)) { ml = v; am = i; }
+                                            const double x = log(v) + P.logprior[i];
+                                            if (x > mp) mp = x;
+                                        }
+                                    }
+                                }
+                            }
+                            // the 4 lanes of a quad hold the same family row
+#pragma unroll
+                            for (int off = 1; off <= 2; off <<= 1) {
+                                double oml = __shfl_xor_sync(0xffffffffu, ml, off); int oam = __shfl_xor_sync(0xffffffffu, am, off);
+                                double omp = __shfl_xor_sync(0xffffffffu, mp, off);
+                                if (oml > ml || (oml == ml && oam < am)) { ml = oml; am = oam; }
+                                if (omp > mp) mp = omp;
+                            }
+                            if (q == 0) { ctl->red_ml[grp][nw][row] = ml; ctl->red_mp[grp][nw][row] = mp; ctl->red_am[grp][nw][row] = am; }
+                        }
+                    }
+                    const long long tk2b = prof ? clock64() : 0;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ctl->c_done);
+                    ++item;
+                    if (prof) {
+                        const long long tk3 = clock64(); t_kloop += tk1 - tk0; t_wait_c += tk2 - tk1; t_sync += tk3 - tk2b;
+                        if (reduce_now) t_epi_root += tk2b - tk2; else if (op.other_kind == 0) t_epi_k0 += tk2b - tk2; else t_epi += tk2b - tk2;
+                    }
+
+                    if (reduce_now) {
+                        group_bar(grp);
+                        if (nw * 32 + lane < HM) {  // the first HM threads of the group own one family row each
+                            const int row = nw * 32 + lane;
+                            for (int w = 0; w < 4; ++w) {
+                                double oml = ctl->red_ml[grp][w][row], omp = ctl->red_mp[grp][w][row]; int oam = ctl->red_am[grp][w][row];
+                                if (oml > run_ml || (oml == run_ml && oam < run_am)) { run_ml = oml; run_am = oam; }
+                                if (omp > run_mp) run_mp = omp;
+                            }
+                            const int f = f0 + row;
+                            if (ch == n_chunks - 1 && row < mbv * 8 && f < P.F) {
+                                // max_j exp(log L + log prior) == exp(max_j(log L + log prior)); its log is the family's term
+                                P.logpost[f] = log(exp(run_mp)); P.maxlik[f] = run_ml; P.argmax[f] = run_am;
+                            }
+                        }
+                        group_bar(grp);
+                    }
+                }
+            }
+        }
+    }
+    if (prof && lane == 0) {
+        long long* o = P.warp_prof + warp * 8;
+        o[0] = clock64() - t_begin; o[1] = t_kloop; o[2] = t_wait_full; o[3] = t_wait_c; o[4] = t_epi; o[5] = t_epi_root; o[6] = t_epi_k0; o[7] = t_sync;
+    }
+}
+
+template <bool PROF>
+__global__ void __launch_bounds__(THREADS, 1)
+k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* stage_base = smem;                       // NSTAGE x (A1 | A2 | B)
+    unsigned char* Cbuf = smem + NSTAGE * STAGE_BYTES;      // 8 boxes of 96 x 16
+    Ctl* ctl = reinterpret_cast<Ctl*>(Cbuf + C_BYTES);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&ctl->full[s], 1 + 32 * N_GATHER_WARPS); mbar_init(&ctl->empty[s], N_CONSUMER_WARPS); }
+        mbar_init(&ctl->c_ready, 32);
+        mbar_init(&ctl->c_done, N_CONSUMER_WARPS);
+        ctl->done[0] = ctl->done[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5;
+    if (warp >= N_CONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+        if (warp == N_CONSUMER_WARPS) { if ((threadIdx.x & 31) == 0) producer_main<PROF>(&tmA, &tmB, P, stage_base, ctl); }
+        else if (warp == N_CONSUMER_WARPS + 3) cmanager_main<PROF>(&tmA, P, Cbuf, ctl);
+        else gatherer_main(P, stage_base, ctl, warp - (N_CONSUMER_WARPS + 1));
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
+        long long t_start = 0;
+        if (P.cta_times && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+        consumer_main<PROF>(P, stage_base, Cbuf, ctl);
+        if (P.cta_times && threadIdx.x == 0) {
+            long long t_end; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const TilePlan plan(P);
+            long long* o = P.cta_times + (size_t)blockIdx.x * 4;
+            o[0] = smid; o[1] = t_start; o[2] = t_end; o[3] = plan.n_mb;
+        }
+    }
+}
+
+}  // namespace fused2
+
+// =================================================================================================
+// host side
+// =================================================================================================
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled2 get_encode_fn2() {
+    static PFN_encodeTiled2 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled2)p;
+    }
+    return fn;
+}
+
+struct Fused2State {
+    fused2::Op* d_ops = nullptr; int ops_cap = 0;
+    double* d_scratch = nullptr; size_t scratch_cap = 0;
+    bool attr_set = false;
+    std::vector<fused2::Op> ops;  // schedule of the current launch
+    int n_slots = 0;
+};
+static Fused2State& fstate2(cafe_gpu_ctx* ctx) {
+    if (!ctx->fused2_state) ctx->fused2_state = new Fused2State();
+    return *static_cast<Fused2State*>(ctx->fused2_state);
+}
+void fused2_release(cafe_gpu_ctx* ctx) {
+    if (!ctx->fused2_state) return;
+    Fused2State* s = static_cast<Fused2State*>(ctx->fused2_state);
+    cudaFree(s->d_ops); cudaFree(s->d_scratch);
+    delete s;
+    ctx->fused2_state = nullptr;
+}
+
+bool fused2_supported(const cafe_gpu_ctx* ctx) {
+    if (get_encode_fn2() == nullptr) return false;
+    if (ctx->n_leaves < 3) return false;                 // the root of a two-leaf tree is itself a leaf pair
+    if (ctx->max_count >= ctx->W) return false;          // a one-hot leaf outside the matvec columns needs the guarded path
+    for (int e : ctx->leaf_err) if (e >= 0) return false;  // error-model leaves are sparse row combinations (prune_fused.cu)
+    return true;
+}
+
+// Post-order schedule of the GEMMs.  A node whose two children are leaves ("cherry") never gets a vector slot; the needier
+// internal child is evaluated first (Sethi–Ullman), its slot is released as soon as its parent's GEMM is issued.
+static void build_schedule2(const cafe_gpu_ctx* ctx, Fused2State& st) {
+    using fused2::Op;
+    const int n = ctx->n_nodes;
+    auto is_leaf = [&](int v) { return ctx->left[v] < 0; };
+    auto is_cherry = [&](int v) { return !is_leaf(v) && is_leaf(ctx->left[v]) && is_leaf(ctx->right[v]); };
+    auto is_virtual = [&](int v) { return is_leaf(v) || is_cherry(v); };
+    std::vector<int> need(n, 0);
+    std::function<int(int)> calc = [&](int v) -> int {
+        if (is_virtual(v)) return need[v] = 0;
+        int a = calc(ctx->left[v]), b = calc(ctx->right[v]);
+        int hi = std::max(a, b), lo = std::min(a, b);
+        int k = std::max(hi, lo + (hi > 0 ? 1 : 0));
+        int live_children = (a > 0) + (b > 0);
+        return need[v] = std::max(k, live_children + 1);
+    };
+    calc(ctx->root);
+
+    st.ops.clear();
+    std::vector<int> free_slots;
+    int n_slots = 0;
+    auto alloc = [&]() {
+        if (!free_slots.empty()) { int s = free_slots.back(); free_slots.pop_back(); return s; }
+        return n_slots++;
+    };
+    auto gemm_over = [&](Op& op, int child, int slot) {  // the GEMM operand: a stored vector or a leaf pair
+        op.key = ctx->node_key[child];
+        if (is_cherry(child)) {
+            const int a = ctx->left[child], b = ctx->right[child];
+            op.a_kind = 1; op.in_slot = 0;
+            op.leaf_a1 = a / 2; op.key_a1 = ctx->node_key[a];
+            op.leaf_a2 = b / 2; op.key_a2 = ctx->node_key[b];
+        } else {
+            op.a_kind = 0; op.in_slot = slot;
+        }
+    };
+    std::function<int(int)> eval = [&](int v) -> int {  // returns the slot of v's vector (v internal, not a cherry)
+        const int a = ctx->left[v], b = ctx->right[v];
+        Op op{};
+        op.is_root = (v == ctx->root);
+        if (is_leaf(a) != is_leaf(b)) {
+            const int gch = is_leaf(a) ? b : a, l = is_leaf(a) ? a : b;
+            const int sg = is_cherry(gch) ? -1 : eval(gch);
+            op.out_slot = alloc();
+            gemm_over(op, gch, sg);
+            op.other_kind = 1; op.leaf_o = l / 2; op.key_o = ctx->node_key[l];
+            st.ops.push_back(op);
+            if (sg >= 0) free_slots.push_back(sg);
+            return op.out_slot;
+        }
+        // two internal children
+        const int first = need[a] >= need[b] ? a : b, second = (first == a) ? b : a;
+        const int s1 = is_cherry(first) ? -1 : eval(first);
+        const int s2 = is_cherry(second) ? -1 : eval(second);
+        op.out_slot = alloc();
+        gemm_over(op, first, s1);
+        op.other_kind = 0;
+        st.ops.push_back(op);
+        if (s1 >= 0) free_slots.push_back(s1);
+        Op op2{};
+        op2.is_root = op.is_root; op2.out_slot = op.out_slot;
+        gemm_over(op2, second, s2);
+        op2.other_kind = 2;
+        st.ops.push_back(op2);
+        if (s2 >= 0) free_slots.push_back(s2);
+        return op.out_slot;
+    };
+    eval(ctx->root);
+    st.n_slots = std::max(1, n_slots);
+}
+
+int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
+    using namespace fused2;
+    Fused2State& st = fstate2(ctx);
+    PFN_encodeTiled2 encode = get_encode_fn2();
+    if (!encode) CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+
+    // ---- schedule (a few hundred host instructions; the keys of the branches change with every rate vector) ----
+    build_schedule2(ctx, st);
+    if ((int)st.ops.size() > st.ops_cap) {
+        cudaFree(st.d_ops); st.d_ops = nullptr;
+        st.ops_cap = std::max<int>((int)st.ops.size(), 2 * ctx->n_nodes);
+        CAFE_CK(ctx, cudaMalloc(&st.d_ops, st.ops_cap * sizeof(Op)));
+    }
+    CAFE_CK(ctx, cudaMemcpyAsync(st.d_ops, st.ops.data(), st.ops.size() * sizeof(Op), cudaMemcpyHostToDevice, ctx->stream));
+
+    // ---- geometry: one CTA per SM, every CTA at least two 8-family blocks ----
+    const int n_mblocks = (ctx->F + 7) / 8;
+    const int grid = std::max(1, std::min(ctx->sm_count, (n_mblocks + 1) / 2));
+    const size_t scratch_doubles = (size_t)grid * 2 * st.n_slots * TILE_M * ctx->Vp;
+    if (scratch_doubles > st.scratch_cap) {
+        cudaFree(st.d_scratch); st.d_scratch = nullptr;
+        CAFE_CK(ctx, cudaMalloc(&st.d_scratch, scratch_doubles * sizeof(double)));
+        CAFE_CK(ctx, cudaMemsetAsync(st.d_scratch, 0, scratch_doubles * sizeof(double), ctx->stream));
+        st.scratch_cap = scratch_doubles;
+    }
+
+    // ---- tensor maps (SWIZZLE_128B, zero OOB fill) ----
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)ctx->Vp, (cuuint64_t)grid * 2 * st.n_slots * TILE_M};
+        cuuint64_t strides[1] = {(cuuint64_t)ctx->Vp * sizeof(double)};
+        cuuint32_t box[2] = {BK, TILE_M};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, st.d_scratch, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) CAFE_FAIL(ctx, CAFE_GPU_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r));
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)ctx->Sp, (cuuint64_t)ctx->Sp, (cuuint64_t)ctx->mat_cap};
+        cuuint64_t strides[2] = {(cuuint64_t)ctx->Sp * sizeof(double), (cuuint64_t)ctx->Sp * ctx->Sp * sizeof(double)};
+        cuuint32_t box[3] = {BK, TN, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ctx->d_M, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) CAFE_FAIL(ctx, CAFE_GPU_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r));
+    }
+
+    Params P{};
+    P.ops = st.d_ops; P.n_ops = (int)st.ops.size(); P.n_slots = st.n_slots; P.F = ctx->F; P.F_pad = ctx->F_pad;
+    P.W = ctx->W; P.R = ctx->R; P.root_min = ctx->root_min; P.Sp = ctx->Sp; P.Vp = ctx->Vp; P.n_mblocks = n_mblocks;
+    P.MT = ctx->d_MT; P.counts = ctx->d_counts; P.logprior = ctx->d_logprior;
+    P.logpost = ctx->d_logpost; P.maxlik = ctx->d_maxlik; P.argmax = ctx->d_argmax; P.Lroot_out = d_Lroot_out;
+
+    const size_t smem_bytes = (size_t)NSTAGE * STAGE_BYTES + C_BYTES + sizeof(Ctl) + 1024;
+    if (!st.attr_set) {
+        CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        st.attr_set = true;
+    }
+    const char* trace_path = std::getenv("CAFE_GPU_TRACE");
+    long long* d_trace = nullptr;
+    if (trace_path) {
+        CAFE_CK(ctx, cudaMalloc(&d_trace, ((size_t)grid * 4 + 128) * sizeof(long long)));
+        CAFE_CK(ctx, cudaMemsetAsync(d_trace, 0, ((size_t)grid * 4 + 128) * sizeof(long long), ctx->stream));
+        P.cta_times = d_trace;
+        P.warp_prof = d_trace + (size_t)grid * 4;
+    }
+    if (trace_path) k_prune_fused2<true><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
+    else k_prune_fused2<false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
+    ctx->launches++;
+    CAFE_CK(ctx, cudaGetLastError());
+    if (trace_path) {  // debug only: synchronous dump "cta <i> <smid> <start ns> <end ns> <8-family blocks>"
+        std::vector<long long> h((size_t)grid * 4 + 128);
+        CAFE_CK(ctx, cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_trace);
+        if (FILE* fp = std::fopen(trace_path, "w")) {
+            for (int c = 0; c < grid; ++c) std::fprintf(fp, "cta %d %lld %lld %lld %lld\n", c, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+            // consumers: total, K loops, wait ring, wait C tile, epilogue (factor), epilogue (root), epilogue (no factor), sync | producer: total, wait done, wait empty
+            // epilogue manager: total, prep, wait consumers, store, items            (cycles, CTA 0)
+            for (int w = 0; w < 16; ++w) {
+                const long long* o = &h[(size_t)grid * 4 + w * 8];
+                std::fprintf(fp, "warp %d %lld %lld %lld %lld %lld %lld %lld %lld\n", w, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+            }
+            std::fclose(fp);
+        }
+    }
+    return CAFE_GPU_OK;
+}

@@ -198,3 +198,80 @@ def test_k2_large_ranges_config2_shape_sample():
     p = Problem(nw, counts, lam)
     assert p.ranges == (0, 250, 1, 250)
     check_problem(p)
+
+
+def _tree_depth(ot):
+    depth, v = 0, 0
+    while ot.parent[v] >= 0:
+        depth += ot.branchlength[v]
+        v = ot.parent[v]
+    return depth
+
+
+def test_k2_root_range_wider_than_vector_lambdamu():
+    # S > W with W % 4 != 0 (the geometry init_family_size produces for max size > 200), cheap sizes: W=61, R=80, S=81
+    nw = random_tree(13, 4)
+    ot = oracle.parse_newick(nw)
+    lam = 0.25 / _tree_depth(ot)
+    mu = 0.8 * lam
+    counts = small_counts(13, 100, 55, 21)
+    p = Problem(nw, counts, lam, mu=mu, ranges=(0, 60, 1, 80))
+    check_problem(p)
+    p = Problem(nw, counts, lam, mu=mu, ranges=(0, 62, 3, 97))
+    check_problem(p)
+
+
+def test_k2_config3_shape_lambdamu_sample():
+    # config-3 geometry: max size 400 -> W=481, R=500, S=501, lambda and mu free.  Two distinct branch lengths only, so
+    # that the CPU oracle's S=501 matrices (3-4 s each) stay affordable; the 50-taxon topology is covered at small S.
+    nw = "(((A:3,B:3):3,(C:3,D:3):3):3,((E:3,F:3):3,G:6):3)"
+    lam, mu = 0.012, 0.009
+    rng = np.random.RandomState(12)
+    base = np.r_[rng.randint(1, 60, 36), 300, 380, 399, 400].reshape(-1, 1)
+    counts = np.clip(base + rng.randint(-3, 4, size=(40, 7)), 0, 400).astype(np.int32)
+    counts[-1, 0] = 400
+    p = Problem(nw, counts, lam, mu=mu)
+    assert p.ranges == (0, 480, 1, 500)
+    check_problem(p)
+
+
+def test_k2_100_taxa_four_classes_error_model():
+    # config-4 topology: 100 taxa, 4 lambda classes on branch subsets, error model on every leaf (small sizes: S=91)
+    nw = random_tree(100, 1)
+    ot = oracle.parse_newick(nw)
+    lam0 = 0.25 / _tree_depth(ot)
+    n = ot.n_nodes
+    counts = simulate_families(ot, [lam0] * n, [-1] * n, 90, 40, np.arange(1, 30), 13)
+    counts = np.minimum(counts, 40)
+    counts[0, 0] = 40
+    rg = chost.init_family_size(40)
+    E = _band_error_matrix(rg["max"] + 1, 0.0274)
+    p = Problem(nw, counts, lam0, err={k: E for k in range(100)})
+    # what cafe_shell_set_lambdas leaves on the nodes for `lambda -t` with classes 1..4
+    p.lam_node = np.array([lam0, 1.3 * lam0, 0.7 * lam0, 1.1 * lam0])[np.arange(n) % 4]
+    assert p.ranges == (0, 90, 1, 50)
+    check_problem(p)
+
+
+def test_k2_config4_shape_error_model_sample():
+    # config-4 sizes (max size 200 -> S=251) with the error model, on the 5-taxon example tree with 2 classes
+    rng = np.random.RandomState(14)
+    base = np.r_[rng.randint(1, 50, 28), 120, 180, 199, 200].reshape(-1, 1)
+    counts = np.clip(base + rng.randint(-2, 3, size=(32, 5)), 0, 200).astype(np.int32)
+    counts[-1, 0] = 200
+    rg = chost.init_family_size(200)
+    E = _band_error_matrix(rg["max"] + 1, 0.0274)
+    p = Problem(EXAMPLE_TREE, counts, [0.002, 0.003], lambda_tree="(((2,2)1,(1,1)1)1,1)", err={k: E for k in range(5)})
+    assert p.ranges == (0, 250, 1, 250)
+    check_problem(p)
+
+
+def _band_error_matrix(dim, eps):
+    E = np.zeros((dim, dim))
+    for j in range(dim):
+        for d, v in ((-1, eps), (0, 1 - 2 * eps), (1, eps)):
+            if 0 <= j + d < dim:
+                E[j + d, j] = v
+    E[0, 0] = 1 - eps
+    E[dim - 1, dim - 1] = 1 - eps
+    return E
