@@ -57,7 +57,7 @@ void cafe_gpu_destroy(cafe_gpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_lnc); cudaFree(ctx->d_lncT); cudaFree(ctx->d_counts); cudaFree(ctx->d_mult); cudaFree(ctx->d_first);
-    cudaFree(ctx->d_logprior); cudaFree(ctx->d_keyparams); cudaFree(ctx->d_M); cudaFree(ctx->d_MT); cudaFree(ctx->d_vec);
+    cudaFree(ctx->d_logprior); cudaFree(ctx->d_prior_mant); cudaFree(ctx->d_prior_exp); cudaFree(ctx->d_keyparams); cudaFree(ctx->d_M); cudaFree(ctx->d_MT); cudaFree(ctx->d_vec);
     cudaFree(ctx->d_logpost); cudaFree(ctx->d_maxlik); cudaFree(ctx->d_argmax); cudaFree(ctx->d_score);
     cudaFreeHost(ctx->h_score);
     free_err_models(ctx);
@@ -211,9 +211,22 @@ int cafe_gpu_set_prior(cafe_gpu_ctx* ctx, const double* prior, int len) {
     ctx->h_prior.assign(prior, prior + ctx->R);
     std::vector<double> lp(ctx->R);
     for (int i = 0; i < ctx->R; ++i) lp[i] = std::log(prior[i]);  // lambda.cpp:682
+    // prior = mant * 2^exp for the exact product compare of the fused root reduction (prune_fused2.cu)
+    std::vector<double> pm(ctx->R);
+    std::vector<int> pe(ctx->R);
+    for (int i = 0; i < ctx->R; ++i) {
+        if (prior[i] > 0 && std::isfinite(prior[i])) { int e; pm[i] = 2.0 * std::frexp(prior[i], &e); pe[i] = e - 1; }
+        else { pm[i] = 1.0; pe[i] = -(1 << 30); }
+    }
     cudaFree(ctx->d_logprior); ctx->d_logprior = nullptr;
+    cudaFree(ctx->d_prior_mant); ctx->d_prior_mant = nullptr;
+    cudaFree(ctx->d_prior_exp); ctx->d_prior_exp = nullptr;
     CAFE_CK(ctx, cudaMalloc(&ctx->d_logprior, ctx->R * sizeof(double)));
+    CAFE_CK(ctx, cudaMalloc(&ctx->d_prior_mant, ctx->R * sizeof(double)));
+    CAFE_CK(ctx, cudaMalloc(&ctx->d_prior_exp, ctx->R * sizeof(int)));
     CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_logprior, lp.data(), ctx->R * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_prior_mant, pm.data(), ctx->R * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_prior_exp, pe.data(), ctx->R * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->results_valid = false;
     return CAFE_GPU_OK;

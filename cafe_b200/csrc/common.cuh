@@ -101,6 +101,8 @@ struct cafe_gpu_ctx {
 
     // prior
     double* d_logprior = nullptr;  // [R] log(prior[i])
+    double* d_prior_mant = nullptr;  // [R] prior[i] = mant * 2^exp with mant in [1,2) (exact compare of L*prior, prune_fused2.cu)
+    int* d_prior_exp = nullptr;      // [R]
     std::vector<double> h_prior;
 
     // error models, per leaf (leaf order)
