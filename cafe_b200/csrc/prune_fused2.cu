@@ -73,6 +73,8 @@ struct Params {
     const double* MT;            // [D][Sp][Sp] transposed matrices
     const int* counts;           // [n_leaves][F_pad]
     const double* logprior;      // [R]
+    const double* prior_mant;    // [R] prior = mant * 2^exp, mant in [1,2)  (host frexp; exp = -2^30 where the prior is 0)
+    const int* prior_exp;        // [R]
     double* logpost;             // [F_pad]
     double* maxlik;
     int* argmax;
@@ -103,6 +105,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
+        : "memory");
+}
+// Same for the helper warps, which are never latency critical: a long suspend-time hint keeps them asleep in hardware instead
+// of re-polling every few dozen cycles next to the DMMA warps of their SM sub-partition.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -217,7 +234,7 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
                 for (int ch = 0; ch < n_chunks; ++ch) {
                     for (int kb = 0; kb < n_kblocks; ++kb) {
                         const long long t0 = prof ? clock64() : 0;
-                        mbar_wait(&ctl->empty[stage], phase ^ 1);
+                        mbar_wait_sleepy(&ctl->empty[stage], phase ^ 1);
                         if (prof) t_wait_empty += clock64() - t0;
                         unsigned char* sA = stage_base + stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&ctl->full[stage], op.a_kind == 0 ? A_BYTES + B_BYTES : B_BYTES);
@@ -268,7 +285,7 @@ __device__ __forceinline__ void gatherer_main(const Params& P, unsigned char* st
                 }
                 for (int ch = 0; ch < n_chunks; ++ch) {
                     for (int kb = 0; kb < n_kblocks; ++kb) {
-                        mbar_wait(&ctl->empty[stage], phase ^ 1);
+                        mbar_wait_sleepy(&ctl->empty[stage], phase ^ 1);
                         if (op.a_kind == 1) {
                             const uint32_t sA1 = smem_u32(stage_base + stage * STAGE_BYTES), sA2 = sA1 + A_BYTES;
                             const int col0 = kb * BK + 2 * c;
@@ -372,7 +389,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                     }
                     // ---- the consumers multiply in place; then the tile goes back to the scratch slot ----
                     const long long tc1 = prof ? clock64() : 0;
-                    mbar_wait(&ctl->c_done, item & 1);
+                    mbar_wait_sleepy(&ctl->c_done, item & 1);
                     const long long tc2 = prof ? clock64() : 0;
                     if (!reduce_now && lane == 0) {
                         fence_proxy_async_smem();  // consumer writes (generic proxy, acquired above) -> TMA store (async proxy)
@@ -399,49 +416,80 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
 }
 
 // ================================ warps 0..7: DMMA consumers ================================
-// One k4-step of the warp tile: 4 B fragments, then per 8-family block one A fragment and 4 DMMAs.
+// Fragments of one k4-step: 4 B fragments and one A fragment per 8-family block (a leaf pair's A is the product of two rows).
 template <int MBV, bool CHERRY>
-__device__ __forceinline__ void kstep(double (&acc)[MB][NB][2], const unsigned char* sA, const unsigned char* sB, int off) {
-    double b[NB];
+__device__ __forceinline__ void load_frags(double (&fa)[MB], double (&fb)[NB], const unsigned char* sA, const unsigned char* sB, int off) {
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) b[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + off);
+    for (int nb = 0; nb < NB; ++nb) fb[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + off);
 #pragma unroll
     for (int mb = 0; mb < MBV; ++mb) {
-        double a = *reinterpret_cast<const double*>(sA + mb * 1024 + off);
-        if (CHERRY) a = __dmul_rn(a, *reinterpret_cast<const double*>(sA + A_BYTES + mb * 1024 + off));
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], a, b[nb]);
+        fa[mb] = *reinterpret_cast<const double*>(sA + mb * 1024 + off);
+        if (CHERRY) fa[mb] = __dmul_rn(fa[mb], *reinterpret_cast<const double*>(sA + A_BYTES + mb * 1024 + off));
     }
 }
+template <int MBV>
+__device__ __forceinline__ void mma_frags(double (&acc)[MB][NB][2], const double (&fa)[MB], const double (&fb)[NB]) {
+#pragma unroll
+    for (int mb = 0; mb < MBV; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], fa[mb], fb[nb]);
+}
 
-// K loop of one pass: consume n_kblocks ring stages.  MBV == 0: this warp has no work in the tile, it only keeps the ring moving.
+// K loop of one pass: consume n_kblocks ring stages.  The fragments of the next k4-step are fetched before the DMMAs of the
+// current one, across the stage boundary too: the mbarrier wait of the next stage (~100 cycles even when it is already
+// full) and the first shared-memory loads hide behind the 24 DMMAs of the last step instead of idling the pipe.
+// MBV == 0: this warp has no work in the tile, it only keeps the ring moving.
 template <int MBV, bool CHERRY>
 __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned char* stage_base, Ctl* ctl, uint32_t& stage,
                                              uint32_t& phase, int n_kblocks, int tail_steps, int grp, int nw, int lane, int pg, int q,
                                              bool prof, long long& t_wait_full) {
     const int off0 = pg * 128 + ((q & 1) << 3);
     const int hi = q >> 1;
-    for (int kb = 0; kb < n_kblocks; ++kb) {
-        if (prof) {
-            const long long t0 = clock64();
+    const int a_off = grp * (HM * 128), b_off = 2 * A_BYTES + nw * WCOLS * 128;
+    if (MBV == 0) {
+        for (int kb = 0; kb < n_kblocks; ++kb) {
             mbar_wait(&ctl->full[stage], phase);
-            t_wait_full += clock64() - t0;
-        } else {
-            mbar_wait(&ctl->full[stage], phase);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->empty[stage]);
+            advance(stage, phase);
         }
-        if (MBV > 0) {
-            const unsigned char* sA = stage_base + stage * STAGE_BYTES + grp * (HM * 128);
-            const unsigned char* sB = stage_base + stage * STAGE_BYTES + 2 * A_BYTES + nw * WCOLS * 128;
-            if (kb + 1 < n_kblocks || tail_steps == 4) {
+        return;
+    }
+    double fa[2][MB], fb[2][NB];
+    {
+        const long long t0 = prof ? clock64() : 0;
+        mbar_wait(&ctl->full[stage], phase);
+        if (prof) t_wait_full += clock64() - t0;
+    }
+    const unsigned char* sbase = stage_base + stage * STAGE_BYTES;
+    load_frags<MBV, CHERRY>(fa[0], fb[0], sbase + a_off, sbase + b_off, off0 + ((hi ^ pg) << 4));
+    for (int kb = 0; kb < n_kblocks; ++kb) {
+        const bool last = kb + 1 == n_kblocks;
+        uint32_t nstage = stage, nphase = phase;
+        advance(nstage, nphase);
+        const unsigned char* nbase = stage_base + nstage * STAGE_BYTES;
+        if (!last || tail_steps == 4) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) kstep<MBV, CHERRY>(acc, sA, sB, off0 + (((2 * kk + hi) ^ pg) << 4));
-            } else {
-                for (int kk = 0; kk < tail_steps; ++kk) kstep<MBV, CHERRY>(acc, sA, sB, off0 + (((2 * kk + hi) ^ pg) << 4));
+            for (int kk = 0; kk < 4; ++kk) {
+                if (kk < 3) {
+                    load_frags<MBV, CHERRY>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sbase + a_off, sbase + b_off, off0 + (((2 * (kk + 1) + hi) ^ pg) << 4));
+                } else if (!last) {
+                    const long long t0 = prof ? clock64() : 0;
+                    mbar_wait(&ctl->full[nstage], nphase);
+                    if (prof) t_wait_full += clock64() - t0;
+                    load_frags<MBV, CHERRY>(fa[0], fb[0], nbase + a_off, nbase + b_off, off0 + ((hi ^ pg) << 4));
+                }
+                mma_frags<MBV>(acc, fa[kk & 1], fb[kk & 1]);
+            }
+        } else {  // last K block of the pass with fewer than 4 steps
+            for (int kk = 0; kk < tail_steps; ++kk) {
+                if (kk > 0) load_frags<MBV, CHERRY>(fa[0], fb[0], sbase + a_off, sbase + b_off, off0 + (((2 * kk + hi) ^ pg) << 4));
+                mma_frags<MBV>(acc, fa[0], fb[0]);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->empty[stage]);
-        advance(stage, phase);
+        stage = nstage; phase = nphase; sbase = nbase;
     }
 }
 
@@ -471,7 +519,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
 
     // debug profile (CTA 0): cycles waiting for ring stages / in K loops / waiting for the C tile / in epilogues
     const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
-    long long t_wait_full = 0, t_kloop = 0, t_wait_c = 0, t_epi = 0, t_epi_root = 0, t_epi_k0 = 0, t_sync = 0;
+    long long t_wait_full = 0, t_kloop = 0, t_wait_c = 0, t_epi = 0, t_epi_root = 0, t_epi_k0 = 0, t_kloop_cherry = 0;
     const long long t_begin = prof ? clock64() : 0;
 
     uint32_t stage = 0, phase = 0, item = 0;
@@ -550,12 +598,26 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         // no proxy fence here (MEMBAR.ALL.CTA drains every store of the warp, ~2k cycles with the DMMA pipe idle):
                         // the arrive below releases the writes, the epilogue manager acquires them and fences before its TMA store
                     } else {
-                        // root: L[i] = acc * other; max/argmax of L and max of log L + log prior (lambda.cpp:670-686)
+                        // root: L[i] = acc * other; max/argmax of L and max of log L + log prior (lambda.cpp:670-686).
+                        // log is monotonic, so among this lane's eight sizes of a family only the one with the largest product
+                        // L * prior can carry the maximum: the products are compared exactly as (exponent sum, mantissa product)
+                        // - no underflow - and ONE log is taken per lane and family instead of eight.  (Two products closer
+                        // than an ulp could swap; their log sums then differ by ~1e-16.)
+                        double pr_m[NB][2], pr_lp[NB][2]; int pr_e[NB][2];  // priors of this lane's 8 sizes, the same for every family
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int i = min(n0 + nb * 8 + (hh ? pcB : pcA), nrows - 1);
+                                pr_m[nb][hh] = __ldg(P.prior_mant + i); pr_e[nb][hh] = __ldg(P.prior_exp + i); pr_lp[nb][hh] = __ldg(P.logprior + i);
+                            }
+                        }
 #pragma unroll
                         for (int mb = 0; mb < MB; ++mb) {
                             double ml = -1.0, mp = -INFINITY; int am = 0x7fffffff;
                             const int row = mb * 8 + pg, f = f0 + row;
                             if (mb < mbw && f < P.F) {
+                                double best_m = 0.0, best_v = 0.0, best_lp = 0.0; int best_e = -0x7fffffff;
 #pragma unroll
                                 for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
@@ -566,11 +628,19 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                                             const double v = __dmul_rn((hh != 0) != swp ? acc[mb][nb][1] : acc[mb][nb][0], fac);
                                             if (P.Lroot_out) P.Lroot_out[(size_t)f * P.R + i] = v;
                                             if (v > ml || (v == ml && i < am)) { ml = v; am = i; }
-                                            const double x = log(v) + P.logprior[i];
-                                            if (x > mp) mp = x;
+                                            if (v > 0.0) {
+                                                double vs = v;
+                                                int hi32 = __double2hiint(vs), e = (hi32 >> 20) & 0x7ff;
+                                                if (e == 0) { vs *= 0x1p200; hi32 = __double2hiint(vs); e = ((hi32 >> 20) & 0x7ff) - 200; }
+                                                double pm = __hiloint2double((hi32 & 0x800fffff) | 0x3ff00000, __double2loint(vs)) * pr_m[nb][hh];
+                                                e += pr_e[nb][hh];
+                                                if (pm >= 2.0) { pm *= 0.5; ++e; }
+                                                if (e > best_e || (e == best_e && pm > best_m)) { best_e = e; best_m = pm; best_v = v; best_lp = pr_lp[nb][hh]; }
+                                            }
                                         }
                                     }
                                 }
+                                if (best_e != -0x7fffffff) mp = log(best_v) + best_lp;
                             }
                             // the 4 lanes of a quad hold the same family row
 #pragma unroll
@@ -588,7 +658,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     if (lane == 0) mbar_arrive(&ctl->c_done);
                     ++item;
                     if (prof) {
-                        const long long tk3 = clock64(); t_kloop += tk1 - tk0; t_wait_c += tk2 - tk1; t_sync += tk3 - tk2b;
+                        t_kloop += tk1 - tk0; t_wait_c += tk2 - tk1; if (op.a_kind == 1) t_kloop_cherry += tk1 - tk0;
                         if (reduce_now) t_epi_root += tk2b - tk2; else if (op.other_kind == 0) t_epi_k0 += tk2b - tk2; else t_epi += tk2b - tk2;
                     }
 
@@ -615,7 +685,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
     }
     if (prof && lane == 0) {
         long long* o = P.warp_prof + warp * 8;
-        o[0] = clock64() - t_begin; o[1] = t_kloop; o[2] = t_wait_full; o[3] = t_wait_c; o[4] = t_epi; o[5] = t_epi_root; o[6] = t_epi_k0; o[7] = t_sync;
+        o[0] = clock64() - t_begin; o[1] = t_kloop; o[2] = t_wait_full; o[3] = t_wait_c; o[4] = t_epi; o[5] = t_epi_root; o[6] = t_epi_k0; o[7] = t_kloop_cherry;
     }
 }
 
@@ -830,6 +900,7 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     P.ops = st.d_ops; P.n_ops = (int)st.ops.size(); P.n_slots = st.n_slots; P.F = ctx->F; P.F_pad = ctx->F_pad;
     P.W = ctx->W; P.R = ctx->R; P.root_min = ctx->root_min; P.Sp = ctx->Sp; P.Vp = ctx->Vp; P.n_mblocks = n_mblocks;
     P.MT = ctx->d_MT; P.counts = ctx->d_counts; P.logprior = ctx->d_logprior;
+    P.prior_mant = ctx->d_prior_mant; P.prior_exp = ctx->d_prior_exp;
     P.logpost = ctx->d_logpost; P.maxlik = ctx->d_maxlik; P.argmax = ctx->d_argmax; P.Lroot_out = d_Lroot_out;
 
     const size_t smem_bytes = (size_t)NSTAGE * STAGE_BYTES + C_BYTES + sizeof(Ctl) + 1024;
@@ -857,7 +928,7 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
         cudaFree(d_trace);
         if (FILE* fp = std::fopen(trace_path, "w")) {
             for (int c = 0; c < grid; ++c) std::fprintf(fp, "cta %d %lld %lld %lld %lld\n", c, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
-            // consumers: total, K loops, wait ring, wait C tile, epilogue (factor), epilogue (root), epilogue (no factor), sync | producer: total, wait done, wait empty
+            // consumers: total, K loops, wait ring, wait C tile, epilogue (factor), epilogue (root), epilogue (no factor), K loops of leaf-pair items | producer: total, wait done, wait empty
             // epilogue manager: total, prep, wait consumers, store, items            (cycles, CTA 0)
             for (int w = 0; w < 16; ++w) {
                 const long long* o = &h[(size_t)grid * 4 + w * 8];
