@@ -50,8 +50,8 @@ constexpr int N_CONSUMER_WARPS = 4 * GM;
 constexpr int THREADS = (N_CONSUMER_WARPS + 4) * 32;
 constexpr int MB = HM / 8, NB = 4, WCOLS = NB * 8;
 constexpr int N_GATHER_WARPS = 2;
-// register re-partition of the 384 x 168 launch allocation: 8*32*200 + 4*32*104 = 64512
-constexpr int REGS_CONSUMER = 200, REGS_AUX = 104;
+// register re-partition of the 384 x 168 launch allocation: 8*32*192 + 4*32*120 = 64512
+constexpr int REGS_CONSUMER = 192, REGS_AUX = 120;
 
 struct Op {              // one GEMM of the post-order schedule (a tree edge below an internal node)
     int is_root;
@@ -81,6 +81,7 @@ struct Params {
     double* Lroot_out;           // nullable, [F][R]
     long long* cta_times;        // nullable debug: [grid][4] = smid, start ns, end ns, 8-family blocks
     long long* warp_prof;        // nullable debug: CTA 0, [16 warps][8] cycle sums (see consumer_main / producer_main)
+    long long* timeline;         // nullable debug: CTA 0, warps 0 and 4 (one sub-partition): [2][1024 items][4] clock stamps
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -155,19 +156,22 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
+constexpr int OPFLAGS_CAP = 1024;
 struct Ctl {
-    uint64_t full[NSTAGE];       // producer expect_tx + 32 gatherer lanes
-    uint64_t empty[NSTAGE];      // 12 consumer warps
+    uint64_t full[NSTAGE];       // producer expect_tx + 64 gatherer lanes
+    uint64_t empty[NSTAGE];      // 8 consumer warps
     uint64_t c_ready;            // 32 lanes of the epilogue manager (+ TMA bytes)
-    uint64_t c_done;             // 12 consumer warps
+    uint64_t c_done;             // 8 consumer warps
     volatile int done[2];        // finished (stored, visible) ops per tile of the pair
-    int rowoff_o[TILE_M];                    // epilogue manager: count * Sp of the leaf sibling
+    int rowoff_o[TILE_M];        // epilogue manager: count * Sp of the leaf sibling, per tile row
+    int rowoff_a[TILE_M], rowoff_b[TILE_M];  // cherry gatherers: count * Sp of the two leaves (gatherer gi owns rows [48 gi, 48 gi + 48))
+    unsigned char opflags[OPFLAGS_CAP];  // per op: bit0 is_root, bit1 a_kind, bits 2-3 other_kind (what the consumers need)
     double red_ml[GM][4][HM];    // root reduction across the 4 N-warps of a group
     double red_mp[GM][4][HM];
     int red_am[GM][4][HM];
 };
+__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
 // This CTA's families: a contiguous range of 8-family blocks cut into an even number of tiles of <= 12 blocks;
 // tiles are processed two at a time (the op sequence of one interleaved with the other's) so that a vector is never
@@ -191,6 +195,12 @@ struct TilePlan {
     __device__ static int mbv(int m, int g) { return (m + GM - 1 - g) / GM; }
     __device__ static int pre(int m, int g) { return g == 0 ? 0 : mbv(m, 0); }
     // family of tile row r (clamped into [0, F) so that gathers of unused rows stay in bounds)
+    // family of tile row r, or -1 for a row without a family
+    __device__ static int family_or_neg(int mb0, int m, int r, int F) {
+        const int g = r / HM, lr = r - g * HM;
+        const int f = (mb0 + pre(m, g)) * 8 + lr;
+        return (lr < mbv(m, g) * 8 && f < F) ? f : -1;
+    }
     __device__ static int family(int mb0, int m, int r, int F) {
         const int g = r / HM, lr = r - g * HM;
         const int f = (mb0 + pre(m, g)) * 8 + lr;
@@ -254,9 +264,11 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
 }
 
 // ================================ cherry gatherers (2 warps) ================================
-// Wait for every ring slot (so that they can never run ahead of the ring) and, when the GEMM child is a leaf pair, fill A1/A2
-// with the gathered rows MT_a[count_a][k..k+16), MT_b[count_b][k..k+16) in the TMA's 128B-swizzle layout.  Gatherer gi owns the
-// tile rows rs + 4*i, i in [12*gi, 12*gi + 12): 8 lanes copy one 128-byte row segment, 4 rows per instruction.
+// Both wait for every ring slot (so that they can never run ahead of the ring); gatherer gi owns the tile rows rs + 4*i,
+// i in [12*gi, 12*gi + 12).  When the GEMM child is a leaf pair they build the child's K block in A1: the rows MT_a[count_a][k..k+16) and MT_b[count_b][k..k+16)
+// are copied with cp.async into A1 / A2 (the TMA's 128B-swizzle layout) and multiplied in place by the lane that copied
+// them - one product per element and pass instead of one per consumer warp (DMUL shares the fp64 pipe with DMMA).
+// 8 lanes copy one 128-byte row segment, 4 rows per instruction.
 __device__ __forceinline__ void gatherer_main(const Params& P, unsigned char* stage_base, Ctl* ctl, int gi) {
     const TilePlan plan(P);
     const int lane = threadIdx.x & 31;
@@ -274,32 +286,42 @@ __device__ __forceinline__ void gatherer_main(const Params& P, unsigned char* st
             for (int h = 0; h < 2; ++h) {
                 int mb0, m;
                 if (!plan.tile(2 * pair + h, mb0, m)) continue;
-                int offa[ROWS], offb[ROWS];
                 if (op.a_kind == 1) {
-#pragma unroll
-                    for (int i = 0; i < ROWS; ++i) {
-                        const int f = TilePlan::family(mb0, m, rs + 4 * (ROWS * gi + i), P.F);
-                        offa[i] = __ldg(P.counts + (size_t)op.leaf_a1 * P.F_pad + f) * P.Sp;
-                        offb[i] = __ldg(P.counts + (size_t)op.leaf_a2 * P.F_pad + f) * P.Sp;
+                    __syncwarp();
+                    for (int k = lane; k < 4 * ROWS; k += 32) {
+                        const int r = 4 * ROWS * gi + k;
+                        const int f = TilePlan::family(mb0, m, r, P.F);
+                        ctl->rowoff_a[r] = __ldg(P.counts + (size_t)op.leaf_a1 * P.F_pad + f) * P.Sp;
+                        ctl->rowoff_b[r] = __ldg(P.counts + (size_t)op.leaf_a2 * P.F_pad + f) * P.Sp;
                     }
+                    __syncwarp();
                 }
                 for (int ch = 0; ch < n_chunks; ++ch) {
                     for (int kb = 0; kb < n_kblocks; ++kb) {
                         mbar_wait_sleepy(&ctl->empty[stage], phase ^ 1);
-                        if (op.a_kind == 1) {
-                            const uint32_t sA1 = smem_u32(stage_base + stage * STAGE_BYTES), sA2 = sA1 + A_BYTES;
-                            const int col0 = kb * BK + 2 * c;
-                            // sizes >= W are zero filled: the child vector has length W although the matrices are wider when S > W
-                            const int nbytes = max(0, min(16, (P.W - col0) * 8));
+                        {
+                            if (op.a_kind == 1) {
+                                const uint32_t sA1 = smem_u32(stage_base + stage * STAGE_BYTES), sA2 = sA1 + A_BYTES;
+                                const int col0 = kb * BK + 2 * c;
+                                // sizes >= W are zero filled: the child vector has length W although the matrices are wider when S > W
+                                const int nbytes = max(0, min(16, (P.W - col0) * 8));
 #pragma unroll
-                            for (int i = 0; i < ROWS; ++i) {
-                                const int r = rs + 4 * (ROWS * gi + i);
-                                const uint32_t dst = r * 128 + ((c ^ (r & 7)) << 4);
-                                cp_async16(sA1 + dst, MTa + offa[i] + col0, nbytes);
-                                cp_async16(sA2 + dst, MTb + offb[i] + col0, nbytes);
+                                for (int i = 0; i < ROWS; ++i) {
+                                    const int r = rs + 4 * (ROWS * gi + i);
+                                    const uint32_t dst = r * 128 + ((c ^ (r & 7)) << 4);
+                                    cp_async16(sA1 + dst, MTa + ctl->rowoff_a[r] + col0, nbytes);
+                                    cp_async16(sA2 + dst, MTb + ctl->rowoff_b[r] + col0, nbytes);
+                                }
+                                asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+                                unsigned char* pA1 = stage_base + stage * STAGE_BYTES;
+#pragma unroll
+                                for (int i = 0; i < ROWS; ++i) {
+                                    const int r = rs + 4 * (ROWS * gi + i);
+                                    double2* d = reinterpret_cast<double2*>(pA1 + r * 128 + ((c ^ (r & 7)) << 4));
+                                    const double2 x = *d, y = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(d) + A_BYTES);
+                                    *d = make_double2(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y));
+                                }
                             }
-                            cp_async_arrive_noinc(&ctl->full[stage]);
-                        } else {
                             mbar_arrive(&ctl->full[stage]);
                         }
                         advance(stage, phase);
@@ -387,15 +409,30 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                     } else {
                         mbar_arrive(&ctl->c_ready);
                     }
-                    // ---- the consumers multiply in place; then the tile goes back to the scratch slot ----
+                    // ---- the consumers multiply in place ----
                     const long long tc1 = prof ? clock64() : 0;
                     mbar_wait_sleepy(&ctl->c_done, item & 1);
                     const long long tc2 = prof ? clock64() : 0;
-                    if (!reduce_now && lane == 0) {
-                        fence_proxy_async_smem();  // consumer writes (generic proxy, acquired above) -> TMA store (async proxy)
-                        for (int b = 0; b < nbx; ++b) tma_store_2d(tmA, ch * TN + b * BK, out_row, Cbuf + b * C_BOX_BYTES);
-                        bulk_commit();
-                        bulk_wait_all();  // the C tile is free again and the slot is written
+                    if (!reduce_now) {
+                        // ... then the tile goes back to the scratch slot
+                        if (lane == 0) {
+                            fence_proxy_async_smem();  // consumer writes (generic proxy, acquired above) -> TMA store (async proxy)
+                            for (int b = 0; b < nbx; ++b) tma_store_2d(tmA, ch * TN + b * BK, out_row, Cbuf + b * C_BOX_BYTES);
+                            bulk_commit();
+                            bulk_wait_all();  // the C tile is free again and the slot is written
+                        }
+                    } else {
+                        // ... or, at the root (reduced by the consumers), is only copied out on request
+                        const int ncols = min(TN, nrows - ch * TN);
+                        if (P.Lroot_out) {  // get_likelihoods (cafe_tree.c:325-329): rows copied out, lanes along the sizes
+                            for (int r = 0; r < TILE_M; ++r) {
+                                const int f = TilePlan::family_or_neg(mb0, m, r, P.F);
+                                if (f < 0) continue;
+                                for (int c = lane; c < ncols; c += 32)
+                                    P.Lroot_out[(size_t)f * P.R + ch * TN + c] =
+                                        *reinterpret_cast<const double*>(Cbuf + (c >> 4) * C_BOX_BYTES + r * 128 + ((((c & 15) >> 1) ^ (r & 7)) << 4) + ((c & 1) << 3));
+                            }
+                        }
                     }
                     __syncwarp();
                     if (ch == n_chunks - 1 && lane == 0) {
@@ -416,15 +453,14 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
 }
 
 // ================================ warps 0..7: DMMA consumers ================================
-// Fragments of one k4-step: 4 B fragments and one A fragment per 8-family block (a leaf pair's A is the product of two rows).
-template <int MBV, bool CHERRY>
+// Fragments of one k4-step: 4 B fragments and one A fragment per 8-family block.
+template <int MBV>
 __device__ __forceinline__ void load_frags(double (&fa)[MB], double (&fb)[NB], const unsigned char* sA, const unsigned char* sB, int off) {
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) fb[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + off);
 #pragma unroll
     for (int mb = 0; mb < MBV; ++mb) {
         fa[mb] = *reinterpret_cast<const double*>(sA + mb * 1024 + off);
-        if (CHERRY) fa[mb] = __dmul_rn(fa[mb], *reinterpret_cast<const double*>(sA + A_BYTES + mb * 1024 + off));
     }
 }
 template <int MBV>
@@ -439,7 +475,7 @@ __device__ __forceinline__ void mma_frags(double (&acc)[MB][NB][2], const double
 // current one, across the stage boundary too: the mbarrier wait of the next stage (~100 cycles even when it is already
 // full) and the first shared-memory loads hide behind the 24 DMMAs of the last step instead of idling the pipe.
 // MBV == 0: this warp has no work in the tile, it only keeps the ring moving.
-template <int MBV, bool CHERRY>
+template <int MBV>
 __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned char* stage_base, Ctl* ctl, uint32_t& stage,
                                              uint32_t& phase, int n_kblocks, int tail_steps, int grp, int nw, int lane, int pg, int q,
                                              bool prof, long long& t_wait_full) {
@@ -462,7 +498,7 @@ __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned 
         if (prof) t_wait_full += clock64() - t0;
     }
     const unsigned char* sbase = stage_base + stage * STAGE_BYTES;
-    load_frags<MBV, CHERRY>(fa[0], fb[0], sbase + a_off, sbase + b_off, off0 + ((hi ^ pg) << 4));
+    load_frags<MBV>(fa[0], fb[0], sbase + a_off, sbase + b_off, off0 + ((hi ^ pg) << 4));
     for (int kb = 0; kb < n_kblocks; ++kb) {
         const bool last = kb + 1 == n_kblocks;
         uint32_t nstage = stage, nphase = phase;
@@ -472,18 +508,18 @@ __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned 
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 if (kk < 3) {
-                    load_frags<MBV, CHERRY>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sbase + a_off, sbase + b_off, off0 + (((2 * (kk + 1) + hi) ^ pg) << 4));
+                    load_frags<MBV>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sbase + a_off, sbase + b_off, off0 + (((2 * (kk + 1) + hi) ^ pg) << 4));
                 } else if (!last) {
                     const long long t0 = prof ? clock64() : 0;
                     mbar_wait(&ctl->full[nstage], nphase);
                     if (prof) t_wait_full += clock64() - t0;
-                    load_frags<MBV, CHERRY>(fa[0], fb[0], nbase + a_off, nbase + b_off, off0 + ((hi ^ pg) << 4));
+                    load_frags<MBV>(fa[0], fb[0], nbase + a_off, nbase + b_off, off0 + ((hi ^ pg) << 4));
                 }
                 mma_frags<MBV>(acc, fa[kk & 1], fb[kk & 1]);
             }
         } else {  // last K block of the pass with fewer than 4 steps
             for (int kk = 0; kk < tail_steps; ++kk) {
-                if (kk > 0) load_frags<MBV, CHERRY>(fa[0], fb[0], sbase + a_off, sbase + b_off, off0 + (((2 * kk + hi) ^ pg) << 4));
+                if (kk > 0) load_frags<MBV>(fa[0], fb[0], sbase + a_off, sbase + b_off, off0 + (((2 * kk + hi) ^ pg) << 4));
                 mma_frags<MBV>(acc, fa[0], fb[0]);
             }
         }
@@ -519,37 +555,42 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
 
     // debug profile (CTA 0): cycles waiting for ring stages / in K loops / waiting for the C tile / in epilogues
     const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
-    long long t_wait_full = 0, t_kloop = 0, t_wait_c = 0, t_epi = 0, t_epi_root = 0, t_epi_k0 = 0, t_kloop_cherry = 0;
+    long long t_wait_full = 0, t_kloop = 0, t_wait_c = 0, t_epi = 0, t_epi_root = 0, t_kloop_cherry = 0;
     const long long t_begin = prof ? clock64() : 0;
 
     uint32_t stage = 0, phase = 0, item = 0;
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        // the two tiles of the pair: this group's 8-family blocks (everything else about a tile concerns the helper warps)
+        int mbv_h[2], f0_h[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int mb0 = 0, m = 0;
+            mbv_h[h] = plan.tile(2 * pair + h, mb0, m) ? TilePlan::mbv(m, grp) : -1;
+            f0_h[h] = (mb0 + TilePlan::pre(m, grp)) * 8;
+        }
         for (int oi = 0; oi < P.n_ops; ++oi) {
-            const Op op = P.ops[oi];
-            const int nrows = op.is_root ? P.R : P.W;
+            const int flags = ctl->opflags[oi];
+            const bool is_root = flags & 1;
+            const int other_kind = (flags >> 2) & 3;
+            const int nrows = is_root ? P.R : P.W;
             const int n_chunks = (nrows + TN - 1) / TN;
-            const bool reduce_now = op.is_root && op.other_kind != 0;
+            const bool reduce_now = is_root && other_kind != 0;
             for (int h = 0; h < 2; ++h) {
-                int mb0, m;
-                if (!plan.tile(2 * pair + h, mb0, m)) continue;
-                const int mbv = TilePlan::mbv(m, grp);
-                const int f0 = (mb0 + TilePlan::pre(m, grp)) * 8;
+                const int mbv_t = h ? mbv_h[1] : mbv_h[0], f0_t = h ? f0_h[1] : f0_h[0];
+                if (mbv_t < 0) continue;
                 // running root reduction of one family row of this group, owned by the group's first HM threads
                 double run_ml = -1.0, run_mp = -INFINITY; int run_am = 0x7fffffff;
-
                 for (int ch = 0; ch < n_chunks; ++ch) {
                     const int n0 = ch * TN + nw * WCOLS;  // first output size of this warp
-                    const int mbw = (n0 < nrows) ? mbv : 0;
+                    const int mbw = (n0 < nrows) ? mbv_t : 0;
                     double acc[MB][NB][2];
 #pragma unroll
                     for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
                         for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
 
- const long long tk0 = prof ? clock64() : 0;
-#define CAFE_K(MBV_)                                                                                                   \
-    if (op.a_kind == 1) gemm_kblocks<MBV_, true>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full); \
-    else gemm_kblocks<MBV_, false>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full);
+                    const long long tk0 = prof ? clock64() : 0;
+#define CAFE_K(MBV_) gemm_kblocks<MBV_>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full);
                     switch (mbw) {
                         case 6: CAFE_K(6) break;
                         case 5: CAFE_K(5) break;
@@ -557,7 +598,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         case 3: CAFE_K(3) break;
                         case 2: CAFE_K(2) break;
                         case 1: CAFE_K(1) break;
-                        default: gemm_kblocks<0, false>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full); break;
+                        default: CAFE_K(0) break;
                     }
 #undef CAFE_K
                     const long long tk1 = prof ? clock64() : 0;
@@ -565,44 +606,46 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     // ---------------- epilogue of this pass: C = acc * C in shared memory ----------------
                     mbar_wait(&ctl->c_ready, item & 1);
                     const long long tk2 = prof ? clock64() : 0;
-                    if (!reduce_now) {
 #pragma unroll
-                        for (int mb = 0; mb < MB; ++mb) {
-                            if (mb < mbw) {
-                                // all eight factors of this 8-family block first, then the products, then the stores
-                                // (shared-memory pointers may alias for the compiler: written out explicitly)
-                                double fac[NB][2];
+                    for (int mb = 0; mb < MB; ++mb) {
+                        if (mb < mbw) {
+                            // all eight factors of this 8-family block first, then the products, then the stores
+                            // (shared-memory pointers may alias for the compiler: written out explicitly)
+                            double fac[NB][2];
 #pragma unroll
-                                for (int nb = 0; nb < NB; ++nb) {
-                                    fac[nb][0] = 1.0; fac[nb][1] = 1.0;
-                                    if (op.other_kind != 0) {
-                                        fac[nb][0] = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[0][nb & 1]);
-                                        fac[nb][1] = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[1][nb & 1]);
-                                    }
-                                }
-                                double out[NB][2];
-#pragma unroll
-                                for (int nb = 0; nb < NB; ++nb) {
-                                    const double v0 = swp ? acc[mb][nb][1] : acc[mb][nb][0], v1 = swp ? acc[mb][nb][0] : acc[mb][nb][1];
-                                    // sizes >= nrows stay exact zeros: matrix rows in [W, S) are not zero when S > W
-                                    out[nb][0] = (n0 + nb * 8 + pcA < nrows) ? __dmul_rn(v0, fac[nb][0]) : 0.0;
-                                    out[nb][1] = (n0 + nb * 8 + pcB < nrows) ? __dmul_rn(v1, fac[nb][1]) : 0.0;
-                                }
-#pragma unroll
-                                for (int nb = 0; nb < NB; ++nb) {
-                                    *reinterpret_cast<volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[0][nb & 1]) = out[nb][0];
-                                    *reinterpret_cast<volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[1][nb & 1]) = out[nb][1];
+                            for (int nb = 0; nb < NB; ++nb) {
+                                fac[nb][0] = 1.0; fac[nb][1] = 1.0;
+                                if (other_kind != 0) {
+                                    fac[nb][0] = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[0][nb & 1]);
+                                    fac[nb][1] = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[1][nb & 1]);
                                 }
                             }
+                            double out[NB][2];
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) {
+                                const double v0 = swp ? acc[mb][nb][1] : acc[mb][nb][0], v1 = swp ? acc[mb][nb][0] : acc[mb][nb][1];
+                                // sizes >= nrows stay exact zeros: matrix rows in [W, S) are not zero when S > W
+                                out[nb][0] = (n0 + nb * 8 + pcA < nrows) ? __dmul_rn(v0, fac[nb][0]) : 0.0;
+                                out[nb][1] = (n0 + nb * 8 + pcB < nrows) ? __dmul_rn(v1, fac[nb][1]) : 0.0;
+                            }
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) {
+                                *reinterpret_cast<volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[0][nb & 1]) = out[nb][0];
+                                *reinterpret_cast<volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[1][nb & 1]) = out[nb][1];
+                            }
                         }
-                        // no proxy fence here (MEMBAR.ALL.CTA drains every store of the warp, ~2k cycles with the DMMA pipe idle):
-                        // the arrive below releases the writes, the epilogue manager acquires them and fences before its TMA store
-                    } else {
-                        // root: L[i] = acc * other; max/argmax of L and max of log L + log prior (lambda.cpp:670-686).
+                    }
+                    // no proxy fence here (MEMBAR.ALL.CTA would drain every store of the warp with the DMMA pipe idle): the arrive
+                    // below releases the writes, the epilogue manager acquires them and fences before its TMA store
+                    if (reduce_now) {
+                        // root: L[i] = acc * other; max / first argmax of L and max of log L + log prior (lambda.cpp:670-686).
                         // log is monotonic, so among this lane's eight sizes of a family only the one with the largest product
                         // L * prior can carry the maximum: the products are compared exactly as (exponent sum, mantissa product)
-                        // - no underflow - and ONE log is taken per lane and family instead of eight.  (Two products closer
-                        // than an ulp could swap; their log sums then differ by ~1e-16.)
+                        // - no underflow - and ONE log is taken per lane and family instead of eight (two products closer than an
+                        // ulp could swap; their log sums then differ by ~1e-16).  Comparisons on bit patterns: non-negative doubles
+                        // order like integers, and DSETP would queue behind the DMMAs of the other group on the fp64 pipe.
+                        // L is read back from the C tile (each lane reads what it just wrote): the accumulators are dead by now, which
+                        // keeps this rarely executed block out of the register budget of the K loops.
                         double pr_m[NB][2], pr_lp[NB][2]; int pr_e[NB][2];  // priors of this lane's 8 sizes, the same for every family
 #pragma unroll
                         for (int nb = 0; nb < NB; ++nb) {
@@ -614,28 +657,26 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         }
 #pragma unroll
                         for (int mb = 0; mb < MB; ++mb) {
-                            double ml = -1.0, mp = -INFINITY; int am = 0x7fffffff;
-                            const int row = mb * 8 + pg, f = f0 + row;
-                            if (mb < mbw && f < P.F) {
-                                double best_m = 0.0, best_v = 0.0, best_lp = 0.0; int best_e = -0x7fffffff;
+                            long long ml = -1, best_f = 0; double mp = -INFINITY, best_v = 0.0, best_lp = 0.0; int am = 0x7fffffff, best_e = -0x7fffffff;
+                            if (mb < mbw) {
 #pragma unroll
                                 for (int nb = 0; nb < NB; ++nb) {
 #pragma unroll
                                     for (int hh = 0; hh < 2; ++hh) {
                                         const int i = n0 + nb * 8 + (hh ? pcB : pcA);
                                         if (i < nrows) {
-                                            const double fac = *reinterpret_cast<const double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[hh][nb & 1]);
-                                            const double v = __dmul_rn((hh != 0) != swp ? acc[mb][nb][1] : acc[mb][nb][0], fac);
-                                            if (P.Lroot_out) P.Lroot_out[(size_t)f * P.R + i] = v;
-                                            if (v > ml || (v == ml && i < am)) { ml = v; am = i; }
-                                            if (v > 0.0) {
+                                            const double v = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[hh][nb & 1]);
+                                            const long long vb = __double_as_longlong(v);
+                                            if (vb > ml || (vb == ml && i < am)) { ml = vb; am = i; }
+                                            if (vb > 0) {
                                                 double vs = v;
                                                 int hi32 = __double2hiint(vs), e = (hi32 >> 20) & 0x7ff;
-                                                if (e == 0) { vs *= 0x1p200; hi32 = __double2hiint(vs); e = ((hi32 >> 20) & 0x7ff) - 200; }
-                                                double pm = __hiloint2double((hi32 & 0x800fffff) | 0x3ff00000, __double2loint(vs)) * pr_m[nb][hh];
-                                                e += pr_e[nb][hh];
-                                                if (pm >= 2.0) { pm *= 0.5; ++e; }
-                                                if (e > best_e || (e == best_e && pm > best_m)) { best_e = e; best_m = pm; best_v = v; best_lp = pr_lp[nb][hh]; }
+                                                if (e == 0) { vs = __dmul_rn(vs, 0x1p200); hi32 = __double2hiint(vs); e = ((hi32 >> 20) & 0x7ff) - 200; }
+                                                // mantissa product in [1,4): its own exponent bit joins the exponent sum, its fraction breaks ties
+                                                const long long pb = __double_as_longlong(__dmul_rn(__hiloint2double((hi32 & 0x000fffff) | 0x3ff00000, __double2loint(vs)), pr_m[nb][hh]));
+                                                e += pr_e[nb][hh] + (int)(pb >> 52);
+                                                const long long frac = pb & 0x000fffffffffffffLL;
+                                                if (e > best_e || (e == best_e && frac > best_f)) { best_e = e; best_f = frac; best_v = v; best_lp = pr_lp[nb][hh]; }
                                             }
                                         }
                                     }
@@ -645,34 +686,35 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                             // the 4 lanes of a quad hold the same family row
 #pragma unroll
                             for (int off = 1; off <= 2; off <<= 1) {
-                                double oml = __shfl_xor_sync(0xffffffffu, ml, off); int oam = __shfl_xor_sync(0xffffffffu, am, off);
-                                double omp = __shfl_xor_sync(0xffffffffu, mp, off);
+                                const long long oml = __shfl_xor_sync(0xffffffffu, ml, off); const int oam = __shfl_xor_sync(0xffffffffu, am, off);
+                                const double omp = __shfl_xor_sync(0xffffffffu, mp, off);
                                 if (oml > ml || (oml == ml && oam < am)) { ml = oml; am = oam; }
                                 if (omp > mp) mp = omp;
                             }
-                            if (q == 0) { ctl->red_ml[grp][nw][row] = ml; ctl->red_mp[grp][nw][row] = mp; ctl->red_am[grp][nw][row] = am; }
+                            const int row = mb * 8 + pg;
+                            if (q == 0) { ctl->red_ml[grp][nw][row] = __longlong_as_double(ml); ctl->red_mp[grp][nw][row] = mp; ctl->red_am[grp][nw][row] = am; }
                         }
                     }
                     const long long tk2b = prof ? clock64() : 0;
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&ctl->c_done);
                     ++item;
-                    if (prof) {
-                        t_kloop += tk1 - tk0; t_wait_c += tk2 - tk1; if (op.a_kind == 1) t_kloop_cherry += tk1 - tk0;
-                        if (reduce_now) t_epi_root += tk2b - tk2; else if (op.other_kind == 0) t_epi_k0 += tk2b - tk2; else t_epi += tk2b - tk2;
+                    if (prof && P.timeline && nw == 0 && lane == 0 && item <= 1024) {
+                        long long* tl = P.timeline + ((size_t)grp * 1024 + (item - 1)) * 4;
+                        tl[0] = tk0; tl[1] = tk1; tl[2] = tk2; tl[3] = tk2b;
                     }
-
+                    if (prof) { t_kloop += tk1 - tk0; t_wait_c += tk2 - tk1; t_epi += tk2b - tk2; if (flags & 2) t_kloop_cherry += tk1 - tk0; if (reduce_now) t_epi_root += tk2b - tk2; }
                     if (reduce_now) {
                         group_bar(grp);
                         if (nw * 32 + lane < HM) {  // the first HM threads of the group own one family row each
                             const int row = nw * 32 + lane;
                             for (int w = 0; w < 4; ++w) {
-                                double oml = ctl->red_ml[grp][w][row], omp = ctl->red_mp[grp][w][row]; int oam = ctl->red_am[grp][w][row];
+                                const double oml = ctl->red_ml[grp][w][row], omp = ctl->red_mp[grp][w][row]; const int oam = ctl->red_am[grp][w][row];
                                 if (oml > run_ml || (oml == run_ml && oam < run_am)) { run_ml = oml; run_am = oam; }
                                 if (omp > run_mp) run_mp = omp;
                             }
-                            const int f = f0 + row;
-                            if (ch == n_chunks - 1 && row < mbv * 8 && f < P.F) {
+                            const int f = f0_t + row;
+                            if (ch == n_chunks - 1 && row < mbv_t * 8 && f < P.F) {
                                 // max_j exp(log L + log prior) == exp(max_j(log L + log prior)); its log is the family's term
                                 P.logpost[f] = log(exp(run_mp)); P.maxlik[f] = run_ml; P.argmax[f] = run_am;
                             }
@@ -685,7 +727,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
     }
     if (prof && lane == 0) {
         long long* o = P.warp_prof + warp * 8;
-        o[0] = clock64() - t_begin; o[1] = t_kloop; o[2] = t_wait_full; o[3] = t_wait_c; o[4] = t_epi; o[5] = t_epi_root; o[6] = t_epi_k0; o[7] = t_kloop_cherry;
+        o[0] = clock64() - t_begin; o[1] = t_kloop; o[2] = t_wait_full; o[3] = t_wait_c; o[4] = t_epi; o[5] = t_epi_root; o[6] = 0; o[7] = t_kloop_cherry;
     }
 }
 
@@ -705,6 +747,10 @@ k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(&ctl->c_done, N_CONSUMER_WARPS);
         ctl->done[0] = ctl->done[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < P.n_ops; i += THREADS) {
+        const Op o = P.ops[i];
+        ctl->opflags[i] = (unsigned char)((o.is_root ? 1 : 0) | (o.a_kind << 1) | (o.other_kind << 2));
     }
     __syncthreads();
 
@@ -772,6 +818,7 @@ void fused2_release(cafe_gpu_ctx* ctx) {
 bool fused2_supported(const cafe_gpu_ctx* ctx) {
     if (get_encode_fn2() == nullptr) return false;
     if (ctx->n_leaves < 3) return false;                 // the root of a two-leaf tree is itself a leaf pair
+    if (ctx->n_nodes > fused2::OPFLAGS_CAP) return false;
     if (ctx->max_count >= ctx->W) return false;          // a one-hot leaf outside the matvec columns needs the guarded path
     for (int e : ctx->leaf_err) if (e >= 0) return false;  // error-model leaves are sparse row combinations (prune_fused.cu)
     return true;
@@ -912,28 +959,35 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     const char* trace_path = std::getenv("CAFE_GPU_TRACE");
     long long* d_trace = nullptr;
     if (trace_path) {
-        CAFE_CK(ctx, cudaMalloc(&d_trace, ((size_t)grid * 4 + 128) * sizeof(long long)));
-        CAFE_CK(ctx, cudaMemsetAsync(d_trace, 0, ((size_t)grid * 4 + 128) * sizeof(long long), ctx->stream));
+        CAFE_CK(ctx, cudaMalloc(&d_trace, ((size_t)grid * 4 + 128 + 8192) * sizeof(long long)));
+        CAFE_CK(ctx, cudaMemsetAsync(d_trace, 0, ((size_t)grid * 4 + 128 + 8192) * sizeof(long long), ctx->stream));
         P.cta_times = d_trace;
         P.warp_prof = d_trace + (size_t)grid * 4;
+        P.timeline = P.warp_prof + 128;
     }
     if (trace_path) k_prune_fused2<true><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
     else k_prune_fused2<false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
     ctx->launches++;
     CAFE_CK(ctx, cudaGetLastError());
     if (trace_path) {  // debug only: synchronous dump "cta <i> <smid> <start ns> <end ns> <8-family blocks>"
-        std::vector<long long> h((size_t)grid * 4 + 128);
+        std::vector<long long> h((size_t)grid * 4 + 128 + 8192);
         CAFE_CK(ctx, cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(d_trace);
         if (FILE* fp = std::fopen(trace_path, "w")) {
             for (int c = 0; c < grid; ++c) std::fprintf(fp, "cta %d %lld %lld %lld %lld\n", c, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
-            // consumers: total, K loops, wait ring, wait C tile, epilogue (factor), epilogue (root), epilogue (no factor), K loops of leaf-pair items | producer: total, wait done, wait empty
+            // consumers: total, K loops, wait ring, wait C tile, epilogues, root epilogues, -, K loops of leaf-pair items | producer: total, wait done, wait empty
             // epilogue manager: total, prep, wait consumers, store, items            (cycles, CTA 0)
             for (int w = 0; w < 16; ++w) {
                 const long long* o = &h[(size_t)grid * 4 + w * 8];
                 std::fprintf(fp, "warp %d %lld %lld %lld %lld %lld %lld %lld %lld\n", w, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
             }
+            // per pass of warps 0 and 4 (the two DMMA warps of sub-partition 0): K loop start, K loop end, C tile ready, epilogue end
+            for (int g2 = 0; g2 < 2; ++g2)
+                for (int it = 0; it < 1024; ++it) {
+                    const long long* o = &h[(size_t)grid * 4 + 128 + ((size_t)g2 * 1024 + it) * 4];
+                    if (o[0]) std::fprintf(fp, "tl %d %d %lld %lld %lld %lld\n", g2, it, o[0], o[1], o[2], o[3]);
+                }
             std::fclose(fp);
         }
     }
