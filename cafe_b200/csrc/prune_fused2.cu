@@ -39,10 +39,10 @@ constexpr int HM = 48;                 // families per group
 constexpr int TILE_M = GM * HM;        // 96 families per CTA tile
 constexpr int TN = 128;                // output sizes per pass
 constexpr int BK = 16;                 // sizes per K block (16 doubles = 128 B = one swizzle row)
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 4;
 constexpr int A_BYTES = TILE_M * 128;  // 12 KB
 constexpr int B_BYTES = TN * 128;      // 16 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES;  // A1 | A2 | B
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // A | B
 constexpr int C_BOX_BYTES = TILE_M * 128;           // one box: 96 families x 16 sizes
 constexpr int C_BOXES = TN / BK;                    // 8
 constexpr int C_BYTES = C_BOXES * C_BOX_BYTES;      // 96 KB
@@ -56,7 +56,7 @@ constexpr int REGS_CONSUMER = 192, REGS_AUX = 120;
 struct Op {              // one GEMM of the post-order schedule (a tree edge below an internal node)
     int is_root;
     int key;             // matrix of the GEMM child's branch
-    int a_kind;          // 0: child vector in in_slot, 1: child is a leaf pair (a1, a2)
+    int a_kind;          // 0: child vector in slot in_slot, 1: child is a leaf pair (a1, a2), its vector in leaf-pair slot in_slot
     int in_slot, out_slot;
     int leaf_a1, key_a1, leaf_a2, key_a2;
     int other_kind;      // 0 none, 1 leaf sibling, 2 multiply into out_slot
@@ -65,11 +65,12 @@ struct Op {              // one GEMM of the post-order schedule (a tree edge bel
 
 struct Params {
     const Op* ops;
-    int n_ops, n_slots;
+    int n_ops, n_slots, n_cherry;   // per CTA and tile: n_slots node-vector slots; per CTA, pair parity and tile: n_cherry leaf-pair slots
     int F, F_pad;
     int W, R, root_min;
     int Sp, Vp;
     int n_mblocks;               // ceil(F / 8)
+    double* scratch;             // [grid][cta_rows][Vp]
     const double* MT;            // [D][Sp][Sp] transposed matrices
     const int* counts;           // [n_leaves][F_pad]
     const double* logprior;      // [R]
@@ -159,13 +160,13 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 
 constexpr int OPFLAGS_CAP = 1024;
 struct Ctl {
-    uint64_t full[NSTAGE];       // producer expect_tx + 64 gatherer lanes
+    uint64_t full[NSTAGE];       // producer expect_tx
     uint64_t empty[NSTAGE];      // 8 consumer warps
     uint64_t c_ready;            // 32 lanes of the epilogue manager (+ TMA bytes)
     uint64_t c_done;             // 8 consumer warps
     volatile int done[2];        // finished (stored, visible) ops per tile of the pair
+    volatile int cherry_count;   // leaf-pair vectors: 2 (gatherer warps) per finished vector, in (pair, op, tile) order
     int rowoff_o[TILE_M];        // epilogue manager: count * Sp of the leaf sibling, per tile row
-    int rowoff_a[TILE_M], rowoff_b[TILE_M];  // cherry gatherers: count * Sp of the two leaves (gatherer gi owns rows [48 gi, 48 gi + 48))
     unsigned char opflags[OPFLAGS_CAP];  // per op: bit0 is_root, bit1 a_kind, bits 2-3 other_kind (what the consumers need)
     double red_ml[GM][4][HM];    // root reduction across the 4 N-warps of a group
     double red_mp[GM][4][HM];
@@ -208,6 +209,12 @@ struct TilePlan {
     }
 };
 
+// Scratch rows of one CTA: [2 tiles][n_slots] node vectors, then [2 pair parities][2 tiles][n_cherry] leaf-pair vectors, 96 rows each.
+__device__ __forceinline__ int cta_rows(const Params& P) { return (2 * P.n_slots + 4 * P.n_cherry) * TILE_M; }
+__device__ __forceinline__ int cherry_row(const Params& P, int pair, int h, int c) {
+    return (2 * P.n_slots + ((pair & 1) * 2 + h) * P.n_cherry + c) * TILE_M;
+}
+
 __device__ __forceinline__ void advance(uint32_t& stage, uint32_t& phase) {
     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
 }
@@ -217,13 +224,14 @@ template <bool PROF>
 __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUtensorMap* tmB, const Params& P,
                                               unsigned char* stage_base, Ctl* ctl) {
     const TilePlan plan(P);
-    const int scratch_row0 = blockIdx.x * 2 * P.n_slots * TILE_M;
+    const int scratch_row0 = blockIdx.x * cta_rows(P);
     const int n_kblocks = (P.W + BK - 1) / BK;
     uint32_t stage = 0, phase = 0;
     int ops_done_base = 0;
     const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
     long long t_wait_done = 0, t_wait_empty = 0;
     const long long t_begin = prof ? clock64() : 0;
+    int cherry_units = 0;  // leaf-pair vectors needed so far, in the gatherers' order (pair, op, tile)
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
         for (int oi = 0; oi < P.n_ops; ++oi) {
             const Op op = P.ops[oi];
@@ -239,17 +247,23 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
                     __threadfence_block();
                     fence_proxy_async();
                     if (prof) t_wait_done += clock64() - t0;
+                } else {
+                    // a leaf-pair vector: written by the two gatherers, normally a whole pair of tiles ahead
+                    ++cherry_units;
+                    while (ctl->cherry_count < 2 * cherry_units) { __nanosleep(20); }
+                    __threadfence_block();
+                    fence_proxy_async();
                 }
-                const int a_row = scratch_row0 + (h * P.n_slots + op.in_slot) * TILE_M;
+                const int a_row = scratch_row0 + (op.a_kind == 0 ? (h * P.n_slots + op.in_slot) * TILE_M : cherry_row(P, pair, h, op.in_slot));
                 for (int ch = 0; ch < n_chunks; ++ch) {
                     for (int kb = 0; kb < n_kblocks; ++kb) {
                         const long long t0 = prof ? clock64() : 0;
                         mbar_wait_sleepy(&ctl->empty[stage], phase ^ 1);
                         if (prof) t_wait_empty += clock64() - t0;
                         unsigned char* sA = stage_base + stage * STAGE_BYTES;
-                        mbar_arrive_expect_tx(&ctl->full[stage], op.a_kind == 0 ? A_BYTES + B_BYTES : B_BYTES);
-                        if (op.a_kind == 0) tma_load_2d(sA, tmA, kb * BK, a_row, &ctl->full[stage]);
-                        tma_load_3d(sA + 2 * A_BYTES, tmB, kb * BK, r0 + ch * TN, op.key, &ctl->full[stage]);
+                        mbar_arrive_expect_tx(&ctl->full[stage], A_BYTES + B_BYTES);
+                        tma_load_2d(sA, tmA, kb * BK, a_row, &ctl->full[stage]);
+                        tma_load_3d(sA + A_BYTES, tmB, kb * BK, r0 + ch * TN, op.key, &ctl->full[stage]);
                         advance(stage, phase);
                     }
                 }
@@ -263,69 +277,72 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
     }
 }
 
-// ================================ cherry gatherers (2 warps) ================================
-// Both wait for every ring slot (so that they can never run ahead of the ring); gatherer gi owns the tile rows rs + 4*i,
-// i in [12*gi, 12*gi + 12).  When the GEMM child is a leaf pair they build the child's K block in A1: the rows MT_a[count_a][k..k+16) and MT_b[count_b][k..k+16)
-// are copied with cp.async into A1 / A2 (the TMA's 128B-swizzle layout) and multiplied in place by the lane that copied
-// them - one product per element and pass instead of one per consumer warp (DMUL shares the fp64 pipe with DMMA).
-// 8 lanes copy one 128-byte row segment, 4 rows per instruction.
-__device__ __forceinline__ void gatherer_main(const Params& P, unsigned char* stage_base, Ctl* ctl, int gi) {
+// ================================ leaf-pair gatherers (2 warps) ================================
+// A node whose two children are leaves has the vector L[j] = M_a[j][count_a] * M_b[j][count_b] (cafe_tree.c:204-210 twice, then
+// the product of :266-270): two gathered rows of the transposed matrices.  The gatherers write these vectors for the NEXT pair
+// of tiles into dedicated scratch slots while the DMMA warps work on the current pair - a whole pair of tiles (milliseconds)
+// of slack, no coupling to the ring, one product per element.  The parent's GEMM then streams the slot like any other vector.
+// Gatherer gi owns the tile rows [48 gi, 48 gi + 48); a warp handles two rows at a time, lanes along the sizes.
+__device__ __forceinline__ void gatherer_main(const Params& P, double* scratch, Ctl* ctl, int gi) {
     const TilePlan plan(P);
     const int lane = threadIdx.x & 31;
-    const int n_kblocks = (P.W + BK - 1) / BK;
-    const int c = lane & 7, rs = lane >> 3;
-    constexpr int ROWS = TILE_M / 4 / N_GATHER_WARPS;  // 12 rows per lane
-    uint32_t stage = 0, phase = 0;
+    if (P.n_cherry == 0) return;
+    double* cta_scratch = scratch + (size_t)blockIdx.x * cta_rows(P) * P.Vp;
+    const int n_pieces = (P.W + 1) / 2;  // 16-byte pieces of a vector that hold a size < W
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        // slot set (pair & 1) was last read by pair - 2: wait until pair - 1 has completed an op (then pair - 2 is over)
+        if (pair >= 2) {
+            const int need = (pair - 1) * P.n_ops + 1;
+            while (ctl->done[0] < need) { __nanosleep(500); }
+            __threadfence_block();
+        }
         for (int oi = 0; oi < P.n_ops; ++oi) {
             const Op op = P.ops[oi];
-            const int nrows = op.is_root ? P.R : P.W;
-            const int n_chunks = (nrows + TN - 1) / TN;
+            if (op.a_kind != 1) continue;
             const double* __restrict__ MTa = P.MT + (size_t)op.key_a1 * P.Sp * P.Sp;
             const double* __restrict__ MTb = P.MT + (size_t)op.key_a2 * P.Sp * P.Sp;
             for (int h = 0; h < 2; ++h) {
                 int mb0, m;
                 if (!plan.tile(2 * pair + h, mb0, m)) continue;
-                if (op.a_kind == 1) {
-                    __syncwarp();
-                    for (int k = lane; k < 4 * ROWS; k += 32) {
-                        const int r = 4 * ROWS * gi + k;
-                        const int f = TilePlan::family(mb0, m, r, P.F);
-                        ctl->rowoff_a[r] = __ldg(P.counts + (size_t)op.leaf_a1 * P.F_pad + f) * P.Sp;
-                        ctl->rowoff_b[r] = __ldg(P.counts + (size_t)op.leaf_a2 * P.F_pad + f) * P.Sp;
+                double* out = cta_scratch + (size_t)cherry_row(P, pair, h, op.in_slot) * P.Vp;
+                for (int r0 = (TILE_M / 2) * gi; r0 < (TILE_M / 2) * (gi + 1); r0 += 2) {
+                    const double2* pa[2]; const double2* pb[2]; double2* po[2]; bool ok[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int f = TilePlan::family_or_neg(mb0, m, r0 + u, P.F);
+                        ok[u] = f >= 0;
+                        const int fc = ok[u] ? f : 0;
+                        pa[u] = reinterpret_cast<const double2*>(MTa + (size_t)__ldg(P.counts + (size_t)op.leaf_a1 * P.F_pad + fc) * P.Sp);
+                        pb[u] = reinterpret_cast<const double2*>(MTb + (size_t)__ldg(P.counts + (size_t)op.leaf_a2 * P.F_pad + fc) * P.Sp);
+                        po[u] = reinterpret_cast<double2*>(out + (size_t)(r0 + u) * P.Vp);
                     }
-                    __syncwarp();
-                }
-                for (int ch = 0; ch < n_chunks; ++ch) {
-                    for (int kb = 0; kb < n_kblocks; ++kb) {
-                        mbar_wait_sleepy(&ctl->empty[stage], phase ^ 1);
-                        {
-                            if (op.a_kind == 1) {
-                                const uint32_t sA1 = smem_u32(stage_base + stage * STAGE_BYTES), sA2 = sA1 + A_BYTES;
-                                const int col0 = kb * BK + 2 * c;
-                                // sizes >= W are zero filled: the child vector has length W although the matrices are wider when S > W
-                                const int nbytes = max(0, min(16, (P.W - col0) * 8));
+                    for (int p0 = 0; p0 < n_pieces; p0 += 128) {  // 4 pieces per lane and row in flight
+                        double2 x[2][4], y[2][4];
 #pragma unroll
-                                for (int i = 0; i < ROWS; ++i) {
-                                    const int r = rs + 4 * (ROWS * gi + i);
-                                    const uint32_t dst = r * 128 + ((c ^ (r & 7)) << 4);
-                                    cp_async16(sA1 + dst, MTa + ctl->rowoff_a[r] + col0, nbytes);
-                                    cp_async16(sA2 + dst, MTb + ctl->rowoff_b[r] + col0, nbytes);
-                                }
-                                asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-                                unsigned char* pA1 = stage_base + stage * STAGE_BYTES;
+                        for (int u = 0; u < 2; ++u)
 #pragma unroll
-                                for (int i = 0; i < ROWS; ++i) {
-                                    const int r = rs + 4 * (ROWS * gi + i);
-                                    double2* d = reinterpret_cast<double2*>(pA1 + r * 128 + ((c ^ (r & 7)) << 4));
-                                    const double2 x = *d, y = *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(d) + A_BYTES);
-                                    *d = make_double2(__dmul_rn(x.x, y.x), __dmul_rn(x.y, y.y));
+                            for (int k = 0; k < 4; ++k) {
+                                const int pc = p0 + k * 32 + lane;
+                                x[u][k] = make_double2(0.0, 0.0); y[u][k] = x[u][k];
+                                if (ok[u] && pc < n_pieces) { x[u][k] = __ldg(pa[u] + pc); y[u][k] = __ldg(pb[u] + pc); }
+                            }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int pc = p0 + k * 32 + lane;
+                                if (ok[u] && pc < n_pieces) {
+                                    // sizes >= W stay exact zeros: the vector has length W although the matrices are wider when S > W
+                                    const double hi = (2 * pc + 1 < P.W) ? __dmul_rn(x[u][k].y, y[u][k].y) : 0.0;
+                                    po[u][pc] = make_double2(__dmul_rn(x[u][k].x, y[u][k].x), hi);
                                 }
                             }
-                            mbar_arrive(&ctl->full[stage]);
-                        }
-                        advance(stage, phase);
                     }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();  // the vector is read by the producer's TMA loads
+                    atomicAdd(const_cast<int*>(&ctl->cherry_count), 1);
                 }
             }
         }
@@ -337,7 +354,7 @@ template <bool PROF>
 __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Params& P, unsigned char* Cbuf, Ctl* ctl) {
     const TilePlan plan(P);
     const int lane = threadIdx.x & 31;
-    const int scratch_row0 = blockIdx.x * 2 * P.n_slots * TILE_M;
+    const int scratch_row0 = blockIdx.x * cta_rows(P);
     const uint32_t sC = smem_u32(Cbuf);
     uint32_t item = 0;
     int ops_done_base = 0;
@@ -481,7 +498,7 @@ __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned 
                                              bool prof, long long& t_wait_full) {
     const int off0 = pg * 128 + ((q & 1) << 3);
     const int hi = q >> 1;
-    const int a_off = grp * (HM * 128), b_off = 2 * A_BYTES + nw * WCOLS * 128;
+    const int a_off = grp * (HM * 128), b_off = A_BYTES + nw * WCOLS * 128;
     if (MBV == 0) {
         for (int kb = 0; kb < n_kblocks; ++kb) {
             mbar_wait(&ctl->full[stage], phase);
@@ -737,15 +754,15 @@ k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* stage_base = smem;                       // NSTAGE x (A1 | A2 | B)
+    unsigned char* stage_base = smem;                       // NSTAGE x (A | B)
     unsigned char* Cbuf = smem + NSTAGE * STAGE_BYTES;      // 8 boxes of 96 x 16
     Ctl* ctl = reinterpret_cast<Ctl*>(Cbuf + C_BYTES);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&ctl->full[s], 1 + 32 * N_GATHER_WARPS); mbar_init(&ctl->empty[s], N_CONSUMER_WARPS); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], N_CONSUMER_WARPS); }
         mbar_init(&ctl->c_ready, 32);
         mbar_init(&ctl->c_done, N_CONSUMER_WARPS);
-        ctl->done[0] = ctl->done[1] = 0;
+        ctl->done[0] = ctl->done[1] = 0; ctl->cherry_count = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < P.n_ops; i += THREADS) {
@@ -759,7 +776,7 @@ k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
         if (warp == N_CONSUMER_WARPS) { if ((threadIdx.x & 31) == 0) producer_main<PROF>(&tmA, &tmB, P, stage_base, ctl); }
         else if (warp == N_CONSUMER_WARPS + 3) cmanager_main<PROF>(&tmA, P, Cbuf, ctl);
-        else gatherer_main(P, stage_base, ctl, warp - (N_CONSUMER_WARPS + 1));
+        else gatherer_main(P, P.scratch, ctl, warp - (N_CONSUMER_WARPS + 1));
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
         long long t_start = 0;
@@ -801,7 +818,7 @@ struct Fused2State {
     double* d_scratch = nullptr; size_t scratch_cap = 0;
     bool attr_set = false;
     std::vector<fused2::Op> ops;  // schedule of the current launch
-    int n_slots = 0;
+    int n_slots = 0, n_cherry = 0;
 };
 static Fused2State& fstate2(cafe_gpu_ctx* ctx) {
     if (!ctx->fused2_state) ctx->fused2_state = new Fused2State();
@@ -850,11 +867,12 @@ static void build_schedule2(const cafe_gpu_ctx* ctx, Fused2State& st) {
         if (!free_slots.empty()) { int s = free_slots.back(); free_slots.pop_back(); return s; }
         return n_slots++;
     };
+    int n_cherry = 0;
     auto gemm_over = [&](Op& op, int child, int slot) {  // the GEMM operand: a stored vector or a leaf pair
         op.key = ctx->node_key[child];
         if (is_cherry(child)) {
             const int a = ctx->left[child], b = ctx->right[child];
-            op.a_kind = 1; op.in_slot = 0;
+            op.a_kind = 1; op.in_slot = n_cherry++;
             op.leaf_a1 = a / 2; op.key_a1 = ctx->node_key[a];
             op.leaf_a2 = b / 2; op.key_a2 = ctx->node_key[b];
         } else {
@@ -894,6 +912,7 @@ static void build_schedule2(const cafe_gpu_ctx* ctx, Fused2State& st) {
     };
     eval(ctx->root);
     st.n_slots = std::max(1, n_slots);
+    st.n_cherry = n_cherry;
 }
 
 int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
@@ -914,7 +933,8 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     // ---- geometry: one CTA per SM, every CTA at least two 8-family blocks ----
     const int n_mblocks = (ctx->F + 7) / 8;
     const int grid = std::max(1, std::min(ctx->sm_count, (n_mblocks + 1) / 2));
-    const size_t scratch_doubles = (size_t)grid * 2 * st.n_slots * TILE_M * ctx->Vp;
+    const size_t cta_rows = (size_t)(2 * st.n_slots + 4 * st.n_cherry) * TILE_M;
+    const size_t scratch_doubles = (size_t)grid * cta_rows * ctx->Vp;
     if (scratch_doubles > st.scratch_cap) {
         cudaFree(st.d_scratch); st.d_scratch = nullptr;
         CAFE_CK(ctx, cudaMalloc(&st.d_scratch, scratch_doubles * sizeof(double)));
@@ -925,7 +945,7 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     // ---- tensor maps (SWIZZLE_128B, zero OOB fill) ----
     CUtensorMap tmA, tmB;
     {
-        cuuint64_t dims[2] = {(cuuint64_t)ctx->Vp, (cuuint64_t)grid * 2 * st.n_slots * TILE_M};
+        cuuint64_t dims[2] = {(cuuint64_t)ctx->Vp, (cuuint64_t)grid * cta_rows};
         cuuint64_t strides[1] = {(cuuint64_t)ctx->Vp * sizeof(double)};
         cuuint32_t box[2] = {BK, TILE_M};
         cuuint32_t estr[2] = {1, 1};
@@ -944,7 +964,8 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     }
 
     Params P{};
-    P.ops = st.d_ops; P.n_ops = (int)st.ops.size(); P.n_slots = st.n_slots; P.F = ctx->F; P.F_pad = ctx->F_pad;
+    P.ops = st.d_ops; P.n_ops = (int)st.ops.size(); P.n_slots = st.n_slots; P.n_cherry = st.n_cherry; P.F = ctx->F; P.F_pad = ctx->F_pad;
+    P.scratch = st.d_scratch;
     P.W = ctx->W; P.R = ctx->R; P.root_min = ctx->root_min; P.Sp = ctx->Sp; P.Vp = ctx->Vp; P.n_mblocks = n_mblocks;
     P.MT = ctx->d_MT; P.counts = ctx->d_counts; P.logprior = ctx->d_logprior;
     P.prior_mant = ctx->d_prior_mant; P.prior_exp = ctx->d_prior_exp;
