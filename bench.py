@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 METRIC = "gene-family log-likelihoods/sec per lambda-eval"
 UNIT = "families/s"
 N_TAXA = 20
-FAMILIES_PER_GPU = 50000
+FAMILIES_PER_GPU = int(os.environ.get("CAFE_BENCH_FAMILIES", 50000))  # override is for kernel experiments only
 MAX_SIZE = 200
 TREE_SEED = 1
 
