@@ -83,6 +83,7 @@ struct Params {
     double* maxlik;
     int* argmax;
     double* Lroot_out;           // nullable, [F][R]
+    int skew;                    // cycles group 1 starts every K loop after group 0 (see consumer_main)
     int dbg;                     // debug ablations (CAFE_GPU_DBG, results are garbage): 1 no epilogue work, 2 no epilogue at all, 4 no store, 8 no ring (K loops on whatever is in shared memory)
     long long* cta_times;        // nullable debug: [grid][4] = smid, start ns, end ns, 8-family blocks
     long long* warp_prof;        // nullable debug: CTA 0, [16 warps][8] cycle sums (see consumer_main / producer_main)
@@ -613,6 +614,8 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
 
                     const long long tk0 = prof ? clock64() : 0;
+                    // experiment knob (CAFE_GPU_SKEW): start group 1 of the very first pass some cycles after group 0
+                    if (grp == 1 && P.skew > 0 && item == 0) { const long long t0 = clock64(); while (clock64() - t0 < P.skew) { } }
 #define CAFE_K(MBV_) gemm_kblocks<MBV_>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full, (P.dbg & 8) != 0);
                     switch (mbw) {
                         case 6: CAFE_K(6) break;
@@ -987,6 +990,8 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     P.logpost = ctx->d_logpost; P.maxlik = ctx->d_maxlik; P.argmax = ctx->d_argmax; P.Lroot_out = d_Lroot_out;
 
     if (const char* d = std::getenv("CAFE_GPU_DBG")) P.dbg = std::atoi(d);
+    P.skew = 0;  // measured: no effect for 0..9000 cycles (profiles/r1_k2_experiments.md)
+    if (const char* d = std::getenv("CAFE_GPU_SKEW")) P.skew = std::atoi(d);
     const size_t smem_bytes = (size_t)NSTAGE * STAGE_BYTES + C_BYTES + sizeof(Ctl) + 1024;
     if (!st.attr_set) {
         CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));

@@ -275,3 +275,62 @@ def _band_error_matrix(dim, eps):
     E[0, 0] = 1 - eps
     E[dim - 1, dim - 1] = 1 - eps
     return E
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE configs[1]: 50 k families x 20 taxa, max size 200): too big for the CPU oracle
+# as a whole, so the checks are (a) a random family sample against the oracle, (b) the three CUDA code paths
+# against each other, (c) invariance under a permutation of the families, (d) score == sum of the family terms.
+# ---------------------------------------------------------------------------------------------------------
+def _config2_problem(F=50000):
+    from cafe_b200 import synth
+    nw = synth.random_tree(20, 1)
+    counts, lam0 = synth.simulate_table(nw, F, 200, seed=10)
+    return nw, counts, lam0
+
+
+def _family_terms(nw, counts, lam, env=None):
+    import os
+    saved = {}
+    for k, v in (env or {}).items():
+        saved[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        p = Problem(nw, counts, lam, prior_lambda=8.0)
+        g = p.make_gpu()
+        s, fz = g.score()
+        lp, ml, am = g.family_results()
+        g.close()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return p, s, fz, lp, ml, am
+
+
+def test_k2_config2_full_size_properties():
+    nw, counts, lam0 = _config2_problem()
+    assert counts.shape == (50000, 20) and counts.max() == 200
+    p, s, fz, lp, ml, am = _family_terms(nw, counts, lam0)
+    assert p.ranges == (0, 250, 1, 250) and fz == -1 and np.isfinite(lp).all()
+    # (d) the score is the sum of the per-family terms (lambda.cpp:721)
+    assert abs(s - float(lp.sum())) <= score_tol(s)
+    # (b) first-generation fused kernel and per-node kernels: same DMMA order over K, same products -> bit-identical terms
+    _, s1, _, lp1, ml1, am1 = _family_terms(nw, counts, lam0, env={"CAFE_GPU_FUSED_V1": "1"})
+    assert np.array_equal(ml, ml1) and np.array_equal(am, am1)
+    assert np.abs(lp - lp1).max() <= 1e-12
+    _, s2, _, lp2, ml2, am2 = _family_terms(nw, counts[:4096], lam0, env={"CAFE_GPU_NO_FUSED": "1"})
+    assert np.array_equal(ml[:4096], ml2) and np.array_equal(am[:4096], am2)
+    assert np.abs(lp[:4096] - lp2).max() <= 1e-12
+    # (c) a family's result does not depend on its position in the table (tile, group, row)
+    perm = np.random.RandomState(5).permutation(len(counts))
+    _, s3, _, lp3, ml3, am3 = _family_terms(nw, counts[perm], lam0)
+    assert np.array_equal(ml[perm], ml3) and np.array_equal(am[perm], am3) and np.array_equal(lp[perm], lp3)
+    # (a) 160 random families against the CPU oracle
+    idx = np.random.RandomState(6).choice(len(counts), 160, replace=False)
+    po = Problem(nw, counts[idx], lam0, prior_lambda=8.0, ranges=p.ranges)
+    o = po.oracle_score(want_L=False)
+    assert np.abs(lp[idx] - o["logpost"]).max() <= TOL_LOGPOST
+    assert rel_err(ml[idx], o["maxlik"], 1e-290).max() <= TOL_L
