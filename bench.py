@@ -31,10 +31,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gene-family log-likelihoods/sec per lambda-eval"
 UNIT = "families/s"
-N_TAXA = 20
-FAMILIES_PER_GPU = int(os.environ.get("CAFE_BENCH_FAMILIES", 50000))  # override is for kernel experiments only
-MAX_SIZE = 200
+# The headline workload is BASELINE configs[1].  The CAFE_BENCH_* overrides exist for kernel experiments and for informational
+# lines on the other BASELINE shapes (e.g. configs[2] per GPU at 8 GPUs: CAFE_BENCH_FAMILIES=25000 CAFE_BENCH_TAXA=50
+# CAFE_BENCH_MAXSIZE=400 CAFE_BENCH_MU=0.8); the JSON line always names the workload it actually ran.
+N_TAXA = int(os.environ.get("CAFE_BENCH_TAXA", 20))
+FAMILIES_PER_GPU = int(os.environ.get("CAFE_BENCH_FAMILIES", 50000))
+MAX_SIZE = int(os.environ.get("CAFE_BENCH_MAXSIZE", 200))
+MU_RATIO = float(os.environ.get("CAFE_BENCH_MU", 0))  # > 0: lambdamu mode with mu = ratio * lambda
 TREE_SEED = 1
+IS_HEADLINE = (N_TAXA, FAMILIES_PER_GPU, MAX_SIZE, MU_RATIO) == (20, 50000, 200, 0)
+WORKLOAD_NAME = "BASELINE configs[1]" if IS_HEADLINE else "experiment override, not the headline workload"
 
 
 def env_int(name, default):
@@ -183,7 +189,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * n_total / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (simulated from the birth-death model)",
-        "config": {"workload": f"{FAMILIES_PER_GPU} families x {N_TAXA} taxa, max size {MAX_SIZE}, single lambda (BASELINE configs[1]) per GPU-equivalent",
+        "config": {"workload": f"{FAMILIES_PER_GPU} families x {N_TAXA} taxa, max size {MAX_SIZE}, single lambda ({WORKLOAD_NAME}) per GPU-equivalent",
                    "families_total": n_total, "W": ranges[1] + 1, "R": ranges[3] - ranges[2] + 1},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": last["kind"], "sample": sample,
                          "note": "the reference's lambda search is single-threaded over families (lambda.cpp:698-722)"},
@@ -222,6 +228,9 @@ def run_ours(args, rank, local_rank, world):
     n = tree.n_nodes
     mu_node = np.full(n, -1.0)
 
+    def mu_of(lam):
+        return np.full(n, MU_RATIO * lam) if MU_RATIO > 0 else mu_node
+
     g = cgpu.CafeGpu(local_rank)
     # everything (our kernels, the NCCL collective, the timing events) runs on one explicit torch stream
     stream = torch.cuda.Stream(device=dev)
@@ -235,7 +244,8 @@ def run_ours(args, rank, local_rank, world):
     out2 = torch.zeros(2, dtype=torch.float64, device=dev)
 
     def step_device(k):
-        g.objective_device(np.full(n, lambda_schedule(lam0, k)), mu_node, out2.data_ptr())
+        lam_k = lambda_schedule(lam0, k)
+        g.objective_device(np.full(n, lam_k), mu_of(lam_k), out2.data_ptr())
         return sharding.reduce_score(out2)
 
     def barrier():
@@ -287,9 +297,9 @@ def run_ours(args, rank, local_rank, world):
     for k in range(args.steps):
         lam_node = np.full(n, lambda_schedule(lam0, args.warmup + k))
         if world == 1:
-            sc, fz = g.objective(lam_node, mu_node)  # host lambda array in, host score out (sync inside)
+            sc, fz = g.objective(lam_node, mu_of(lam_node[0]))  # host lambda array in, host score out (sync inside)
         else:
-            g.objective_device(lam_node, mu_node, out2.data_ptr())
+            g.objective_device(lam_node, mu_of(lam_node[0]), out2.data_ptr())
             s2, z2 = sharding.reduce_score(out2)
             sc, fz = sharding.finish_score(s2.cpu(), z2.cpu())
     torch.cuda.synchronize()
@@ -354,7 +364,7 @@ def run_ours(args, rank, local_rank, world):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (simulated from the birth-death model at lambda0=0.25/depth)",
         "config": {
-            "workload": f"{FAMILIES_PER_GPU} families x {N_TAXA} taxa per GPU, max size {MAX_SIZE}, single lambda (BASELINE configs[1])",
+            "workload": f"{FAMILIES_PER_GPU} families x {N_TAXA} taxa per GPU, max size {MAX_SIZE}, " + ("lambda and mu" if MU_RATIO > 0 else "single lambda") + f" ({WORKLOAD_NAME})",
             "families_total": families_total, "unique_patterns_rank0": int(len(uniq)), "W": ranges[1] + 1, "R": R,
             "S": max(ranges[1], ranges[3]) + 1, "keys": g.num_keys(), "parallelism": f"families sharded x{world}",
             "l2": "no explicit flush: node-vector slots (>=4 x 102 MB) exceed the 126 MB L2 and matrices are rewritten every step",

@@ -39,10 +39,12 @@ constexpr int HM = 48;                 // families per group
 constexpr int TILE_M = GM * HM;        // 96 families per CTA tile
 constexpr int TN = 128;                // output sizes per pass
 constexpr int BK = 16;                 // sizes per K block (16 doubles = 128 B = one swizzle row)
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 2;                // ring stages, each KB_PER_STAGE K blocks
+constexpr int KB_PER_STAGE = 2;
 constexpr int A_BYTES = TILE_M * 128;  // 12 KB
 constexpr int B_BYTES = TN * 128;      // 16 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;      // A | B
+constexpr int SUB_BYTES = A_BYTES + B_BYTES;        // one K block: A | B
+constexpr int STAGE_BYTES = KB_PER_STAGE * SUB_BYTES;
 constexpr int C_BOX_BYTES = TILE_M * 128;           // one box: 96 families x 16 sizes
 constexpr int C_BOXES = TN / BK;                    // 8
 constexpr int C_BYTES = C_BOXES * C_BOX_BYTES;      // 96 KB
@@ -192,10 +194,16 @@ struct TilePlan {
         if (n_mb >= 2 && (n_tiles & 1)) ++n_tiles;
         n_pairs = (n_tiles + 1) / 2;
     }
+    // Tile sizes are even wherever possible (both groups of a tile then hold the same number of blocks and finish every ring
+    // stage together): all tiles get the even base size e, the first ones 2 more, and one tile the odd block if n_mb is odd.
     __device__ bool tile(int t, int& mb0, int& m) const {
         if (t >= n_tiles) return false;
-        mb0 = mb_lo + (int)((long long)n_mb * t / n_tiles);
-        m = mb_lo + (int)((long long)n_mb * (t + 1) / n_tiles) - mb0;
+        const int e = (n_mb / n_tiles) & ~1;
+        const int r = n_mb - e * n_tiles;   // < 2 * n_tiles
+        const int n2 = r >> 1;              // tiles with e + 2 blocks
+        auto size = [&](int i) { return e + (i < n2 ? 2 : 0) + ((r & 1) && i == n2 ? 1 : 0); };
+        mb0 = mb_lo + e * t + 2 * min(t, n2) + ((r & 1) && t > n2 ? 1 : 0);
+        m = size(t);
         return true;
     }
     __device__ static int mbv(int m, int g) { return (m + GM - 1 - g) / GM; }
@@ -262,14 +270,17 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
                 }
                 const int a_row = scratch_row0 + (op.a_kind == 0 ? (h * P.n_slots + op.in_slot) * TILE_M : cherry_row(P, pair, h, op.in_slot));
                 for (int ch = 0; ch < n_chunks; ++ch) {
-                    for (int kb = 0; kb < n_kblocks; ++kb) {
+                    for (int kb = 0; kb < n_kblocks; kb += KB_PER_STAGE) {
                         const long long t0 = prof ? clock64() : 0;
                         mbar_wait_sleepy(&ctl->empty[stage], phase ^ 1);
                         if (prof) t_wait_empty += clock64() - t0;
-                        unsigned char* sA = stage_base + stage * STAGE_BYTES;
-                        mbar_arrive_expect_tx(&ctl->full[stage], A_BYTES + B_BYTES);
-                        tma_load_2d(sA, tmA, kb * BK, a_row, &ctl->full[stage]);
-                        tma_load_3d(sA + A_BYTES, tmB, kb * BK, r0 + ch * TN, op.key, &ctl->full[stage]);
+                        const int nsub = min(KB_PER_STAGE, n_kblocks - kb);
+                        mbar_arrive_expect_tx(&ctl->full[stage], nsub * SUB_BYTES);
+                        for (int j = 0; j < nsub; ++j) {
+                            unsigned char* sA = stage_base + stage * STAGE_BYTES + j * SUB_BYTES;
+                            tma_load_2d(sA, tmA, (kb + j) * BK, a_row, &ctl->full[stage]);
+                            tma_load_3d(sA + A_BYTES, tmB, (kb + j) * BK, r0 + ch * TN, op.key, &ctl->full[stage]);
+                        }
                         advance(stage, phase);
                     }
                 }
@@ -495,26 +506,55 @@ __device__ __forceinline__ void mma_frags(double (&acc)[MB][NB][2], const double
         for (int nb = 0; nb < NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], fa[mb], fb[nb]);
 }
 
-// K loop of one pass: consume n_kblocks ring stages.  The fragments of the next k4-step are fetched before the DMMAs of the
-// current one, across the stage boundary too: the mbarrier wait of the next stage (~100 cycles even when it is already
-// full) and the first shared-memory loads hide behind the 24 DMMAs of the last step instead of idling the pipe.
+// STEPS k4-steps (one or two full K blocks of a ring stage).  The fragments of the next step are fetched before the DMMAs of the
+// current one; after the last step (do_next) the first fragments of whatever follows - the next K block of the stage, or the
+// next stage after its mbarrier wait (~100 cycles even when already full) - so that neither sits between two DMMAs.
+template <int MBV, int STEPS>
+__device__ __forceinline__ void steps_full(double (&acc)[MB][NB][2], double (&fa)[2][MB], double (&fb)[2][NB], const unsigned char* sa,
+                                           const unsigned char* sb, const int (&koff)[4], bool do_next, const unsigned char* next_a,
+                                           const unsigned char* next_b, uint64_t* wait_bar, uint32_t wait_phase,
+                                           bool prof, long long& t_wait_full) {
+#pragma unroll
+    for (int kk = 0; kk < STEPS; ++kk) {
+        if (kk + 1 < STEPS) {
+            const int j = (kk + 1) >> 2;
+            load_frags<MBV>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sa + j * SUB_BYTES, sb + j * SUB_BYTES, koff[(kk + 1) & 3]);
+        } else if (do_next) {
+            if (wait_bar) {
+                const long long t0 = prof ? clock64() : 0;
+                mbar_wait(wait_bar, wait_phase);
+                if (prof) t_wait_full += clock64() - t0;
+            }
+            load_frags<MBV>(fa[0], fb[0], next_a, next_b, koff[0]);
+        }
+        mma_frags<MBV>(acc, fa[kk & 1], fb[kk & 1]);
+    }
+}
+
+// K loop of one pass: n_kblocks K blocks of 16 sizes (the last one with tail_steps k4-steps), KB_PER_STAGE per ring stage.
 // MBV == 0: this warp has no work in the tile, it only keeps the ring moving.
 template <int MBV>
 __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned char* stage_base, Ctl* ctl, uint32_t& stage,
                                              uint32_t& phase, int n_kblocks, int tail_steps, int grp, int nw, int lane, int pg, int q,
                                              bool prof, long long& t_wait_full, bool nosync) {
-    const int off0 = pg * 128 + ((q & 1) << 3);
-    const int hi = q >> 1;
-    const int a_off = grp * (HM * 128), b_off = A_BYTES + nw * WCOLS * 128;
+    static_assert(KB_PER_STAGE == 2, "the stage loop below is written for two K blocks per stage");
+    const int n_stages = (n_kblocks + KB_PER_STAGE - 1) / KB_PER_STAGE;
     if (MBV == 0) {
-        for (int kb = 0; kb < n_kblocks; ++kb) {
-            mbar_wait(&ctl->full[stage], phase);
+        for (int st = 0; st < n_stages; ++st) {
+            if (!nosync) mbar_wait(&ctl->full[stage], phase);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl->empty[stage]);
+            if (lane == 0 && !nosync) mbar_arrive(&ctl->empty[stage]);
             advance(stage, phase);
         }
         return;
     }
+    const int off0 = pg * 128 + ((q & 1) << 3), hi = q >> 1;
+    int koff[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) koff[kk] = off0 + (((2 * kk + hi) ^ pg) << 4);
+    const int a_off = grp * (HM * 128), b_off = A_BYTES + nw * WCOLS * 128;
+    const int n_full = (tail_steps == 4) ? n_kblocks : n_kblocks - 1;  // K blocks with all four steps
+
     double fa[2][MB], fb[2][NB];
     if (!nosync) {
         const long long t0 = prof ? clock64() : 0;
@@ -522,29 +562,33 @@ __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned 
         if (prof) t_wait_full += clock64() - t0;
     }
     const unsigned char* sbase = stage_base + stage * STAGE_BYTES;
-    load_frags<MBV>(fa[0], fb[0], sbase + a_off, sbase + b_off, off0 + ((hi ^ pg) << 4));
-    for (int kb = 0; kb < n_kblocks; ++kb) {
-        const bool last = kb + 1 == n_kblocks;
+    load_frags<MBV>(fa[0], fb[0], sbase + a_off, sbase + b_off, koff[0]);
+    for (int st = 0; st < n_stages; ++st) {
         uint32_t nstage = stage, nphase = phase;
         advance(nstage, nphase);
         const unsigned char* nbase = stage_base + nstage * STAGE_BYTES;
-        if (!last || tail_steps == 4) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                if (kk < 3) {
-                    load_frags<MBV>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sbase + a_off, sbase + b_off, off0 + (((2 * (kk + 1) + hi) ^ pg) << 4));
-                } else if (!last) {
-                    const long long t0 = prof ? clock64() : 0;
-                    if (!nosync) mbar_wait(&ctl->full[nstage], nphase);
-                    if (prof) t_wait_full += clock64() - t0;
-                    load_frags<MBV>(fa[0], fb[0], nbase + a_off, nbase + b_off, off0 + ((hi ^ pg) << 4));
-                }
-                mma_frags<MBV>(acc, fa[kk & 1], fb[kk & 1]);
+        const unsigned char* sa = sbase + a_off;
+        const unsigned char* sb = sbase + b_off;
+        const int kb0 = st * KB_PER_STAGE;
+        const bool has_next = st + 1 < n_stages;
+        uint64_t* nbar = nosync ? nullptr : &ctl->full[nstage];
+        if (kb0 + 2 <= n_full) {
+            // two full K blocks; then the next stage (if any)
+            steps_full<MBV, 8>(acc, fa, fb, sa, sb, koff, has_next, nbase + a_off, nbase + b_off, nbar, nphase, prof, t_wait_full);
+        } else {
+            // the last stage of the pass: [full block] [partial block], either may be missing
+            int kb = kb0;
+            if (kb < n_full) {
+                const bool more = kb + 1 < n_kblocks;  // a partial block follows in this stage
+                steps_full<MBV, 4>(acc, fa, fb, sa, sb, koff, more, sa + SUB_BYTES, sb + SUB_BYTES, nullptr, 0, prof, t_wait_full);
+                ++kb;
             }
-        } else {  // last K block of the pass with fewer than 4 steps
-            for (int kk = 0; kk < tail_steps; ++kk) {
-                if (kk > 0) load_frags<MBV>(fa[0], fb[0], sbase + a_off, sbase + b_off, off0 + (((2 * kk + hi) ^ pg) << 4));
-                mma_frags<MBV>(acc, fa[0], fb[0]);
+            if (kb < n_kblocks && kb >= n_full) {
+                const int j = kb - kb0;
+                for (int kk = 0; kk < tail_steps; ++kk) {
+                    if (kk > 0) load_frags<MBV>(fa[0], fb[0], sa + j * SUB_BYTES, sb + j * SUB_BYTES, off0 + (((2 * kk + hi) ^ pg) << 4));
+                    mma_frags<MBV>(acc, fa[0], fb[0]);
+                }
             }
         }
         __syncwarp();
@@ -772,7 +816,7 @@ k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    unsigned char* stage_base = smem;                       // NSTAGE x (A | B)
+    unsigned char* stage_base = smem;                       // NSTAGE x KB_PER_STAGE x (A | B)
     unsigned char* Cbuf = smem + NSTAGE * STAGE_BYTES;      // 8 boxes of 96 x 16
     Ctl* ctl = reinterpret_cast<Ctl*>(Cbuf + C_BYTES);
 
