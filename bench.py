@@ -243,8 +243,14 @@ def run_ours(args, rank, local_rank, world):
     g.set_prior(prior)
     out2 = torch.zeros(2, dtype=torch.float64, device=dev)
 
+    shard_k1 = world > 1 and os.environ.get("CAFE_BENCH_NO_K1_SHARD") is None
+    if shard_k1:
+        g.set_key_shard(rank, world)  # every rank builds 1/world of the matrices, NCCL all-gathers them (sharding.objective_sharded)
+
     def step_device(k):
         lam_k = lambda_schedule(lam0, k)
+        if shard_k1:
+            return sharding.objective_sharded(g, np.full(n, lam_k), mu_of(lam_k), out2, rank, world, dev)
         g.objective_device(np.full(n, lam_k), mu_of(lam_k), out2.data_ptr())
         return sharding.reduce_score(out2)
 
@@ -283,7 +289,7 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     clocks = sampler.stop(max(0, mark0 - 1), mark1) if rank == 0 else None
-    launches = g.launch_count() + (args.steps if world > 1 else 0)  # + one NCCL all-gather per step
+    launches = g.launch_count() + (args.steps * (3 if shard_k1 else 1) if world > 1 else 0)  # + the NCCL all-gathers of every step
     k1_ms, k2_ms = g.timing_collect()
     g.enable_timing(False)
     ms_per_step = float(ms_total.item()) / args.steps
@@ -299,8 +305,11 @@ def run_ours(args, rank, local_rank, world):
         if world == 1:
             sc, fz = g.objective(lam_node, mu_of(lam_node[0]))  # host lambda array in, host score out (sync inside)
         else:
-            g.objective_device(lam_node, mu_of(lam_node[0]), out2.data_ptr())
-            s2, z2 = sharding.reduce_score(out2)
+            if shard_k1:
+                s2, z2 = sharding.objective_sharded(g, lam_node, mu_of(lam_node[0]), out2, rank, world, dev)
+            else:
+                g.objective_device(lam_node, mu_of(lam_node[0]), out2.data_ptr())
+                s2, z2 = sharding.reduce_score(out2)
             sc, fz = sharding.finish_score(s2.cpu(), z2.cpu())
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -366,7 +375,7 @@ def run_ours(args, rank, local_rank, world):
         "config": {
             "workload": f"{FAMILIES_PER_GPU} families x {N_TAXA} taxa per GPU, max size {MAX_SIZE}, " + ("lambda and mu" if MU_RATIO > 0 else "single lambda") + f" ({WORKLOAD_NAME})",
             "families_total": families_total, "unique_patterns_rank0": int(len(uniq)), "W": ranges[1] + 1, "R": R,
-            "S": max(ranges[1], ranges[3]) + 1, "keys": g.num_keys(), "parallelism": f"families sharded x{world}",
+            "S": max(ranges[1], ranges[3]) + 1, "keys": g.num_keys(), "parallelism": f"families sharded x{world}" + (f", matrix build sharded x{world} + 2 NCCL all-gathers" if shard_k1 else ""),
             "l2": "no explicit flush: node-vector slots (>=4 x 102 MB) exceed the 126 MB L2 and matrices are rewritten every step",
             "last_score": last_score, "k1_ms": k1, "k2_ms": k2,
         },

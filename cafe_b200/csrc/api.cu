@@ -318,9 +318,15 @@ int cafe_gpu_set_rates(cafe_gpu_ctx* ctx, const double* lambda_per_node, const d
 
 static int ensure_matrix_buffers(cafe_gpu_ctx* ctx) {
     const size_t D = ctx->keys.size();
-    if (D > ctx->mat_cap) {
+    // key range of this context: everything, or one of shard_world equal chunks (the all-gather needs equal chunks, so the
+    // buffers hold keys_per_rank * shard_world matrices)
+    ctx->keys_per_rank = (int)((D + ctx->shard_world - 1) / ctx->shard_world);
+    ctx->key_lo = std::min<int>((int)D, ctx->shard_rank * ctx->keys_per_rank);
+    ctx->key_hi = std::min<int>((int)D, ctx->key_lo + ctx->keys_per_rank);
+    const size_t need = (size_t)ctx->keys_per_rank * ctx->shard_world;
+    if (need > ctx->mat_cap) {
         cudaFree(ctx->d_M); cudaFree(ctx->d_MT); ctx->d_M = ctx->d_MT = nullptr;
-        size_t cap = std::max<size_t>(D, (size_t)ctx->n_nodes - 1);  // never more keys than branches
+        size_t cap = std::max<size_t>(need, (size_t)ctx->n_nodes - 1 + ctx->shard_world);  // never more keys than branches
         size_t bytes = cap * ctx->Sp * ctx->Sp * sizeof(double);
         CAFE_CK(ctx, cudaMalloc(&ctx->d_M, bytes));
         CAFE_CK(ctx, cudaMalloc(&ctx->d_MT, bytes));
@@ -352,8 +358,35 @@ int cafe_gpu_build_matrices(cafe_gpu_ctx* ctx) {
     CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_keyparams, kp.data(), kp.size() * sizeof(BdKeyParams), cudaMemcpyHostToDevice, ctx->stream));
     rc = launch_bd_matrices(ctx);
     if (rc) return rc;
-    ctx->matrices_valid = true;
+    ctx->matrices_need_exchange = ctx->shard_world > 1;
+    ctx->matrices_valid = !ctx->matrices_need_exchange;
     ctx->results_valid = false;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_set_key_shard(cafe_gpu_ctx* ctx, int rank, int world) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    if (world < 1 || rank < 0 || rank >= world) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_key_shard: need 0 <= rank < world");
+    ctx->shard_rank = rank; ctx->shard_world = world;
+    ctx->matrices_valid = false; ctx->results_valid = false;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_matrix_storage(cafe_gpu_ctx* ctx, void** d_M, void** d_MT, int64_t* doubles_per_key, int32_t* keys_per_rank) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    if (!ctx->d_M) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "matrix_storage: build_matrices first");
+    if (d_M) *d_M = ctx->d_M;
+    if (d_MT) *d_MT = ctx->d_MT;
+    if (doubles_per_key) *doubles_per_key = (int64_t)ctx->Sp * ctx->Sp;
+    if (keys_per_rank) *keys_per_rank = ctx->keys_per_rank;
+    return CAFE_GPU_OK;
+}
+
+int cafe_gpu_matrices_exchanged(cafe_gpu_ctx* ctx) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    if (!ctx->matrices_need_exchange) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "matrices_exchanged: no sharded build_matrices pending");
+    ctx->matrices_need_exchange = false;
+    ctx->matrices_valid = true;
     return CAFE_GPU_OK;
 }
 
@@ -388,7 +421,7 @@ int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad) {
 extern "C" {
 
 static int check_ready(cafe_gpu_ctx* ctx, const char* who) {
-    if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + ": build_matrices first");
+    if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + (ctx->matrices_need_exchange ? ": all-gather the matrices and call cafe_gpu_matrices_exchanged first" : ": build_matrices first"));
     if (ctx->F == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + ": set_families first");
     if (!ctx->d_logprior) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + ": set_prior first");
     if (ctx->leaf_err.empty() || std::all_of(ctx->leaf_err.begin(), ctx->leaf_err.end(), [](int e) { return e < 0; })) {
@@ -437,6 +470,11 @@ int cafe_gpu_objective(cafe_gpu_ctx* ctx, const double* lambda_per_node, const d
     rc = cafe_gpu_build_matrices(ctx);
     if (rc) return rc;
     return cafe_gpu_score(ctx, score_out, first_zero_family);
+}
+
+int cafe_gpu_score_device(cafe_gpu_ctx* ctx, double* out_device) {
+    if (!ctx || !out_device) return CAFE_GPU_ERR_ARG;
+    return score_device(ctx, out_device);
 }
 
 int cafe_gpu_objective_device(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node, double* out_device) {

@@ -117,6 +117,10 @@ struct cafe_gpu_ctx {
     BdKeyParams* d_keyparams = nullptr;
     int keys_cap = 0;
     bool matrices_valid = false;
+    // K1 sharded over ranks (cafe_gpu_set_key_shard): this context builds keys [key_lo, key_hi) only, the caller all-gathers
+    int shard_rank = 0, shard_world = 1;
+    int key_lo = 0, key_hi = 0, keys_per_rank = 0;
+    bool matrices_need_exchange = false;
     double* d_M = nullptr;   // [D][Sp][Sp]  M[s][c]
     double* d_MT = nullptr;  // [D][Sp][Sp]  MT[c][s]
     size_t mat_cap = 0;      // allocated matrices

@@ -27,6 +27,7 @@ ABI_SYMBOLS = [
     "cafe_gpu_objective_device", "cafe_gpu_family_results", "cafe_gpu_family_likelihoods",
     "cafe_gpu_conditional_distribution", "cafe_gpu_pvalues", "cafe_gpu_launch_count",
     "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_timing_collect", "cafe_gpu_score_flops",
+    "cafe_gpu_score_device", "cafe_gpu_set_key_shard", "cafe_gpu_matrix_storage", "cafe_gpu_matrices_exchanged",
 ]
 
 
@@ -59,6 +60,10 @@ def load_library():
     L.cafe_gpu_score.argtypes = [vp, _dp, _ip]
     L.cafe_gpu_objective.argtypes = [vp, _dp, _dp, _dp, _ip]
     L.cafe_gpu_objective_device.argtypes = [vp, _dp, _dp, vp]
+    L.cafe_gpu_score_device.argtypes = [vp, vp]
+    L.cafe_gpu_set_key_shard.argtypes = [vp, C.c_int, C.c_int]
+    L.cafe_gpu_matrix_storage.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    L.cafe_gpu_matrices_exchanged.argtypes = [vp]
     L.cafe_gpu_family_results.argtypes = [vp, _dp, _dp, _ip]
     L.cafe_gpu_family_likelihoods.argtypes = [vp, _dp]
     L.cafe_gpu_conditional_distribution.argtypes = [vp, C.c_int, _dp, C.c_uint64, _dp]
@@ -190,6 +195,23 @@ class CafeGpu:
         lam = np.ascontiguousarray(lam, dtype=np.float64)
         mu = np.ascontiguousarray(mu, dtype=np.float64)
         self._ck(self.L.cafe_gpu_objective_device(self.h, _d(lam), _d(mu), C.c_void_p(out_device_ptr)), "objective_device")
+
+    def score_device(self, out_device_ptr):
+        self._ck(self.L.cafe_gpu_score_device(self.h, C.c_void_p(out_device_ptr)), "score_device")
+
+    # ---- K1 sharded across ranks (include/cafe_gpu.h: cafe_gpu_set_key_shard) ----
+    def set_key_shard(self, rank, world):
+        self._ck(self.L.cafe_gpu_set_key_shard(self.h, rank, world), "set_key_shard")
+
+    def matrix_storage(self):
+        """(d_M, d_MT, doubles_per_key, keys_per_rank): device pointers of the two matrix buffers."""
+        pm, pt = C.c_void_p(), C.c_void_p()
+        dpk, kpr = C.c_int64(), C.c_int32()
+        self._ck(self.L.cafe_gpu_matrix_storage(self.h, C.byref(pm), C.byref(pt), C.byref(dpk), C.byref(kpr)), "matrix_storage")
+        return pm.value, pt.value, dpk.value, kpr.value
+
+    def matrices_exchanged(self):
+        self._ck(self.L.cafe_gpu_matrices_exchanged(self.h), "matrices_exchanged")
 
     def family_results(self):
         lp = np.zeros(self.F)

@@ -44,6 +44,41 @@ def reduce_score(local2, group=None):
     return s, z
 
 
+class _DeviceBuffer:
+    """A device allocation owned by the C-ABI library, exposed to torch through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, n_doubles: int):
+        self.__cuda_array_interface__ = {"shape": (n_doubles,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def gather_chunks(full, rank: int, world_size: int, group=None):
+    """In-place all-gather over a flat tensor of world_size equal chunks: chunk `rank` holds this rank's data on entry,
+    every chunk is filled on return.  (CPU tensors with gloo work too.)"""
+    import torch.distributed as dist
+
+    chunk = full.numel() // world_size
+    dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk], group=group)
+    return full
+
+
+def objective_sharded(g, lam_node, mu_node, out2, rank: int, world_size: int, device, group=None):
+    """One objective evaluation with BOTH kernels sharded: every rank builds ceil(D/world) of the D distinct transition
+    matrices (K1), two in-place NCCL all-gathers over NVLink (M and its transposed copy) give every rank all of them, then
+    K2+K3 run on this rank's families and the 2-double reduction follows (reduce_score).  The matrices of BASELINE configs[1]
+    are 20 x 0.5 MB x 2, those of configs[2] 98 x 2 MB x 2.  g must have had set_key_shard(rank, world_size)."""
+    import torch
+
+    g.set_rates(lam_node, mu_node)
+    g.build_matrices()
+    pm, pt, dpk, kpr = g.matrix_storage()
+    n = dpk * kpr * world_size
+    for ptr in (pm, pt):
+        gather_chunks(torch.as_tensor(_DeviceBuffer(ptr, n), device=device), rank, world_size, group)
+    g.matrices_exchanged()
+    g.score_device(out2.data_ptr())
+    return reduce_score(out2, group)
+
+
 def finish_score(s, z):
     """Host-side decode of reduce_score's result: (-inf, index) when some family had zero likelihood."""
     s, z = float(s), float(z)

@@ -126,6 +126,20 @@ int cafe_gpu_objective(cafe_gpu_ctx* ctx, const double* lambda_per_node, const d
 int cafe_gpu_objective_device(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node,
                               double* out_device /* device pointer, 2 doubles */);
 
+/* Device-resident score of the current matrices (K2+K3 only): out_device as for cafe_gpu_objective_device. */
+int cafe_gpu_score_device(cafe_gpu_ctx* ctx, double* out_device /* device pointer, 2 doubles */);
+
+/* K1 sharded across ranks (one context per GPU, every rank with the same tree and rates).  After cafe_gpu_set_key_shard
+ * (rank, world), cafe_gpu_build_matrices builds only this rank's contiguous chunk of keys_per_rank = ceil(D / world) distinct
+ * keys; the caller then all-gathers the chunks IN PLACE over the two device buffers returned by cafe_gpu_matrix_storage
+ * (chunk r = doubles [r * keys_per_rank * doubles_per_key, +keys_per_rank * doubles_per_key) of d_M and of d_MT, e.g. one
+ * ncclAllGather each) and calls cafe_gpu_matrices_exchanged; scoring before that fails with CAFE_GPU_ERR_STATE.  The
+ * reference builds all matrices in one `omp for` (libtree/birthdeath.c:331-343) — this is its distributed equivalent.
+ * world == 1 restores the unsharded behaviour. */
+int cafe_gpu_set_key_shard(cafe_gpu_ctx* ctx, int rank, int world);
+int cafe_gpu_matrix_storage(cafe_gpu_ctx* ctx, void** d_M, void** d_MT, int64_t* doubles_per_key, int32_t* keys_per_rank);
+int cafe_gpu_matrices_exchanged(cafe_gpu_ctx* ctx);
+
 /* Per-family results of the last score: log(max posterior), max likelihood, argmax_j L[j]
  * (the `maxlh` side effect, cafe/lambda.cpp:672-676).  Any pointer may be NULL. */
 int cafe_gpu_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, double* max_likelihood,

@@ -80,3 +80,26 @@ def test_reduce_score_without_process_group():
     assert sharding.finish_score(s, z) == (-12.5, -1)
     s, z = sharding.reduce_score(torch.tensor([-12.5, 7.0], dtype=torch.float64))
     assert sharding.finish_score(s, z) == (-np.inf, 7)
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the matrix buffers of a sharded K1: D = 5 keys -> keys_per_rank = 3, buffers hold 3 * 2 matrices of 4 doubles;
+    # every rank has filled its own chunk only (key k holds the value 10 + k), the rest is stale
+    keys_per_rank, per_key, D = 3, 4, 5
+    full = torch.full((keys_per_rank * world * per_key,), -1.0, dtype=torch.float64)
+    for k in range(rank * keys_per_rank, min(D, (rank + 1) * keys_per_rank)):
+        full[k * per_key:(k + 1) * per_key] = 10.0 + k
+    sharding.gather_chunks(full, rank, world)
+    out[rank] = full.view(-1, per_key)[:D, 0].tolist()
+    dist.destroy_process_group()
+
+
+def test_in_place_chunk_gather_gives_every_rank_all_keys():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gather_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert out[0] == out[1] == [10.0, 11.0, 12.0, 13.0, 14.0]

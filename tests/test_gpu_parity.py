@@ -334,3 +334,43 @@ def test_k2_config2_full_size_properties():
     o = po.oracle_score(want_L=False)
     assert np.abs(lp[idx] - o["logpost"]).max() <= TOL_LOGPOST
     assert rel_err(ml[idx], o["maxlik"], 1e-290).max() <= TOL_L
+
+
+def test_k1_key_shard_two_contexts_match_unsharded():
+    # cafe_gpu_set_key_shard: two contexts stand in for two ranks; the "all-gather" is two device copies through torch
+    import torch
+    from cafe_b200 import sharding
+    counts = small_counts(5, 64, 22, 31)
+    p = Problem(EXAMPLE_TREE, counts, [0.002, 0.006], lambda_tree="(((2,2)1,(1,1)1)1,1)")
+    ref = p.make_gpu()
+    s_ref, _ = ref.score()
+    D = ref.num_keys()
+    assert D >= 3
+    ctxs = []
+    for rank in range(2):
+        g = p.make_gpu()            # builds everything once (unsharded) ...
+        g.set_key_shard(rank, 2)    # ... then only its own chunk
+        g.set_rates(p.lam_node, p.mu_node)
+        g.build_matrices()
+        with pytest.raises(Exception):
+            g.score()               # not before the exchange
+        ctxs.append(g)
+    views = []
+    for g in ctxs:
+        pm, pt, dpk, kpr = g.matrix_storage()
+        assert kpr == (D + 1) // 2
+        views.append([torch.as_tensor(sharding._DeviceBuffer(ptr, dpk * kpr * 2), device="cuda") for ptr in (pm, pt)])
+    torch.cuda.synchronize()
+    chunk = views[0][0].numel() // 2
+    for which in range(2):
+        views[1][which][:chunk].copy_(views[0][which][:chunk])      # rank 0's chunk -> rank 1
+        views[0][which][chunk:].copy_(views[1][which][chunk:])      # rank 1's chunk -> rank 0
+    torch.cuda.synchronize()
+    for g in ctxs:
+        g.matrices_exchanged()
+        s, fz = g.score()
+        assert fz == -1 and s == s_ref
+        for node in (0, 2, 4):
+            assert np.array_equal(g.get_matrix(node), ref.get_matrix(node))
+        g.close()
+    ref.close()
