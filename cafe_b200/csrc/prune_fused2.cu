@@ -506,6 +506,18 @@ __device__ __forceinline__ void mma_frags(double (&acc)[MB][NB][2], const double
         for (int nb = 0; nb < NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], fa[mb], fb[nb]);
 }
 
+// non-blocking probe of an mbarrier phase: issued a few k4-steps before the result is needed
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok;
+}
+
 // STEPS k4-steps (one or two full K blocks of a ring stage).  The fragments of the next step are fetched before the DMMAs of the
 // current one; after the last step (do_next) the first fragments of whatever follows - the next K block of the stage, or the
 // next stage after its mbarrier wait (~100 cycles even when already full) - so that neither sits between two DMMAs.
@@ -514,13 +526,16 @@ __device__ __forceinline__ void steps_full(double (&acc)[MB][NB][2], double (&fa
                                            const unsigned char* sb, const int (&koff)[4], bool do_next, const unsigned char* next_a,
                                            const unsigned char* next_b, uint64_t* wait_bar, uint32_t wait_phase,
                                            bool prof, long long& t_wait_full) {
+    uint32_t ready = 0;
 #pragma unroll
     for (int kk = 0; kk < STEPS; ++kk) {
+        // probe the next stage's barrier two steps early: its ~100-cycle latency then never sits between two DMMAs
+        if (STEPS >= 4 && kk == STEPS - 3 && do_next && wait_bar) ready = mbar_test(wait_bar, wait_phase);
         if (kk + 1 < STEPS) {
             const int j = (kk + 1) >> 2;
             load_frags<MBV>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sa + j * SUB_BYTES, sb + j * SUB_BYTES, koff[(kk + 1) & 3]);
         } else if (do_next) {
-            if (wait_bar) {
+            if (wait_bar && !ready) {
                 const long long t0 = prof ? clock64() : 0;
                 mbar_wait(wait_bar, wait_phase);
                 if (prof) t_wait_full += clock64() - t0;
