@@ -328,10 +328,12 @@ static int ensure_matrix_buffers(cafe_gpu_ctx* ctx) {
         cudaFree(ctx->d_M); cudaFree(ctx->d_MT); ctx->d_M = ctx->d_MT = nullptr;
         size_t cap = std::max<size_t>(need, (size_t)ctx->n_nodes - 1 + ctx->shard_world);  // never more keys than branches
         size_t bytes = cap * ctx->Sp * ctx->Sp * sizeof(double);
+        // the transposed copy carries n_leaves extra matrices behind the keys: the error-model leaf matrices of prune_fused2.cu
+        size_t bytes_t = (cap + ctx->n_leaves) * ctx->Sp * ctx->Sp * sizeof(double);
         CAFE_CK(ctx, cudaMalloc(&ctx->d_M, bytes));
-        CAFE_CK(ctx, cudaMalloc(&ctx->d_MT, bytes));
+        CAFE_CK(ctx, cudaMalloc(&ctx->d_MT, bytes_t));
         CAFE_CK(ctx, cudaMemsetAsync(ctx->d_M, 0, bytes, ctx->stream));   // padding stays zero forever
-        CAFE_CK(ctx, cudaMemsetAsync(ctx->d_MT, 0, bytes, ctx->stream));
+        CAFE_CK(ctx, cudaMemsetAsync(ctx->d_MT, 0, bytes_t, ctx->stream));
         ctx->mat_cap = cap;
     }
     if ((int)D > ctx->keys_cap) {

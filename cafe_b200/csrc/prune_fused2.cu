@@ -1,5 +1,4 @@
-// prune_fused2.cu — K2, second generation of the fused persistent pruning kernel (the default path when no
-// leaf carries an error model).
+// prune_fused2.cu — K2, second generation of the fused persistent pruning kernel (the default path).
 //
 // Replaces, per objective evaluation, the reference's F x (2n-2) calls of square_matrix_multiply
 // (libtree/birthdeath.c:163-182) under compute_internal_node_likelihood (cafe/cafe_tree.c:226-271),
@@ -870,6 +869,25 @@ k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// Error-model leaves (cafe_tree.c:196-203): the leaf vector is row `observed` of the error matrix, so the leaf's factor is
+// factor[i] = sum_j M[i][j] * E[observed][j] (birthdeath.c:172-180).  Built once per evaluation as ONE more transposed matrix
+// per such leaf, MTE[observed][i] - same terms, same ascending-j order, one rounding per product and per sum, true sizes above
+// colmax skipped as the matvec's column window does - the fused kernel then gathers a row of it exactly like a row of MT.
+__global__ void __launch_bounds__(256)
+k_err_leaf_matrix(const double* __restrict__ MTsrc, const int* __restrict__ rowptr, const int* __restrict__ col,
+                  const double* __restrict__ val, int dim, int Sp, int colmax, double* __restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x, o = blockIdx.y;
+    if (i >= Sp) return;
+    double s = 0.0;
+    if (o < dim) {
+        for (int k = rowptr[o]; k < rowptr[o + 1]; ++k) {
+            const int j = col[k];
+            if (j <= colmax) s = __dadd_rn(s, __dmul_rn(MTsrc[(size_t)j * Sp + i], val[k]));
+        }
+    }
+    out[(size_t)o * Sp + i] = s;
+}
+
 }  // namespace fused2
 
 // =================================================================================================
@@ -914,7 +932,6 @@ bool fused2_supported(const cafe_gpu_ctx* ctx) {
     if (ctx->n_leaves < 3) return false;                 // the root of a two-leaf tree is itself a leaf pair
     if (ctx->n_nodes > fused2::OPFLAGS_CAP) return false;
     if (ctx->max_count >= ctx->W) return false;          // a one-hot leaf outside the matvec columns needs the guarded path
-    for (int e : ctx->leaf_err) if (e >= 0) return false;  // error-model leaves are sparse row combinations (prune_fused.cu)
     return true;
 }
 
@@ -923,6 +940,12 @@ bool fused2_supported(const cafe_gpu_ctx* ctx) {
 static void build_schedule2(const cafe_gpu_ctx* ctx, Fused2State& st) {
     using fused2::Op;
     const int n = ctx->n_nodes;
+    // matrix index of a leaf's factor rows: its branch's key, or its own error-model matrix behind the keys (launch_prune_fused2)
+    auto leaf_key = [&](int leaf_node) {
+        const int k = leaf_node / 2;
+        const bool err = !ctx->leaf_err.empty() && ctx->leaf_err[k] >= 0;
+        return err ? (int)ctx->mat_cap + k : ctx->node_key[leaf_node];
+    };
     auto is_leaf = [&](int v) { return ctx->left[v] < 0; };
     auto is_cherry = [&](int v) { return !is_leaf(v) && is_leaf(ctx->left[v]) && is_leaf(ctx->right[v]); };
     auto is_virtual = [&](int v) { return is_leaf(v) || is_cherry(v); };
@@ -950,8 +973,8 @@ static void build_schedule2(const cafe_gpu_ctx* ctx, Fused2State& st) {
         if (is_cherry(child)) {
             const int a = ctx->left[child], b = ctx->right[child];
             op.a_kind = 1; op.in_slot = n_cherry++;
-            op.leaf_a1 = a / 2; op.key_a1 = ctx->node_key[a];
-            op.leaf_a2 = b / 2; op.key_a2 = ctx->node_key[b];
+            op.leaf_a1 = a / 2; op.key_a1 = leaf_key(a);
+            op.leaf_a2 = b / 2; op.key_a2 = leaf_key(b);
         } else {
             op.a_kind = 0; op.in_slot = slot;
         }
@@ -965,7 +988,7 @@ static void build_schedule2(const cafe_gpu_ctx* ctx, Fused2State& st) {
             const int sg = is_cherry(gch) ? -1 : eval(gch);
             op.out_slot = alloc();
             gemm_over(op, gch, sg);
-            op.other_kind = 1; op.leaf_o = l / 2; op.key_o = ctx->node_key[l];
+            op.other_kind = 1; op.leaf_o = l / 2; op.key_o = leaf_key(l);
             st.ops.push_back(op);
             if (sg >= 0) free_slots.push_back(sg);
             return op.out_slot;
@@ -1006,6 +1029,19 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
         CAFE_CK(ctx, cudaMalloc(&st.d_ops, st.ops_cap * sizeof(Op)));
     }
     CAFE_CK(ctx, cudaMemcpyAsync(st.d_ops, st.ops.data(), st.ops.size() * sizeof(Op), cudaMemcpyHostToDevice, ctx->stream));
+
+    // ---- error-model leaves: one extra transposed matrix each, behind the keys ----
+    for (int k = 0; k < ctx->n_leaves; ++k) {
+        const int e = ctx->leaf_err.empty() ? -1 : ctx->leaf_err[k];
+        if (e < 0) continue;
+        const ErrModelDev& E = ctx->errs[e];
+        const size_t mat = (size_t)ctx->Sp * ctx->Sp;
+        dim3 g((ctx->Sp + 255) / 256, ctx->Sp);
+        k_err_leaf_matrix<<<g, 256, 0, ctx->stream>>>(ctx->d_MT + (size_t)ctx->node_key[2 * k] * mat, E.d_rowptr, E.d_col, E.d_val, E.dim,
+                                                      ctx->Sp, ctx->W - 1, ctx->d_MT + ((size_t)ctx->mat_cap + k) * mat);
+        ctx->launches++;
+    }
+    CAFE_CK(ctx, cudaGetLastError());
 
     // ---- geometry: one CTA per SM, every CTA at least two 8-family blocks ----
     const int n_mblocks = (ctx->F + 7) / 8;

@@ -374,3 +374,33 @@ def test_k1_key_shard_two_contexts_match_unsharded():
             assert np.array_equal(g.get_matrix(node), ref.get_matrix(node))
         g.close()
     ref.close()
+
+
+def test_k2_error_model_same_bits_on_both_fused_kernels():
+    # error-model leaves: prune_fused2.cu gathers rows of a per-leaf matrix MTE = E x MT built once per evaluation,
+    # prune_fused.cu combines the rows in its epilogue - same terms in the same order, so the results are identical
+    import os
+    rg = chost.init_family_size(60)
+    E = _band_error_matrix(rg["max"] + 1, 0.0274)
+    nw = random_tree(13, 4)
+    counts = np.minimum(small_counts(13, 200, 55, 41), 60)
+    res = []
+    for env in (None, "CAFE_GPU_FUSED_V1"):
+        if env:
+            os.environ[env] = "1"
+        try:
+            p = Problem(nw, counts, 0.004, err={k: E for k in range(0, 13, 2)},   # every second leaf has the error model
+                        ranges=(rg["min"], rg["max"], rg["root_min"], rg["root_max"]))
+            g = p.make_gpu()
+            s, fz = g.score()
+            res.append((s, fz, g.family_likelihoods(), g.family_results()))
+            g.close()
+        finally:
+            if env:
+                os.environ.pop(env, None)
+    (s2, fz2, L2, r2), (s1, fz1, L1, r1) = res
+    assert fz1 == fz2 == -1
+    assert np.array_equal(L1, L2) and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+    assert np.abs(r1[0] - r2[0]).max() <= 1e-12 and abs(s1 - s2) <= 1e-9
+    o = p.oracle_score(want_L=True)
+    assert rel_err(L2[o["L"] > 1e-290], o["L"][o["L"] > 1e-290]).max() <= TOL_L
