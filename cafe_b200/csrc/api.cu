@@ -498,6 +498,13 @@ int cafe_gpu_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, double
     return CAFE_GPU_OK;
 }
 
+int cafe_gpu_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_likelihood_out) {
+    if (!ctx || !node_sizes_out) return CAFE_GPU_ERR_ARG;
+    int rc = check_ready(ctx, "viterbi");
+    if (rc) return rc;
+    return run_viterbi(ctx, node_sizes_out, max_likelihood_out);
+}
+
 int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {
     if (!ctx || !L_out) return CAFE_GPU_ERR_ARG;
     int rc = check_ready(ctx, "family_likelihoods");

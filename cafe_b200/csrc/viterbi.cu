@@ -1,0 +1,225 @@
+// viterbi.cu — Viterbi ancestral reconstruction for every family.
+//
+// Replaces cafe_tree_viterbi (cafe/viterbi.cpp:494-521) as driven per family by the report / viterbi commands:
+// the max-product pruning of __cafe_tree_node_compute_viterbi (:209-321) in post-order, then the back-track of
+// __cafe_tree_node_backtrack_viterbi (:323-351) in prefix order.  Same data flow as K2 with (max, argmax) in place of the sum:
+//     factor_c[i] = max_j M_c[r0+i][j] * L_c[j]      (strict ">" from 0: the first maximum wins, an all-zero row keeps pointer 0)
+//     L_v[i]      = factor_left[i] * factor_right[i]
+// A (max, x) semiring product has no tensor-core form; the kernel keeps the K2 layout instead (transposed matrices, so that the
+// threads of a block - consecutive output sizes - read consecutive addresses, 8 families per block to reuse every matrix element
+// from registers) and is bound by the fp64 pipe (one DMUL + one compare per matrix element and family).
+// Every leaf must carry an observed size (the reference's "familysize < 0" branch for missing data is not implemented).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int VT_THREADS = 128;  // output sizes per block
+constexpr int VT_FB = 8;         // families per block
+
+struct VitChild {
+    int is_leaf;
+    const double* MT;        // transposed matrix of the child's branch
+    const int* counts;       // leaf: observed sizes [F_pad] of this leaf (+ family offset)
+    const int* err_rowptr;   // leaf with error model: sparse rows, else nullptr
+    const int* err_col;
+    const double* err_val;
+    const double* L;         // internal child: its vector [FC][Vp]
+    short* vit;              // back-pointers of the child [FC][Vp]
+};
+
+// one internal node: both children, FB families x VT_THREADS output sizes per block
+__global__ void __launch_bounds__(VT_THREADS)
+k_viterbi_node(VitChild A, VitChild B, int Sp, int Vp, int W, int r0, int nrows, int n_fam, double* __restrict__ Lout) {
+    extern __shared__ double sL[];  // [VT_FB][W] child vector of the families of this block
+    const int i = blockIdx.x * VT_THREADS + threadIdx.x;  // output size index
+    const int f0 = blockIdx.y * VT_FB;
+    const int nf = min(VT_FB, n_fam - f0);
+    double prod[VT_FB];
+#pragma unroll
+    for (int u = 0; u < VT_FB; ++u) prod[u] = 1.0;
+
+    for (int side = 0; side < 2; ++side) {
+        const VitChild& C = side ? B : A;
+        double best[VT_FB]; int arg[VT_FB];
+#pragma unroll
+        for (int u = 0; u < VT_FB; ++u) { best[u] = 0.0; arg[u] = 0; }
+        if (C.is_leaf) {
+            if (i < nrows) {
+                for (int u = 0; u < nf; ++u) {
+                    const int cnt = C.counts[f0 + u];
+                    if (C.err_rowptr == nullptr) {
+                        // one-hot leaf (:262-266): the only non-zero product is M[s][count]
+                        const double v = (cnt < W) ? C.MT[(size_t)cnt * Sp + r0 + i] : 0.0;
+                        if (v > 0.0) { best[u] = v; arg[u] = cnt; }
+                    } else {
+                        // error-model leaf (:252-260): L[j] = errormatrix[count][j], ascending j
+                        for (int k = C.err_rowptr[cnt]; k < C.err_rowptr[cnt + 1]; ++k) {
+                            const int j = C.err_col[k];
+                            if (j < W) {
+                                const double v = __dmul_rn(C.MT[(size_t)j * Sp + r0 + i], C.err_val[k]);
+                                if (v > best[u]) { best[u] = v; arg[u] = j; }
+                            }
+                        }
+                    }
+                }
+            }
+        } else {
+            __syncthreads();
+            for (int x = threadIdx.x; x < VT_FB * W; x += VT_THREADS) {
+                const int u = x / W, j = x - u * W;
+                sL[x] = (u < nf) ? C.L[(size_t)(f0 + u) * Vp + j] : 0.0;
+            }
+            __syncthreads();
+            if (i < nrows) {
+                const double* __restrict__ mcol = C.MT + r0 + i;
+                for (int j = 0; j < W; ++j) {
+                    const double m = mcol[(size_t)j * Sp];
+#pragma unroll
+                    for (int u = 0; u < VT_FB; ++u) {
+                        const double v = __dmul_rn(m, sL[u * W + j]);
+                        if (v > best[u]) { best[u] = v; arg[u] = j; }
+                    }
+                }
+            }
+        }
+        if (i < nrows) {
+            for (int u = 0; u < nf; ++u) {
+                C.vit[(size_t)(f0 + u) * Vp + i] = (short)arg[u];
+                prod[u] = __dmul_rn(prod[u], best[u]);
+            }
+        }
+    }
+    if (i < Vp)
+        for (int u = 0; u < nf; ++u) Lout[(size_t)(f0 + u) * Vp + i] = (i < nrows) ? prod[u] : 0.0;
+}
+
+// back-track: one thread per family, prefix order (parent before child)
+__global__ void __launch_bounds__(128)
+k_viterbi_backtrack(const int* __restrict__ prefix, int n_prefix, const int* __restrict__ parent, const int* __restrict__ is_leaf,
+                    const int* __restrict__ leaf_ord, int root, const double* __restrict__ Lroot, const short* __restrict__ vit,
+                    size_t node_stride, int Vp, int R, int root_min, int range_min, const int* __restrict__ counts, int F_pad,
+                    int fam0, int n_fam, int n_nodes, int* __restrict__ sizes_out, double* __restrict__ maxlik_out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_fam) return;
+    int* sz = sizes_out + (size_t)(fam0 + f) * n_nodes;
+    for (int p = 0; p < n_prefix; ++p) {
+        const int v = prefix[p];
+        if (is_leaf[v]) { sz[v] = counts[(size_t)leaf_ord[v] * F_pad + fam0 + f]; continue; }
+        if (v == root) {
+            const double* L = Lroot + (size_t)f * Vp;
+            double ml = L[0]; int am = 0;
+            for (int i = 1; i < R; ++i) if (L[i] > ml) { ml = L[i]; am = i; }  // __maxidx: first maximum
+            sz[v] = root_min + am;
+            if (maxlik_out) maxlik_out[fam0 + f] = ml;
+        } else {
+            const int par = parent[v];
+            const int base = (par == root) ? root_min : range_min;
+            sz[v] = vit[(size_t)v * node_stride + (size_t)f * Vp + (sz[par] - base)] + range_min;
+        }
+    }
+}
+
+}  // namespace
+
+int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out) {
+    const int n = ctx->n_nodes, F = ctx->F, Vp = ctx->Vp, W = ctx->W, Sp = ctx->Sp;
+    if (W > 32767) CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "viterbi: vector longer than the 16-bit back-pointers");
+    const size_t mat = (size_t)Sp * Sp;
+    // families per chunk: vectors (8 B) of the internal nodes + back-pointers (2 B) of all nodes, <= ~1.5 GB
+    const int n_internal = n / 2;
+    size_t per_family = (size_t)Vp * (8 * (size_t)n_internal + 2 * (size_t)n);
+    int FC = (int)std::max<size_t>(VT_FB, std::min<size_t>((size_t)F, (size_t)(1500u << 20) / per_family));
+    FC = (FC + VT_FB - 1) / VT_FB * VT_FB;
+
+    // prefix order with the root first; parents, leaf flags
+    std::vector<int> prefix, parent(n, -1), is_leaf(n, 0), leaf_ord(n, 0), slot_of(n, -1);
+    {
+        std::vector<int> st{ctx->root};
+        while (!st.empty()) {
+            int v = st.back(); st.pop_back();
+            prefix.push_back(v);
+            if (ctx->left[v] >= 0) { st.push_back(ctx->right[v]); st.push_back(ctx->left[v]); }
+        }
+        int s = 0;
+        for (int v = 0; v < n; ++v) {
+            if (ctx->left[v] >= 0) { parent[ctx->left[v]] = v; parent[ctx->right[v]] = v; slot_of[v] = s++; }
+            else { is_leaf[v] = 1; leaf_ord[v] = v / 2; }
+        }
+    }
+    int *d_prefix = nullptr, *d_parent = nullptr, *d_is_leaf = nullptr, *d_leaf_ord = nullptr, *d_sizes = nullptr;
+    double *d_L = nullptr, *d_ml = nullptr;
+    short* d_vit = nullptr;
+    auto cleanup = [&]() { cudaFree(d_prefix); cudaFree(d_parent); cudaFree(d_is_leaf); cudaFree(d_leaf_ord); cudaFree(d_sizes); cudaFree(d_L); cudaFree(d_ml); cudaFree(d_vit); };
+#define VT_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return CAFE_GPU_ERR_CUDA; } } while (0)
+    VT_CK(cudaMalloc(&d_prefix, n * sizeof(int)));
+    VT_CK(cudaMalloc(&d_parent, n * sizeof(int)));
+    VT_CK(cudaMalloc(&d_is_leaf, n * sizeof(int)));
+    VT_CK(cudaMalloc(&d_leaf_ord, n * sizeof(int)));
+    VT_CK(cudaMalloc(&d_sizes, (size_t)F * n * sizeof(int)));
+    VT_CK(cudaMalloc(&d_ml, (size_t)F * sizeof(double)));
+    VT_CK(cudaMalloc(&d_L, (size_t)n_internal * FC * Vp * sizeof(double)));
+    VT_CK(cudaMalloc(&d_vit, (size_t)n * FC * Vp * sizeof(short)));
+    VT_CK(cudaMemcpyAsync(d_prefix, prefix.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    VT_CK(cudaMemcpyAsync(d_parent, parent.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    VT_CK(cudaMemcpyAsync(d_is_leaf, is_leaf.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    VT_CK(cudaMemcpyAsync(d_leaf_ord, leaf_ord.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t node_stride = (size_t)FC * Vp;
+
+    // post-order list of the internal nodes
+    std::vector<int> post;
+    {
+        std::vector<std::pair<int, int>> st{{ctx->root, 0}};
+        while (!st.empty()) {
+            auto [v, state] = st.back(); st.pop_back();
+            if (ctx->left[v] < 0) continue;
+            if (state == 0) { st.push_back({v, 1}); st.push_back({ctx->right[v], 0}); st.push_back({ctx->left[v], 0}); }
+            else post.push_back(v);
+        }
+    }
+    const size_t smem = (size_t)VT_FB * W * sizeof(double);
+    VT_CK(cudaFuncSetAttribute(k_viterbi_node, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+
+    for (int fam0 = 0; fam0 < F; fam0 += FC) {
+        const int nf = std::min(FC, F - fam0);
+        for (int v : post) {
+            const bool is_root = (v == ctx->root);
+            const int r0 = is_root ? ctx->root_min : ctx->rmin;
+            const int nrows = is_root ? ctx->R : W;
+            VitChild ch[2];
+            const int kids[2] = {ctx->left[v], ctx->right[v]};
+            for (int s = 0; s < 2; ++s) {
+                const int c = kids[s];
+                VitChild& C = ch[s];
+                C.is_leaf = ctx->left[c] < 0;
+                C.MT = ctx->d_MT + (size_t)ctx->node_key[c] * mat;
+                C.counts = nullptr; C.err_rowptr = nullptr; C.err_col = nullptr; C.err_val = nullptr; C.L = nullptr;
+                C.vit = d_vit + (size_t)c * node_stride;
+                if (C.is_leaf) {
+                    const int k = c / 2;
+                    C.counts = ctx->d_counts + (size_t)k * ctx->F_pad + fam0;
+                    const int e = ctx->leaf_err.empty() ? -1 : ctx->leaf_err[k];
+                    if (e >= 0) { C.err_rowptr = ctx->errs[e].d_rowptr; C.err_col = ctx->errs[e].d_col; C.err_val = ctx->errs[e].d_val; }
+                } else {
+                    C.L = d_L + (size_t)slot_of[c] * node_stride;
+                }
+            }
+            dim3 grid((Vp + VT_THREADS - 1) / VT_THREADS, (nf + VT_FB - 1) / VT_FB);
+            k_viterbi_node<<<grid, VT_THREADS, smem, ctx->stream>>>(ch[0], ch[1], Sp, Vp, W, r0, nrows, nf,
+                                                                    d_L + (size_t)slot_of[v] * node_stride);
+            ctx->launches++;
+        }
+        k_viterbi_backtrack<<<(nf + 127) / 128, 128, 0, ctx->stream>>>(
+            d_prefix, n, d_parent, d_is_leaf, d_leaf_ord, ctx->root, d_L + (size_t)slot_of[ctx->root] * node_stride, d_vit, node_stride, Vp,
+            ctx->R, ctx->root_min, ctx->rmin, ctx->d_counts, ctx->F_pad, fam0, nf, n, d_sizes, d_ml);
+        ctx->launches++;
+        VT_CK(cudaGetLastError());
+    }
+    if (sizes_out) VT_CK(cudaMemcpyAsync(sizes_out, d_sizes, (size_t)F * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (maxlik_out) VT_CK(cudaMemcpyAsync(maxlik_out, d_ml, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    VT_CK(cudaStreamSynchronize(ctx->stream));
+#undef VT_CK
+    cleanup();
+    return CAFE_GPU_OK;
+}

@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "cafe_gpu_conditional_distribution", "cafe_gpu_pvalues", "cafe_gpu_launch_count",
     "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_timing_collect", "cafe_gpu_score_flops",
     "cafe_gpu_score_device", "cafe_gpu_set_key_shard", "cafe_gpu_matrix_storage", "cafe_gpu_matrices_exchanged",
+    "cafe_gpu_viterbi",
 ]
 
 
@@ -64,6 +65,7 @@ def load_library():
     L.cafe_gpu_set_key_shard.argtypes = [vp, C.c_int, C.c_int]
     L.cafe_gpu_matrix_storage.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     L.cafe_gpu_matrices_exchanged.argtypes = [vp]
+    L.cafe_gpu_viterbi.argtypes = [vp, _ip, _dp]
     L.cafe_gpu_family_results.argtypes = [vp, _dp, _dp, _ip]
     L.cafe_gpu_family_likelihoods.argtypes = [vp, _dp]
     L.cafe_gpu_conditional_distribution.argtypes = [vp, C.c_int, _dp, C.c_uint64, _dp]
@@ -219,6 +221,13 @@ class CafeGpu:
         am = np.zeros(self.F, dtype=np.int32)
         self._ck(self.L.cafe_gpu_family_results(self.h, _d(lp), _d(ml), _i(am)), "family_results")
         return lp, ml, am
+
+    def viterbi(self):
+        """(sizes[F][n_nodes] int32 in nlist order, max root likelihood[F]) — cafe_tree_viterbi for every family."""
+        sizes = np.zeros((self.F, self.n_nodes), dtype=np.int32)
+        ml = np.zeros(self.F)
+        self._ck(self.L.cafe_gpu_viterbi(self.h, _i(sizes), _d(ml)), "viterbi")
+        return sizes, ml
 
     def family_likelihoods(self):
         out = np.zeros((self.F, self.R))

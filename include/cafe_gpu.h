@@ -148,6 +148,12 @@ int cafe_gpu_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, double
  * (get_likelihoods, cafe/cafe_tree.c:325-329).  Recomputes with the current matrices. */
 int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out);
 
+/* Viterbi ancestral reconstruction (cafe_tree_viterbi, cafe/viterbi.cpp:494-521; max-product pruning :209-321 and
+ * back-track :323-351) for every family with the current matrices: node_sizes_out[f * n_nodes + v] = reconstructed size of
+ * node v (nlist order; leaves keep their observed size), max_likelihood_out[f] (nullable) = max_i of the root's max-product
+ * vector.  Every leaf must carry an observed size (missing data, familysize < 0, is not supported). */
+int cafe_gpu_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_likelihood_out);
+
 /* K4: conditional distribution (cafe/conditional_distribution.cpp:10-120): for every root size
  * s = root_min..root_max, n_samples simulated families (cafe/cafe_tree.c:533-569), each pruned with
  * root range {s} and the range.max ratchet of conditional_distribution.cpp:29; rows sorted ascending.

@@ -62,6 +62,8 @@ def lib():
     L.orc_prune.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _ip, _dpp, C.c_int,
                             C.c_int, C.c_int, C.c_int, C.c_int, _dp]
     L.orc_posterior.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _ip]
+    L.orc_viterbi.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _ip, _dpp, C.c_int,
+                              C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp]
     L.orc_score.restype = C.c_double
     L.orc_score.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _dpp, C.c_int,
                             C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int, _ip, _ip,
@@ -115,6 +117,8 @@ def ref():
     R.refshim_set_errormodel.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int, C.c_int]
     R.refshim_read_errormodel.restype = C.c_int
     R.refshim_read_errormodel.argtypes = [C.c_char_p, C.c_int, _dp, _ip, _ip]
+    R.refshim_viterbi.restype = C.c_double
+    R.refshim_viterbi.argtypes = [C.c_void_p, _ip, _ip]
     R.refshim_likelihoods.restype = C.c_int
     R.refshim_likelihoods.argtypes = [C.c_void_p, _ip, _dp]
     R.refshim_set_families.argtypes = [C.c_void_p, C.c_int, _ip, C.c_int]
@@ -285,6 +289,26 @@ def prune(tree: FlatTree, mats, counts_by_leaf, rng, leaf_err=None):
     if rc != 0:
         raise ValueError("leaf count outside the likelihood vector")
     return out
+
+
+def viterbi(tree: FlatTree, mats, counts_by_leaf, rng, leaf_err=None):
+    """cafe_tree_viterbi for one family: (sizes per node in nlist order, max root likelihood)."""
+    S = next(m for m in mats if m is not None).shape[0]
+    lc = np.full(tree.n_nodes, -1, dtype=np.int32)
+    lc[0::2] = counts_by_leaf
+    mp, keep = _matrix_ptrs(mats)
+    E = 0
+    ep = None
+    if leaf_err is not None:
+        ep, keep2 = _matrix_ptrs(leaf_err)
+        E = next(m for m in leaf_err if m is not None).shape[0]
+    sizes = np.zeros(tree.n_nodes, dtype=np.int32)
+    ml = C.c_double(0)
+    rc = lib().orc_viterbi(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S, _iptr(lc),
+                           ep, E, rng[0], rng[1], rng[2], rng[3], _iptr(sizes), C.byref(ml))
+    if rc != 0:
+        raise ValueError("leaf count outside the likelihood vector")
+    return sizes, ml.value
 
 
 def score(tree: FlatTree, mats, counts, rng, prior, ref_idx=None, leaf_err=None, want_L=False):

@@ -371,3 +371,97 @@ double orc_family_pvalue(int n_nodes, const int *left, const int *right, int roo
     free(L);
     return best;
 }
+
+/* ------------------------------------------------------------------ Viterbi ancestral reconstruction */
+
+/* cafe_tree_viterbi (cafe/viterbi.cpp:494-521): max-product pruning in post-order
+ * (__cafe_tree_node_compute_viterbi :209-321) followed by the back-track in prefix order
+ * (__cafe_tree_node_backtrack_viterbi :323-351).  All leaves carry an observed size (the reference's
+ * "familysize < 0" branch for missing data is not restated).  sizes_out[v] = reconstructed size of node v
+ * (leaves keep their observed size); *root_max_lik = max_i L_root[i].
+ * Per child: factor[i] = max_j M_child[s][c] * L_child[j] with a strict ">" from 0 (first maximum wins; a row
+ * whose products are all 0 keeps back-pointer 0, the calloc'ed initial value of pcnode->viterbi). */
+typedef struct {
+    int n_nodes; const int *left, *right; int root;
+    const double *const *node_matrix; int S;
+    const int *leaf_count; const double *const *leaf_err; int E;
+    int rmin, rmax, root_min, root_max, size_of_factor;
+    double *lik; int *vit; double *f[2];
+} vit_ctx;
+
+static void vit_node(vit_ctx *cx, int v)
+{
+    double *Lv = cx->lik + (size_t)v * cx->size_of_factor;
+    if (cx->left[v] < 0) { /* leaf, :251-267 */
+        memset(Lv, 0, sizeof(double) * cx->size_of_factor);
+        int fs = cx->leaf_count[v];
+        if (cx->leaf_err && cx->leaf_err[v]) {
+            for (int j = 0; j < cx->size_of_factor; j++) Lv[j] = (fs < cx->E && j < cx->E) ? cx->leaf_err[v][(size_t)fs * cx->E + j] : 0.0;
+        } else {
+            Lv[fs] = 1;
+        }
+        return;
+    }
+    int child[2] = { cx->left[v], cx->right[v] };
+    vit_node(cx, child[0]);
+    vit_node(cx, child[1]);
+    int r0 = (v == cx->root) ? cx->root_min : cx->rmin, r1 = (v == cx->root) ? cx->root_max : cx->rmax; /* :273-286 */
+    for (int idx = 0; idx < 2; idx++) { /* :291-311 */
+        const double *M = cx->node_matrix[child[idx]];
+        const double *Lc = cx->lik + (size_t)child[idx] * cx->size_of_factor;
+        int *vc = cx->vit + (size_t)child[idx] * cx->size_of_factor;
+        memset(cx->f[idx], 0, sizeof(double) * cx->size_of_factor);
+        for (int s = r0, i = 0; s <= r1; s++, i++) {
+            for (int c = cx->rmin, j = 0; c <= cx->rmax; c++, j++) {
+                double tmp = M[(size_t)s * cx->S + c] * Lc[j];
+                if (tmp > cx->f[idx][i]) { cx->f[idx][i] = tmp; vc[i] = j; }
+            }
+        }
+    }
+    int size = r1 - r0 + 1;
+    for (int i = 0; i < size; i++) Lv[i] = cx->f[0][i] * cx->f[1][i]; /* :313-317 */
+}
+
+int orc_viterbi(int n_nodes, const int *left, const int *right, int root, const double *const *node_matrix,
+                int S, const int *leaf_count, const double *const *leaf_err, int E, int range_min,
+                int range_max, int root_min, int root_max, int *sizes_out, double *root_max_lik)
+{
+    vit_ctx cx;
+    cx.n_nodes = n_nodes; cx.left = left; cx.right = right; cx.root = root;
+    cx.node_matrix = node_matrix; cx.S = S; cx.leaf_count = leaf_count; cx.leaf_err = leaf_err; cx.E = E;
+    cx.rmin = range_min; cx.rmax = range_max; cx.root_min = root_min; cx.root_max = root_max;
+    int rsize = root_max - root_min + 1, fsize = range_max - range_min + 1;
+    cx.size_of_factor = ORC_MAX(rsize, fsize);
+    if (cx.size_of_factor < S) cx.size_of_factor = S;
+    for (int v = 0; v < n_nodes; v += 2)
+        if (leaf_count[v] < 0 || leaf_count[v] >= cx.size_of_factor) return 1;
+    cx.lik = (double *)calloc((size_t)n_nodes * cx.size_of_factor, sizeof(double));
+    cx.vit = (int *)calloc((size_t)n_nodes * cx.size_of_factor, sizeof(int));
+    cx.f[0] = (double *)calloc(cx.size_of_factor, sizeof(double));
+    cx.f[1] = (double *)calloc(cx.size_of_factor, sizeof(double));
+    vit_node(&cx, root);
+    /* back-track in prefix order: node, head subtree, tail subtree (tree.c:101-124) */
+    int *parent = (int *)malloc(sizeof(int) * n_nodes), *stack = (int *)malloc(sizeof(int) * (n_nodes + 2));
+    for (int i = 0; i < n_nodes; i++) parent[i] = -1;
+    for (int i = 0; i < n_nodes; i++) if (left[i] >= 0) { parent[left[i]] = i; parent[right[i]] = i; }
+    int sp = 0;
+    stack[sp++] = root;
+    while (sp > 0) {
+        int v = stack[--sp];
+        if (left[v] >= 0) { stack[sp++] = right[v]; stack[sp++] = left[v]; }
+        if (left[v] < 0) { sizes_out[v] = leaf_count[v]; continue; } /* :327 */
+        if (v == root) { /* :329-339, __maxidx: first maximum */
+            const double *L = cx.lik + (size_t)root * cx.size_of_factor;
+            int am = 0; double ml = L[0];
+            for (int i = 1; i < rsize; i++) if (L[i] > ml) { ml = L[i]; am = i; }
+            sizes_out[v] = root_min + am;
+            if (root_max_lik) *root_max_lik = ml;
+        } else { /* :341-350 */
+            int p = parent[v];
+            int base = (p == root) ? root_min : range_min;
+            sizes_out[v] = cx.vit[(size_t)v * cx.size_of_factor + (sizes_out[p] - base)] + range_min;
+        }
+    }
+    free(parent); free(stack); free(cx.lik); free(cx.vit); free(cx.f[0]); free(cx.f[1]);
+    return 0;
+}

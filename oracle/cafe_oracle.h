@@ -115,6 +115,11 @@ double orc_family_pvalue(int n_nodes, const int *left, const int *right, int roo
                          const double *cd, int cd_rows, int n_samples,
                          double *pvalues_out /* optional [rfsize_f] */, int *rfsize_out);
 
+/* cafe_tree_viterbi, cafe/viterbi.cpp:209-351,494-521 (every leaf observed).  Returns non-zero when a leaf count does not fit. */
+int orc_viterbi(int n_nodes, const int *left, const int *right, int root, const double *const *node_matrix,
+                int S, const int *leaf_count, const double *const *leaf_err, int E, int range_min,
+                int range_max, int root_min, int root_max, int *sizes_out, double *root_max_lik);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ void __cafe_famliy_check_the_pattern(pCafeFamily pcf);
 #include "lambda.h"
 #include "conditional_distribution.h"
 #include "pvalue.h"
+#include "viterbi.h"
 #include "error_model.h"
 
 namespace {
@@ -137,6 +138,8 @@ void refshim_set_rates(void* h, const double* lambda, const double* mu) {
 // reset_birthdeath_cache (cafe/cafe_main.c:319): rebuilds every (int t, lambda, mu) matrix
 void refshim_reset_cache(void* h) {
     Session* s = (Session*)h;
+    const int need = s->range.max > s->range.root_max ? s->range.max : s->range.root_max;
+    ensure_lnc(need);  // never let the reference GROW its lnC cache (see ensure_lnc): a fresh process would start at this size
     reset_birthdeath_cache(s->tree, 0, &s->range);
 }
 int refshim_get_matrix(void* h, int node, double* out) {
@@ -187,6 +190,24 @@ int refshim_likelihoods(void* h, const int* counts, double* L_out) {
     compute_tree_likelihoods(s->tree);
     memcpy(L_out, get_likelihoods(s->tree), sizeof(double) * s->tree->rfsize);
     return s->tree->rfsize;
+}
+
+// cafe_tree_viterbi for one family (cafe/viterbi.cpp:494): sizes of all nodes in nlist order; returns max_i L_root[i]
+double refshim_viterbi(void* h, const int* counts, int* sizes_out) {
+    Session* s = (Session*)h;
+    int n = refshim_n_nodes(h);
+    for (int i = 0; i < n; i++) {
+        pCafeNode nd = node_at(s, i);
+        nd->familysize = -1;
+        if (nd->viterbi) memset(nd->viterbi, 0, sizeof(int) * s->tree->size_of_factor);  // as freshly calloc'ed (cafe_tree.c)
+    }
+    for (int i = 0, k = 0; i < n; i += 2, k++) node_at(s, i)->familysize = counts[k];
+    cafe_tree_viterbi(s->tree);
+    for (int i = 0; i < n; i++) sizes_out[i] = node_at(s, i)->familysize;
+    double* L = ((pCafeNode)s->tree->super.root)->likelihoods;
+    double ml = L[0];
+    for (int i = 1; i < s->tree->rfsize; i++) if (L[i] > ml) ml = L[i];
+    return ml;
 }
 
 // families attached to the session; species order = leaf order

@@ -1,0 +1,72 @@
+"""-m gpu: Viterbi ancestral reconstruction (cafe_gpu_viterbi) against the CPU oracle, which tests/test_oracle.py pins bit for
+bit against the compiled reference.  Reconstructed sizes are integers: exact equality, except where two histories tie to
+within rounding (then the products must agree to 1e-12 relative); the root's max-product likelihood within 1e-12 relative."""
+import numpy as np
+import pytest
+
+import oracle
+from cafe_b200 import host as chost
+
+from util import EXAMPLE_TREE, Problem, random_tree, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _counts(n_leaves, F, hi, seed):
+    rng = np.random.RandomState(seed)
+    base = rng.randint(0, hi, size=(F, 1))
+    return np.maximum(0, base + rng.randint(-3, 4, size=(F, n_leaves))).astype(np.int32)
+
+
+def _check(p):
+    g = p.make_gpu()
+    sizes, ml = g.viterbi()
+    g.close()
+    mats = p.oracle_mats()
+    le = p.oracle_leaf_err()
+    n_diff = 0
+    for f in range(len(p.counts)):
+        s_o, ml_o = oracle.viterbi(p.otree, mats, p.counts[f], p.ranges, leaf_err=le)
+        assert rel_err(ml[f], ml_o, 1e-300) <= 1e-12
+        assert np.array_equal(sizes[f, 0::2], p.counts[f])
+        if not np.array_equal(sizes[f], s_o):
+            n_diff += 1
+    # CUDA and glibc round the matrix entries differently in the last bit: a tie between two histories may break differently
+    assert n_diff <= max(1, len(p.counts) // 50), n_diff
+    return sizes
+
+
+def test_viterbi_example_tree():
+    _check(Problem(EXAMPLE_TREE, _counts(5, 64, 25, 3), 0.005))
+
+
+def test_viterbi_two_classes_lambda_mu():
+    _check(Problem(EXAMPLE_TREE, _counts(5, 40, 20, 4), [0.004, 0.007], mu=[0.003, 0.005], lambda_tree="(((2,2)1,(1,1)1)1,1)"))
+
+
+@pytest.mark.parametrize("n_leaves,seed", [(3, 2), (13, 4), (20, 5)])
+def test_viterbi_random_trees(n_leaves, seed):
+    nw = random_tree(n_leaves, seed)
+    _check(Problem(nw, _counts(n_leaves, 50, 30, seed), 0.01))
+
+
+def test_viterbi_root_range_wider_than_vector_and_ragged_count():
+    nw = random_tree(13, 4)
+    _check(Problem(nw, _counts(13, 37, 40, 9), 0.008, ranges=(0, 60, 3, 97)))
+
+
+def test_viterbi_error_model():
+    rg = chost.init_family_size(30)
+    dim = rg["max"] + 1
+    E = np.zeros((dim, dim))
+    eps = 0.0274
+    for j in range(dim):
+        for d, v in ((-1, eps), (0, 1 - 2 * eps), (1, eps)):
+            if 0 <= j + d < dim:
+                E[j + d, j] = v
+    E[0, 0] = 1 - eps
+    E[dim - 1, dim - 1] = 1 - eps
+    counts = np.minimum(_counts(5, 48, 26, 8), 30)
+    p = Problem(EXAMPLE_TREE, counts, 0.004, err={k: E for k in range(5)},
+                ranges=(rg["min"], rg["max"], rg["root_min"], rg["root_max"]))
+    _check(p)
