@@ -1,4 +1,4 @@
-"""Time K4 (conditional distribution) and K5 (family p-values) at a BASELINE configs[4]-like shape on one GPU.
+"""Time K4 (conditional distribution), K5 (family p-values) and the Viterbi reconstruction at a BASELINE configs[4]-like shape on one GPU.
    python tools/time_cd_pvalue.py [n_taxa] [max_size] [n_samples] [n_families]"""
 import sys, time, json
 import numpy as np
@@ -30,7 +30,10 @@ cd = g.conditional_distribution(n_samples, seed=7)
 t1 = time.perf_counter()
 pv = g.pvalues(cd)
 t2 = time.perf_counter()
-print(json.dumps({"n_taxa": n_taxa, "max_size": max_size, "R": R, "n_samples": n_samples, "families": int(len(uniq)),
+t3 = time.perf_counter()
+sizes, ml = g.viterbi()
+t4 = time.perf_counter()
+print(json.dumps({"viterbi_seconds": t4 - t3, "viterbi_families_per_s": len(uniq) / (t4 - t3), "n_taxa": n_taxa, "max_size": max_size, "R": R, "n_samples": n_samples, "families": int(len(uniq)),
                   "cd_seconds": t1 - t0, "simulated_prunings_per_s": R * n_samples / (t1 - t0),
                   "pvalue_seconds": t2 - t1, "family_pvalues_per_s": len(uniq) / (t2 - t1),
                   "pvalue_mean": float(np.mean(pv)), "launches": g.launch_count()}))
