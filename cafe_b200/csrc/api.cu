@@ -502,7 +502,14 @@ int cafe_gpu_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_lik
     if (!ctx || !node_sizes_out) return CAFE_GPU_ERR_ARG;
     int rc = check_ready(ctx, "viterbi");
     if (rc) return rc;
-    return run_viterbi(ctx, node_sizes_out, max_likelihood_out);
+    return run_viterbi(ctx, node_sizes_out, max_likelihood_out, false, nullptr);
+}
+
+int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* branch_pvalues_out) {
+    if (!ctx || !node_sizes_out) return CAFE_GPU_ERR_ARG;
+    int rc = check_ready(ctx, "viterbi_report");
+    if (rc) return rc;
+    return run_viterbi(ctx, node_sizes_out, nullptr, true, branch_pvalues_out);
 }
 
 int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {

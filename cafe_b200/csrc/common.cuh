@@ -169,7 +169,7 @@ void fused2_release(cafe_gpu_ctx* ctx);
 int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed,
                                  double* cd_out);                       // conddist.cu    (K4)
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out);  // pvalue.cu (K5)
-int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out);                      // viterbi.cu
+int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool forced, double* branch_pv_out);  // viterbi.cu
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

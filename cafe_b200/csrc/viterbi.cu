@@ -31,14 +31,20 @@ struct VitChild {
 
 // one internal node: both children, FB families x VT_THREADS output sizes per block
 __global__ void __launch_bounds__(VT_THREADS)
-k_viterbi_node(VitChild A, VitChild B, int Sp, int Vp, int W, int r0, int nrows, int n_fam, double* __restrict__ Lout) {
+k_viterbi_node(VitChild A, VitChild B, int Sp, int Vp, int W, int r0, int nrows, int n_fam, double* __restrict__ Lout,
+               const int* __restrict__ colmax, const int* __restrict__ rfsize, int is_root) {
     extern __shared__ double sL[];  // [VT_FB][W] child vector of the families of this block
     const int i = blockIdx.x * VT_THREADS + threadIdx.x;  // output size index
     const int f0 = blockIdx.y * VT_FB;
     const int nf = min(VT_FB, n_fam - f0);
     double prod[VT_FB];
+    int cm[VT_FB], nr[VT_FB];  // per family: last column of the window, number of output rows (forced ranges of the report)
 #pragma unroll
-    for (int u = 0; u < VT_FB; ++u) prod[u] = 1.0;
+    for (int u = 0; u < VT_FB; ++u) {
+        prod[u] = 1.0;
+        cm[u] = (colmax && u < nf) ? colmax[f0 + u] : W - 1;
+        nr[u] = !colmax ? nrows : (u < nf ? (is_root ? rfsize[f0 + u] : cm[u] + 1) : 0);
+    }
 
     for (int side = 0; side < 2; ++side) {
         const VitChild& C = side ? B : A;
@@ -51,13 +57,13 @@ k_viterbi_node(VitChild A, VitChild B, int Sp, int Vp, int W, int r0, int nrows,
                     const int cnt = C.counts[f0 + u];
                     if (C.err_rowptr == nullptr) {
                         // one-hot leaf (:262-266): the only non-zero product is M[s][count]
-                        const double v = (cnt < W) ? C.MT[(size_t)cnt * Sp + r0 + i] : 0.0;
+                        const double v = (cnt <= cm[u]) ? C.MT[(size_t)cnt * Sp + r0 + i] : 0.0;
                         if (v > 0.0) { best[u] = v; arg[u] = cnt; }
                     } else {
                         // error-model leaf (:252-260): L[j] = errormatrix[count][j], ascending j
                         for (int k = C.err_rowptr[cnt]; k < C.err_rowptr[cnt + 1]; ++k) {
                             const int j = C.err_col[k];
-                            if (j < W) {
+                            if (j <= cm[u]) {
                                 const double v = __dmul_rn(C.MT[(size_t)j * Sp + r0 + i], C.err_val[k]);
                                 if (v > best[u]) { best[u] = v; arg[u] = j; }
                             }
@@ -79,20 +85,24 @@ k_viterbi_node(VitChild A, VitChild B, int Sp, int Vp, int W, int r0, int nrows,
 #pragma unroll
                     for (int u = 0; u < VT_FB; ++u) {
                         const double v = __dmul_rn(m, sL[u * W + j]);
-                        if (v > best[u]) { best[u] = v; arg[u] = j; }
+                        if (v > best[u] && j <= cm[u]) { best[u] = v; arg[u] = j; }
                     }
                 }
             }
         }
         if (i < nrows) {
-            for (int u = 0; u < nf; ++u) {
-                C.vit[(size_t)(f0 + u) * Vp + i] = (short)arg[u];
+#pragma unroll
+            for (int u = 0; u < VT_FB; ++u) {
+                if (u < nf && i < nr[u]) C.vit[(size_t)(f0 + u) * Vp + i] = (short)arg[u];
                 prod[u] = __dmul_rn(prod[u], best[u]);
             }
         }
     }
-    if (i < Vp)
-        for (int u = 0; u < nf; ++u) Lout[(size_t)(f0 + u) * Vp + i] = (i < nrows) ? prod[u] : 0.0;
+    if (i < Vp) {
+#pragma unroll
+        for (int u = 0; u < VT_FB; ++u)
+            if (u < nf) Lout[(size_t)(f0 + u) * Vp + i] = (i < nr[u]) ? prod[u] : 0.0;
+    }
 }
 
 // back-track: one thread per family, prefix order (parent before child)
@@ -100,16 +110,18 @@ __global__ void __launch_bounds__(128)
 k_viterbi_backtrack(const int* __restrict__ prefix, int n_prefix, const int* __restrict__ parent, const int* __restrict__ is_leaf,
                     const int* __restrict__ leaf_ord, int root, const double* __restrict__ Lroot, const short* __restrict__ vit,
                     size_t node_stride, int Vp, int R, int root_min, int range_min, const int* __restrict__ counts, int F_pad,
-                    int fam0, int n_fam, int n_nodes, int* __restrict__ sizes_out, double* __restrict__ maxlik_out) {
+                    int fam0, int n_fam, int n_nodes, int* __restrict__ sizes_out, double* __restrict__ maxlik_out,
+                    const int* __restrict__ rfsize) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_fam) return;
+    if (rfsize) R = rfsize[f];
     int* sz = sizes_out + (size_t)(fam0 + f) * n_nodes;
     for (int p = 0; p < n_prefix; ++p) {
         const int v = prefix[p];
         if (is_leaf[v]) { sz[v] = counts[(size_t)leaf_ord[v] * F_pad + fam0 + f]; continue; }
         if (v == root) {
             const double* L = Lroot + (size_t)f * Vp;
-            double ml = L[0]; int am = 0;
+            double ml = (R > 0) ? L[0] : 0.0; int am = 0;
             for (int i = 1; i < R; ++i) if (L[i] > ml) { ml = L[i]; am = i; }  // __maxidx: first maximum
             sz[v] = root_min + am;
             if (maxlik_out) maxlik_out[fam0 + f] = ml;
@@ -121,10 +133,51 @@ k_viterbi_backtrack(const int* __restrict__ prefix, int n_prefix, const int* __r
     }
 }
 
+// viterbi_sum_probabilities (cafe/viterbi.cpp:42-70): one warp per (family, non-root node): the row of the branch's matrix at the
+// parent's reconstructed size; entries equal to the realised transition count half, smaller ones fully.
+__global__ void __launch_bounds__(256)
+k_viterbi_branch_pvalues(const double* __restrict__ M, const int* __restrict__ node_key, const int* __restrict__ parent, int Sp,
+                         int n_nodes, int n_fam_total, const int* __restrict__ sizes, const int* __restrict__ colmax, int W,
+                         double* __restrict__ out) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (long long)n_fam_total * n_nodes) return;
+    const int f = (int)(w / n_nodes), c = (int)(w - (long long)f * n_nodes);
+    const int par = parent[c];
+    if (par < 0) { if (lane == 0) out[w] = -1.0; return; }
+    const int* sz = sizes + (size_t)f * n_nodes;
+    const double* __restrict__ row = M + (size_t)node_key[c] * Sp * Sp + (size_t)sz[par] * Sp;
+    const double p = row[sz[c]];
+    const int cmax = colmax ? colmax[f] : W - 1;
+    double acc = 0.0;
+    for (int m = lane; m <= cmax; m += 32) {
+        const double x = row[m];
+        if (x == p) acc += x / 2.0; else if (x < p) acc += x;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[w] = acc;
+}
+
 }  // namespace
 
-int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out) {
+// forced: per-family ranges as viterbi_section uses them (cafe_family_set_size_with_family_forced, cafe/cafe_family.c:236-255):
+// root 1..rint(1.25*max_f), columns 0..max_f + max(50, max_f/5).  branch_pv_out (nullable): [F][n_nodes], see k_viterbi_branch_pvalues.
+int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool forced, double* branch_pv_out) {
     const int n = ctx->n_nodes, F = ctx->F, Vp = ctx->Vp, W = ctx->W, Sp = ctx->Sp;
+    std::vector<int> h_colmax, h_rf;
+    if (forced) {
+        const int nl = ctx->n_leaves;
+        h_colmax.assign(ctx->F_pad, 0); h_rf.assign(ctx->F_pad, 0);
+        for (int f = 0; f < F; ++f) {
+            int mx = 0;
+            for (int k = 0; k < nl; ++k) mx = std::max(mx, ctx->h_counts[(size_t)f * nl + k]);
+            h_colmax[f] = std::min(mx + std::max(50, mx / 5), W - 1);
+            h_rf[f] = (int)std::rint(mx * 1.25);
+            if (h_rf[f] > Vp || 1 + h_rf[f] > ctx->S)
+                CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "viterbi: a family's root range rint(1.25*max) exceeds the matrices (set_ranges from the table's max first)");
+        }
+    }
     if (W > 32767) CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "viterbi: vector longer than the 16-bit back-pointers");
     const size_t mat = (size_t)Sp * Sp;
     // families per chunk: vectors (8 B) of the internal nodes + back-pointers (2 B) of all nodes, <= ~1.5 GB
@@ -149,9 +202,11 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out) {
         }
     }
     int *d_prefix = nullptr, *d_parent = nullptr, *d_is_leaf = nullptr, *d_leaf_ord = nullptr, *d_sizes = nullptr;
-    double *d_L = nullptr, *d_ml = nullptr;
+    int *d_colmax = nullptr, *d_rf = nullptr, *d_node_key = nullptr;
+    double *d_L = nullptr, *d_ml = nullptr, *d_bpv = nullptr;
     short* d_vit = nullptr;
-    auto cleanup = [&]() { cudaFree(d_prefix); cudaFree(d_parent); cudaFree(d_is_leaf); cudaFree(d_leaf_ord); cudaFree(d_sizes); cudaFree(d_L); cudaFree(d_ml); cudaFree(d_vit); };
+    auto cleanup = [&]() { cudaFree(d_prefix); cudaFree(d_parent); cudaFree(d_is_leaf); cudaFree(d_leaf_ord); cudaFree(d_sizes); cudaFree(d_L); cudaFree(d_ml); cudaFree(d_vit);
+                           cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_node_key); cudaFree(d_bpv); };
 #define VT_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return CAFE_GPU_ERR_CUDA; } } while (0)
     VT_CK(cudaMalloc(&d_prefix, n * sizeof(int)));
     VT_CK(cudaMalloc(&d_parent, n * sizeof(int)));
@@ -161,6 +216,12 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out) {
     VT_CK(cudaMalloc(&d_ml, (size_t)F * sizeof(double)));
     VT_CK(cudaMalloc(&d_L, (size_t)n_internal * FC * Vp * sizeof(double)));
     VT_CK(cudaMalloc(&d_vit, (size_t)n * FC * Vp * sizeof(short)));
+    if (forced) {
+        VT_CK(cudaMalloc(&d_colmax, ctx->F_pad * sizeof(int)));
+        VT_CK(cudaMalloc(&d_rf, ctx->F_pad * sizeof(int)));
+        VT_CK(cudaMemcpyAsync(d_colmax, h_colmax.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        VT_CK(cudaMemcpyAsync(d_rf, h_rf.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
     VT_CK(cudaMemcpyAsync(d_prefix, prefix.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     VT_CK(cudaMemcpyAsync(d_parent, parent.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     VT_CK(cudaMemcpyAsync(d_is_leaf, is_leaf.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -185,8 +246,8 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out) {
         const int nf = std::min(FC, F - fam0);
         for (int v : post) {
             const bool is_root = (v == ctx->root);
-            const int r0 = is_root ? ctx->root_min : ctx->rmin;
-            const int nrows = is_root ? ctx->R : W;
+            const int r0 = is_root ? (forced ? 1 : ctx->root_min) : ctx->rmin;
+            const int nrows = is_root ? (forced ? std::min(Vp, ctx->S - 1) : ctx->R) : W;
             VitChild ch[2];
             const int kids[2] = {ctx->left[v], ctx->right[v]};
             for (int s = 0; s < 2; ++s) {
@@ -207,14 +268,26 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out) {
             }
             dim3 grid((Vp + VT_THREADS - 1) / VT_THREADS, (nf + VT_FB - 1) / VT_FB);
             k_viterbi_node<<<grid, VT_THREADS, smem, ctx->stream>>>(ch[0], ch[1], Sp, Vp, W, r0, nrows, nf,
-                                                                    d_L + (size_t)slot_of[v] * node_stride);
+                                                                    d_L + (size_t)slot_of[v] * node_stride,
+                                                                    forced ? d_colmax + fam0 : nullptr, forced ? d_rf + fam0 : nullptr, is_root ? 1 : 0);
             ctx->launches++;
         }
         k_viterbi_backtrack<<<(nf + 127) / 128, 128, 0, ctx->stream>>>(
             d_prefix, n, d_parent, d_is_leaf, d_leaf_ord, ctx->root, d_L + (size_t)slot_of[ctx->root] * node_stride, d_vit, node_stride, Vp,
-            ctx->R, ctx->root_min, ctx->rmin, ctx->d_counts, ctx->F_pad, fam0, nf, n, d_sizes, d_ml);
+            ctx->R, forced ? 1 : ctx->root_min, ctx->rmin, ctx->d_counts, ctx->F_pad, fam0, nf, n, d_sizes, d_ml, forced ? d_rf + fam0 : nullptr);
         ctx->launches++;
         VT_CK(cudaGetLastError());
+    }
+    if (branch_pv_out) {
+        VT_CK(cudaMalloc(&d_node_key, n * sizeof(int)));
+        VT_CK(cudaMalloc(&d_bpv, (size_t)F * n * sizeof(double)));
+        VT_CK(cudaMemcpyAsync(d_node_key, ctx->node_key.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        const long long warps = (long long)F * n;
+        k_viterbi_branch_pvalues<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_M, d_node_key, d_parent, Sp, n, F, d_sizes, forced ? d_colmax : nullptr, W, d_bpv);
+        ctx->launches++;
+        VT_CK(cudaGetLastError());
+        VT_CK(cudaMemcpyAsync(branch_pv_out, d_bpv, (size_t)F * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (sizes_out) VT_CK(cudaMemcpyAsync(sizes_out, d_sizes, (size_t)F * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (maxlik_out) VT_CK(cudaMemcpyAsync(maxlik_out, d_ml, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

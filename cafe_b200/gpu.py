@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "cafe_gpu_conditional_distribution", "cafe_gpu_pvalues", "cafe_gpu_launch_count",
     "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_timing_collect", "cafe_gpu_score_flops",
     "cafe_gpu_score_device", "cafe_gpu_set_key_shard", "cafe_gpu_matrix_storage", "cafe_gpu_matrices_exchanged",
-    "cafe_gpu_viterbi",
+    "cafe_gpu_viterbi", "cafe_gpu_viterbi_report",
 ]
 
 
@@ -66,6 +66,7 @@ def load_library():
     L.cafe_gpu_matrix_storage.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     L.cafe_gpu_matrices_exchanged.argtypes = [vp]
     L.cafe_gpu_viterbi.argtypes = [vp, _ip, _dp]
+    L.cafe_gpu_viterbi_report.argtypes = [vp, _ip, _dp]
     L.cafe_gpu_family_results.argtypes = [vp, _dp, _dp, _ip]
     L.cafe_gpu_family_likelihoods.argtypes = [vp, _dp]
     L.cafe_gpu_conditional_distribution.argtypes = [vp, C.c_int, _dp, C.c_uint64, _dp]
@@ -228,6 +229,13 @@ class CafeGpu:
         ml = np.zeros(self.F)
         self._ck(self.L.cafe_gpu_viterbi(self.h, _i(sizes), _d(ml)), "viterbi")
         return sizes, ml
+
+    def viterbi_report(self):
+        """(sizes[F][n_nodes], branch p-values[F][n_nodes]) with every family's forced range, as viterbi_section does."""
+        sizes = np.zeros((self.F, self.n_nodes), dtype=np.int32)
+        pv = np.zeros((self.F, self.n_nodes))
+        self._ck(self.L.cafe_gpu_viterbi_report(self.h, _i(sizes), _d(pv)), "viterbi_report")
+        return sizes, pv
 
     def family_likelihoods(self):
         out = np.zeros((self.F, self.R))

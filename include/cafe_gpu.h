@@ -153,6 +153,14 @@ int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out);
  * node v (nlist order; leaves keep their observed size), max_likelihood_out[f] (nullable) = max_i of the root's max-product
  * vector.  Every leaf must carry an observed size (missing data, familysize < 0, is not supported). */
 int cafe_gpu_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_likelihood_out);
+/* The same as the `report` command runs it (viterbi_section, cafe/viterbi.cpp:88-119): every family with its own forced range
+ * (cafe_family_set_size_with_family_forced, cafe/cafe_family.c:236-255: root 1..rint(1.25*max_f), sizes 0..max_f+max(50,max_f/5)),
+ * then viterbi_sum_probabilities (:42-70): branch_pvalues_out[f * n_nodes + c] (nullable) for the branch above node c =
+ * sum over sizes m of the branch's transition row at the parent's reconstructed size, entries equal to the realised
+ * transition probability counted half and smaller ones fully; -1 at the root.  (The reference stores the same numbers under
+ * node id 2*j+k for child k of internal node 2j+1, and overwrites them with -1 when the family's max p-value exceeds the
+ * cut-off - that filter is the caller's.) */
+int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* branch_pvalues_out);
 
 /* K4: conditional distribution (cafe/conditional_distribution.cpp:10-120): for every root size
  * s = root_min..root_max, n_samples simulated families (cafe/cafe_tree.c:533-569), each pruned with

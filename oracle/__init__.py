@@ -62,6 +62,7 @@ def lib():
     L.orc_prune.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _ip, _dpp, C.c_int,
                             C.c_int, C.c_int, C.c_int, C.c_int, _dp]
     L.orc_posterior.argtypes = [_dp, _dp, C.c_int, _dp, _dp, _ip]
+    L.orc_viterbi_branch_pvalues.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _ip, C.c_int, _dp]
     L.orc_viterbi.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _ip, _dpp, C.c_int,
                               C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp]
     L.orc_score.restype = C.c_double
@@ -117,6 +118,7 @@ def ref():
     R.refshim_set_errormodel.argtypes = [C.c_void_p, C.c_int, _dp, C.c_int, C.c_int, C.c_int]
     R.refshim_read_errormodel.restype = C.c_int
     R.refshim_read_errormodel.argtypes = [C.c_char_p, C.c_int, _dp, _ip, _ip]
+    R.refshim_viterbi_forced.argtypes = [C.c_void_p, C.c_int, _ip, _dp]
     R.refshim_viterbi.restype = C.c_double
     R.refshim_viterbi.argtypes = [C.c_void_p, _ip, _ip]
     R.refshim_likelihoods.restype = C.c_int
@@ -309,6 +311,21 @@ def viterbi(tree: FlatTree, mats, counts_by_leaf, rng, leaf_err=None):
     if rc != 0:
         raise ValueError("leaf count outside the likelihood vector")
     return sizes, ml.value
+
+
+def forced_range(counts_by_leaf):
+    """cafe_family_set_size_with_family_forced (cafe/cafe_family.c:236-255): (min, max, root_min, root_max) of one family."""
+    mx = int(max(counts_by_leaf))
+    return (0, mx + max(50, mx // 5), 1, int(np.rint(mx * 1.25)))
+
+
+def viterbi_branch_pvalues(tree: FlatTree, mats, sizes, range_max):
+    S = next(m for m in mats if m is not None).shape[0]
+    mp, keep = _matrix_ptrs(mats)
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    out = np.zeros(tree.n_nodes)
+    lib().orc_viterbi_branch_pvalues(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S, _iptr(sizes), range_max, _dptr(out))
+    return out
 
 
 def score(tree: FlatTree, mats, counts, rng, prior, ref_idx=None, leaf_err=None, want_L=False):

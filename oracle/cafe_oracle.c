@@ -465,3 +465,28 @@ int orc_viterbi(int n_nodes, const int *left, const int *right, int root, const 
     free(parent); free(stack); free(cx.lik); free(cx.vit); free(cx.f[0]); free(cx.f[1]);
     return 0;
 }
+
+/* viterbi_sum_probabilities (cafe/viterbi.cpp:42-70): for the branch above every non-root node c with parent size ps and
+ * child size cs (both from the Viterbi reconstruction), p = M_c[ps][cs] and the branch p-value is
+ * sum_{m=0..range_max} ( M_c[ps][m] == p ? M_c[ps][m] / 2 : M_c[ps][m] < p ? M_c[ps][m] : 0 ).  out[c], -1 at the root. */
+void orc_viterbi_branch_pvalues(int n_nodes, const int *left, const int *right, int root, const double *const *node_matrix,
+                                int S, const int *sizes, int range_max, double *out)
+{
+    for (int v = 0; v < n_nodes; v++) out[v] = -1;
+    for (int v = 0; v < n_nodes; v++) {
+        if (left[v] < 0) continue;
+        int child[2] = { left[v], right[v] };
+        for (int k = 0; k < 2; k++) {
+            const double *M = node_matrix[child[k]];
+            double p = M[(size_t)sizes[v] * S + sizes[child[k]]];
+            double acc = 0;
+            for (int m = 0; m <= range_max; m++) {
+                double x = M[(size_t)sizes[v] * S + m];
+                if (x == p) acc += x / 2.0;
+                else if (x < p) acc += x;
+            }
+            out[child[k]] = acc;
+        }
+    }
+    (void)root;
+}

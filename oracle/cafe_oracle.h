@@ -120,6 +120,10 @@ int orc_viterbi(int n_nodes, const int *left, const int *right, int root, const 
                 int S, const int *leaf_count, const double *const *leaf_err, int E, int range_min,
                 int range_max, int root_min, int root_max, int *sizes_out, double *root_max_lik);
 
+/* viterbi_sum_probabilities, cafe/viterbi.cpp:42-70; out[c] for the branch above node c, -1 at the root */
+void orc_viterbi_branch_pvalues(int n_nodes, const int *left, const int *right, int root, const double *const *node_matrix,
+                                int S, const int *sizes, int range_max, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -306,6 +306,34 @@ double refshim_family_pvalue(void* h, int idx, const double* cd, int cd_rows, in
     return best;
 }
 
+// Viterbi as viterbi_section does it for family `idx` (viterbi.cpp:88-119): forced per-family range, cafe_tree_viterbi,
+// viterbi_sum_probabilities.  sizes_out[n_nodes]; branch_pv_out[n_nodes] indexed by the CHILD node of each branch (root: -1).
+void refshim_viterbi_forced(void* h, int idx, int* sizes_out, double* branch_pv_out) {
+    Session* s = (Session*)h;
+    int n = refshim_n_nodes(h);
+    for (int i = 0; i < n; i++) {
+        pCafeNode nd = node_at(s, i);
+        if (nd->viterbi) memset(nd->viterbi, 0, sizeof(int) * s->tree->size_of_factor);
+    }
+    cafe_family_set_size_with_family_forced(s->family, idx, s->tree);
+    cafe_tree_viterbi(s->tree);
+    for (int i = 0; i < n; i++) { sizes_out[i] = node_at(s, i)->familysize; branch_pv_out[i] = -1; }
+    viterbi_parameters vp;
+    pCafeFamilyItem pitem = (pCafeFamilyItem)s->family->flist->array[idx];
+    viterbi_sum_probabilities(&vp, s->tree, pitem);
+    int nnodes = (n - 1) / 2;
+    for (int j = 0; j < nnodes; j++) {
+        pTreeNode pn = (pTreeNode)s->tree->super.nlist->array[2 * j + 1];
+        pTreeNode child[2] = {(pTreeNode)pn->children->head->data, (pTreeNode)pn->children->tail->data};
+        for (int k = 0; k < 2; k++) {
+            int ci = -1;
+            for (int i = 0; i < n; i++) if ((pTreeNode)s->tree->super.nlist->array[i] == child[k]) ci = i;
+            branch_pv_out[ci] = vp.viterbiPvalues[viterbi_parameters::NodeFamilyKey(2 * j + k, pitem)];
+        }
+    }
+    copy_range_to_tree(s->tree, &s->range);
+}
+
 // reference family-table reader + dedup (gene_family.cpp:186-225, cafe_family.c:9-34)
 int refshim_load_families(const char* path, int max_size, int* n_species, int* F_out, int* counts_out, int cap, int* ref_out, int* max_size_out) {
     std::ifstream ifs(path);

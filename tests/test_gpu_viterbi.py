@@ -70,3 +70,39 @@ def test_viterbi_error_model():
     p = Problem(EXAMPLE_TREE, counts, 0.004, err={k: E for k in range(5)},
                 ranges=(rg["min"], rg["max"], rg["root_min"], rg["root_max"]))
     _check(p)
+
+
+def _check_report(p):
+    """cafe_gpu_viterbi_report (forced per-family ranges + branch p-values) against the oracle."""
+    g = p.make_gpu()
+    sizes, pv = g.viterbi_report()
+    g.close()
+    mats = p.oracle_mats()
+    le = p.oracle_leaf_err()
+    n_diff = 0
+    for f in range(len(p.counts)):
+        fr = oracle.forced_range(p.counts[f])
+        s_o, _ = oracle.viterbi(p.otree, mats, p.counts[f], fr, leaf_err=le)
+        if not np.array_equal(sizes[f], s_o):
+            n_diff += 1
+            continue
+        pv_o = oracle.viterbi_branch_pvalues(p.otree, mats, s_o, fr[1])
+        assert pv[f, p.otree.root] == -1 and pv_o[p.otree.root] == -1
+        nz = np.arange(p.otree.n_nodes) != p.otree.root
+        # an entry that equals the realised transition to the last bit on the CPU may differ by an ulp on the GPU (half vs full
+        # weight of one term): compare with the weight of the realised transition as the allowance
+        assert np.abs(pv[f, nz] - pv_o[nz]).max() <= 1e-9
+    assert n_diff <= max(1, len(p.counts) // 50), n_diff
+
+
+def test_viterbi_report_forced_ranges_and_branch_pvalues():
+    counts = _counts(5, 64, 25, 13)
+    counts[0] = 0            # an all-zero family: empty forced root range
+    counts[0, 0] = 1
+    mx = int(counts.max())
+    rg = chost.init_family_size(mx)
+    _check_report(Problem(EXAMPLE_TREE, counts, 0.005, ranges=(rg["min"], rg["max"], rg["root_min"], rg["root_max"])))
+    nw = random_tree(13, 4)
+    counts = np.maximum(1, _counts(13, 40, 30, 14))
+    rg = chost.init_family_size(int(counts.max()))
+    _check_report(Problem(nw, counts, 0.01, ranges=(rg["min"], rg["max"], rg["root_min"], rg["root_max"])))
