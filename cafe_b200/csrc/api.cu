@@ -534,7 +534,16 @@ int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {
 int cafe_gpu_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, double* cd_out) {
     if (!ctx || !cd_out || n_samples < 1) return CAFE_GPU_ERR_ARG;
     if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "conditional_distribution: build_matrices first");
-    return run_conditional_distribution(ctx, n_samples, uniforms, seed, cd_out);
+    return run_conditional_distribution(ctx, n_samples, uniforms, seed, 0, ctx->R, cd_out);
+}
+
+int cafe_gpu_conditional_distribution_rows(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
+                                           double* cd_out) {
+    if (!ctx || !cd_out || n_samples < 1) return CAFE_GPU_ERR_ARG;
+    if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "conditional_distribution_rows: build_matrices first");
+    if (row_lo < 0 || row_hi > ctx->R || row_lo > row_hi) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "conditional_distribution_rows: need 0 <= row_lo <= row_hi <= root_max-root_min+1");
+    if (row_lo == row_hi) return CAFE_GPU_OK;
+    return run_conditional_distribution(ctx, n_samples, uniforms, seed, row_lo, row_hi, cd_out);
 }
 
 int cafe_gpu_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* max_pvalue_out) {

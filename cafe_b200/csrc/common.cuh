@@ -166,7 +166,7 @@ void fused_release(cafe_gpu_ctx* ctx);
 bool fused2_supported(const cafe_gpu_ctx* ctx);                         // prune_fused2.cu
 int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out);        // prune_fused2.cu (K2, one CTA per SM, default)
 void fused2_release(cafe_gpu_ctx* ctx);
-int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed,
+int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
                                  double* cd_out);                       // conddist.cu    (K4)
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out);  // pvalue.cu (K5)
 int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool forced, double* branch_pv_out);  // viterbi.cu

@@ -134,7 +134,10 @@ k_root_single_row(RootChild c0, RootChild c1, const double* __restrict__ M, cons
 
 }  // namespace
 
-int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, double* cd_out) {
+// rows [row_lo, row_hi) of the distribution (root sizes root_min + row): cd_out is [(row_hi - row_lo)][n_samples]; the replay
+// stream `uniforms` always starts at row 0.  Rows are independent (the device RNG is keyed by (seed, root size, trial, node)), so
+// ranks can split them (sharding.conditional_distribution_sharded).
+int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi, double* cd_out) {
     const int R = ctx->R, n = ctx->n_nodes, n_nonroot = n - 1, D = (int)ctx->keys.size();
     const size_t mat_bytes = (size_t)D * ctx->Sp * ctx->Sp * sizeof(double);
     double* d_cdf = nullptr;
@@ -201,8 +204,8 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
     if (rc) { cleanup(); return rc; }
     const size_t slot_stride = (size_t)Fc_pad * ctx->Vp;
 
-    for (int r_lo = 0; r_lo < R; r_lo += rows_per_chunk) {
-        const int rows = std::min(rows_per_chunk, R - r_lo), Fc = rows * n_samples, s_lo = ctx->root_min + r_lo;
+    for (int r_lo = row_lo; r_lo < row_hi; r_lo += rows_per_chunk) {
+        const int rows = std::min(rows_per_chunk, row_hi - r_lo), Fc = rows * n_samples, s_lo = ctx->root_min + r_lo;
         if (uniforms)
             CD_CK(cudaMemcpyAsync(d_uniforms, uniforms + (size_t)r_lo * n_samples * n_nonroot, (size_t)Fc * n_nonroot * sizeof(double),
                                   cudaMemcpyHostToDevice, ctx->stream));
@@ -223,16 +226,16 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
     // ascending sort of every row (std::sort, conditional_distribution.cpp:41)
     {
         std::vector<int> off(R + 1);
-        for (int r = 0; r <= R; ++r) off[r] = r * n_samples;
+        for (int r = 0; r <= R; ++r) off[r] = (row_lo + std::min(r, row_hi - row_lo)) * n_samples;  // segments of the requested rows only
         CD_CK(cudaMalloc(&d_offsets, (R + 1) * sizeof(int)));
         CD_CK(cudaMemcpyAsync(d_offsets, off.data(), (R + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         size_t tmp_bytes = 0;
-        CD_CK(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_L0, d_sorted, R * n_samples, R, d_offsets, d_offsets + 1, ctx->stream));
+        CD_CK(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_L0, d_sorted, R * n_samples, row_hi - row_lo, d_offsets, d_offsets + 1, ctx->stream));
         CD_CK(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
-        CD_CK(cub::DeviceSegmentedSort::SortKeys(d_tmp, tmp_bytes, d_L0, d_sorted, R * n_samples, R, d_offsets, d_offsets + 1, ctx->stream));
+        CD_CK(cub::DeviceSegmentedSort::SortKeys(d_tmp, tmp_bytes, d_L0, d_sorted, R * n_samples, row_hi - row_lo, d_offsets, d_offsets + 1, ctx->stream));
         ctx->launches++;
     }
-    CD_CK(cudaMemcpyAsync(cd_out, d_sorted, (size_t)R * n_samples * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CD_CK(cudaMemcpyAsync(cd_out, d_sorted + (size_t)row_lo * n_samples, (size_t)(row_hi - row_lo) * n_samples * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CD_CK(cudaStreamSynchronize(ctx->stream));
     cleanup();
     ctx->results_valid = false;  // the vector slots were reused

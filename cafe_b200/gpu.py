@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "cafe_gpu_conditional_distribution", "cafe_gpu_pvalues", "cafe_gpu_launch_count",
     "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_timing_collect", "cafe_gpu_score_flops",
     "cafe_gpu_score_device", "cafe_gpu_set_key_shard", "cafe_gpu_matrix_storage", "cafe_gpu_matrices_exchanged",
-    "cafe_gpu_viterbi", "cafe_gpu_viterbi_report",
+    "cafe_gpu_viterbi", "cafe_gpu_viterbi_report", "cafe_gpu_conditional_distribution_rows",
 ]
 
 
@@ -70,6 +70,7 @@ def load_library():
     L.cafe_gpu_family_results.argtypes = [vp, _dp, _dp, _ip]
     L.cafe_gpu_family_likelihoods.argtypes = [vp, _dp]
     L.cafe_gpu_conditional_distribution.argtypes = [vp, C.c_int, _dp, C.c_uint64, _dp]
+    L.cafe_gpu_conditional_distribution_rows.argtypes = [vp, C.c_int, _dp, C.c_uint64, C.c_int, C.c_int, _dp]
     L.cafe_gpu_pvalues.argtypes = [vp, _dp, C.c_int, C.c_int, _dp]
     L.cafe_gpu_launch_count.restype = C.c_int64
     L.cafe_gpu_launch_count.argtypes = [vp]
@@ -253,6 +254,12 @@ class CafeGpu:
             up = _d(uniforms)
         self._ck(self.L.cafe_gpu_conditional_distribution(self.h, n_samples, up, C.c_uint64(seed), _d(out)),
                  "conditional_distribution")
+        return out
+
+    def conditional_distribution_rows(self, n_samples, row_lo, row_hi, seed=0):
+        out = np.zeros((row_hi - row_lo, n_samples))
+        self._ck(self.L.cafe_gpu_conditional_distribution_rows(self.h, n_samples, None, C.c_uint64(seed), row_lo, row_hi, _d(out)),
+                 "conditional_distribution_rows")
         return out
 
     def pvalues(self, cd):

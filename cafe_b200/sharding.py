@@ -79,6 +79,36 @@ def objective_sharded(g, lam_node, mu_node, out2, rank: int, world_size: int, de
     return reduce_score(out2, group)
 
 
+def gather_rows(local_rows, n_rows: int, rank: int, world_size: int, group=None):
+    """All-gather of a row-sharded matrix: rank r holds rows shard_bounds(n_rows, world, r) as a [rows_r][n] array; every rank
+    gets the full [n_rows][n] array.  Shards are padded to the largest one, so one all_gather_into_tensor suffices."""
+    import torch
+    import torch.distributed as dist
+
+    local = torch.as_tensor(np.ascontiguousarray(local_rows, dtype=np.float64))
+    n = local.shape[1]
+    if not (dist.is_available() and dist.is_initialized()) or world_size == 1:
+        return local.numpy()
+    per = (n_rows + world_size - 1) // world_size
+    use_cuda = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    mine = torch.zeros((per, n), dtype=torch.float64, device=dev)
+    mine[: local.shape[0]] = local.to(dev)
+    full = torch.empty((world_size * per, n), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    full = full.cpu().numpy().reshape(world_size, per, n)
+    return np.concatenate([full[r, : shard_bounds(n_rows, world_size, r)[1] - shard_bounds(n_rows, world_size, r)[0]] for r in range(world_size)])
+
+
+def conditional_distribution_sharded(g, n_samples: int, seed: int, rank: int, world_size: int, group=None):
+    """The conditional distribution (K4) with its R root-size rows split over the ranks — every rank simulates and prunes
+    R/world x n_samples families, one all-gather of the sorted rows (R x n_samples doubles, 4 MB at BASELINE configs[4]) gives
+    every rank the whole matrix for the p-values of its own families (cafe_gpu_pvalues).  The device RNG is keyed by
+    (seed, root size, trial, node): the result does not depend on the number of ranks."""
+    lo, hi = shard_bounds(g.R, world_size, rank)
+    return gather_rows(g.conditional_distribution_rows(n_samples, lo, hi, seed=seed), g.R, rank, world_size, group)
+
+
 def finish_score(s, z):
     """Host-side decode of reduce_score's result: (-inf, index) when some family had zero likelihood."""
     s, z = float(s), float(z)

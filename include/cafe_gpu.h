@@ -173,6 +173,12 @@ int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* 
 int cafe_gpu_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms,
                                       uint64_t seed, double* cd_out);
 
+/* Rows [row_lo, row_hi) of the same distribution (root sizes root_min + row), cd_out row-major [(row_hi-row_lo)][n_samples]:
+ * the rows are independent, so ranks can split them and all-gather the result — the distributed form of the reference's
+ * pthreads over root sizes (cafe/conditional_distribution.cpp:86-120).  `uniforms` still starts at row 0. */
+int cafe_gpu_conditional_distribution_rows(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed,
+                                           int row_lo, int row_hi, double* cd_out);
+
 /* K5: family-wide p-values (cafe/viterbi.cpp:88-97,32-39; cafe/pvalue.cpp:143-154;
  * libcommon/mathfunc.c:663-689): per family the forced range of cafe/cafe_family.c:236-255, prune,
  * p[s] = pvalue(L[s], cd[s]), result = max_s (0 when the family's root range is empty).

@@ -103,3 +103,23 @@ def test_in_place_chunk_gather_gives_every_rank_all_keys():
     out = mgr.dict()
     mp.spawn(_gather_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert out[0] == out[1] == [10.0, 11.0, 12.0, 13.0, 14.0]
+
+
+def _rows_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_rows, n = 7, 3   # 7 root sizes over 2 ranks: shards of 4 and 3 rows
+    full = np.arange(n_rows * n, dtype=np.float64).reshape(n_rows, n)
+    lo, hi = sharding.shard_bounds(n_rows, world, rank)
+    out[rank] = sharding.gather_rows(full[lo:hi], n_rows, rank, world).tolist()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_matrix_gather():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_rows_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    expect = np.arange(21, dtype=np.float64).reshape(7, 3).tolist()
+    assert out[0] == expect and out[1] == expect

@@ -119,3 +119,20 @@ def test_k4_then_score_still_correct():
     o = p.oracle_score(want_L=False)
     assert abs(s1 - o["score"]) < 1e-6
     g.close()
+
+
+def test_k4_rows_split_equals_whole_distribution():
+    # cafe_gpu_conditional_distribution_rows: the rows two ranks would compute, concatenated, are the single-rank result
+    import oracle
+    from util import EXAMPLE_TREE, Problem
+    rng = np.random.RandomState(5)
+    counts = np.maximum(0, rng.randint(1, 20, size=(16, 1)) + rng.randint(-2, 3, size=(16, 5))).astype(np.int32)
+    p = Problem(EXAMPLE_TREE, counts, 0.006)
+    g = p.make_gpu()
+    whole = g.conditional_distribution(64, seed=11)
+    R = whole.shape[0]
+    cut = R // 2 + 1
+    parts = np.concatenate([g.conditional_distribution_rows(64, 0, cut, seed=11), g.conditional_distribution_rows(64, cut, R, seed=11)])
+    assert np.array_equal(parts, whole)
+    assert g.conditional_distribution_rows(64, 3, 3, seed=11).shape == (0, 64)
+    g.close()
