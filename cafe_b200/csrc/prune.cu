@@ -178,21 +178,34 @@ k_node_gemm(const double* __restrict__ Min, int Sp, int r0, int nrows, int K,  /
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) frag_off[kk] = pg * 128 + (((2 * kk + (q >> 1)) ^ pg) << 4) + ((q & 1) << 3);
 
+    // Stage pipeline: the next K block travels global -> registers while the DMMAs of the current one run, then registers ->
+    // shared memory between two barriers (the fused kernels use TMA with the same swizzle instead).
+    constexpr int PIECES = TM * 8 / GEMM_THREADS;  // 16-byte pieces per thread and operand
+    double2 pa[PIECES], pb[PIECES];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < PIECES; ++i) {
+            const int ch = threadIdx.x + i * GEMM_THREADS, row = ch >> 3, c = ch & 7;
+            pa[i] = *reinterpret_cast<const double2*>(in + (size_t)(f0 + row) * Vp + k0 + 2 * c);
+            const int mr = r0 + n0 + row;
+            pb[i] = make_double2(0.0, 0.0);
+            if (mr < Sp) pb[i] = *reinterpret_cast<const double2*>(Min + (size_t)mr * Sp + k0 + 2 * c);
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int i = 0; i < PIECES; ++i) {
+            const int ch = threadIdx.x + i * GEMM_THREADS, row = ch >> 3, c = ch & 7;
+            *reinterpret_cast<double2*>(sA + swz(row, c)) = pa[i];
+            *reinterpret_cast<double2*>(sB + swz(row, c)) = pb[i];
+        }
+    };
+    gload(0);
+    sstore();
+    __syncthreads();
     for (int k0 = 0; k0 < K; k0 += BK) {
-        // ---- stage load (generic loads; the fused kernel uses TMA with the same swizzle) ----
-        for (int ch = threadIdx.x; ch < TM * 8; ch += GEMM_THREADS) {
-            int row = ch >> 3, c = ch & 7;
-            double2 v = *reinterpret_cast<const double2*>(in + (size_t)(f0 + row) * Vp + k0 + 2 * c);
-            *reinterpret_cast<double2*>(sA + swz(row, c)) = v;
-        }
-        for (int ch = threadIdx.x; ch < TN * 8; ch += GEMM_THREADS) {
-            int row = ch >> 3, c = ch & 7;
-            int mr = r0 + n0 + row;
-            double2 v = make_double2(0.0, 0.0);
-            if (mr < Sp) v = *reinterpret_cast<const double2*>(Min + (size_t)mr * Sp + k0 + 2 * c);
-            *reinterpret_cast<double2*>(sB + swz(row, c)) = v;
-        }
-        __syncthreads();
+        const bool more = k0 + BK < K;
+        if (more) gload(k0 + BK);
         if (warp_active) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -213,6 +226,7 @@ k_node_gemm(const double* __restrict__ Min, int Sp, int r0, int nrows, int K,  /
             }
         }
         __syncthreads();
+        if (more) { sstore(); __syncthreads(); }
     }
 
     // ---- epilogue: child product, masks, store --------------------------------------------------
