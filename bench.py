@@ -376,7 +376,7 @@ def run_ours(args, rank, local_rank, world):
             "workload": f"{FAMILIES_PER_GPU} families x {N_TAXA} taxa per GPU, max size {MAX_SIZE}, " + ("lambda and mu" if MU_RATIO > 0 else "single lambda") + f" ({WORKLOAD_NAME})",
             "families_total": families_total, "unique_patterns_rank0": int(len(uniq)), "W": ranges[1] + 1, "R": R,
             "S": max(ranges[1], ranges[3]) + 1, "keys": g.num_keys(), "parallelism": f"families sharded x{world}" + (f", matrix build sharded x{world} + 2 NCCL all-gathers" if shard_k1 else ""),
-            "l2": "no explicit flush: node-vector slots (>=4 x 102 MB) exceed the 126 MB L2 and matrices are rewritten every step",
+            "l2": "no explicit flush: the node-vector scratch of K2 (0.9 GB, 4.9 GB of DRAM traffic per launch) exceeds the 126 MB L2 and the matrices are rewritten every step",
             "last_score": last_score, "k1_ms": k1, "k2_ms": k2,
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
