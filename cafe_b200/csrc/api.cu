@@ -409,6 +409,30 @@ int cafe_gpu_get_matrix(cafe_gpu_ctx* ctx, int node, double* out, int out_dim) {
 // ------------------------------------------------------------------------------------------- K2 + K3
 }  // extern "C"
 
+// K1 for the single key `key` of ctx->keys (the other matrices stay as they are): the lengthened branch of lrt.cu
+int build_one_matrix(cafe_gpu_ctx* ctx, int key) {
+    const int D = (int)ctx->keys.size();
+    if (key < 0 || key >= D || (size_t)D > ctx->mat_cap) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "build_one_matrix: bad key");
+    if (D > ctx->keys_cap) {  // grow, keeping the parameters of the keys already built
+        BdKeyParams* grown = nullptr;
+        const int cap = std::max(D, 2 * ctx->keys_cap);
+        CAFE_CK(ctx, cudaMalloc(&grown, cap * sizeof(BdKeyParams)));
+        if (ctx->d_keyparams)
+            CAFE_CK(ctx, cudaMemcpyAsync(grown, ctx->d_keyparams, ctx->keys_cap * sizeof(BdKeyParams), cudaMemcpyDeviceToDevice, ctx->stream));
+        CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_keyparams);
+        ctx->d_keyparams = grown;
+        ctx->keys_cap = cap;
+    }
+    const BdKeyParams kp = key_params(ctx->keys[key]);
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_keyparams + key, &kp, sizeof(BdKeyParams), cudaMemcpyHostToDevice, ctx->stream));
+    const int lo = ctx->key_lo, hi = ctx->key_hi;
+    ctx->key_lo = key; ctx->key_hi = key + 1;
+    const int rc = launch_bd_matrices(ctx);
+    ctx->key_lo = lo; ctx->key_hi = hi;
+    return rc;
+}
+
 int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad) {
     size_t need = (size_t)ctx->n_slots * F_pad * ctx->Vp;
     if (need > ctx->vec_cap) {
@@ -510,6 +534,17 @@ int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* 
     int rc = check_ready(ctx, "viterbi_report");
     if (rc) return rc;
     return run_viterbi(ctx, node_sizes_out, nullptr, true, branch_pvalues_out);
+}
+
+int cafe_gpu_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, double* base_max_likelihood_out,
+                                   double* best_max_likelihood_out, int32_t* steps_out) {
+    if (!ctx || !best_max_likelihood_out) return CAFE_GPU_ERR_ARG;
+    int rc = check_ready(ctx, "likelihood_ratio_test");
+    if (rc) return rc;
+    if (ctx->shard_world > 1) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "likelihood_ratio_test: matrices must be unsharded (cafe_gpu_set_key_shard(ctx, 0, 1))");
+    rc = ensure_vec_buffers(ctx, ctx->F_pad);
+    if (rc) return rc;
+    return run_lrt_branch_stretch(ctx, tested, base_max_likelihood_out, best_max_likelihood_out, steps_out);
 }
 
 int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {

@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_timing_collect", "cafe_gpu_score_flops",
     "cafe_gpu_score_device", "cafe_gpu_set_key_shard", "cafe_gpu_matrix_storage", "cafe_gpu_matrices_exchanged",
     "cafe_gpu_viterbi", "cafe_gpu_viterbi_report", "cafe_gpu_conditional_distribution_rows",
+    "cafe_gpu_likelihood_ratio_test",
 ]
 
 
@@ -68,6 +69,7 @@ def load_library():
     L.cafe_gpu_viterbi.argtypes = [vp, _ip, _dp]
     L.cafe_gpu_viterbi_report.argtypes = [vp, _ip, _dp]
     L.cafe_gpu_family_results.argtypes = [vp, _dp, _dp, _ip]
+    L.cafe_gpu_likelihood_ratio_test.argtypes = [vp, C.POINTER(C.c_uint8), _dp, _dp, _ip]
     L.cafe_gpu_family_likelihoods.argtypes = [vp, _dp]
     L.cafe_gpu_conditional_distribution.argtypes = [vp, C.c_int, _dp, C.c_uint64, _dp]
     L.cafe_gpu_conditional_distribution_rows.argtypes = [vp, C.c_int, _dp, C.c_uint64, C.c_int, C.c_int, _dp]
@@ -237,6 +239,19 @@ class CafeGpu:
         pv = np.zeros((self.F, self.n_nodes))
         self._ck(self.L.cafe_gpu_viterbi_report(self.h, _i(sizes), _d(pv)), "viterbi_report")
         return sizes, pv
+
+    def likelihood_ratio_test(self, tested=None):
+        """(base max likelihood [F], best max likelihood [n_nodes][F], steps [n_nodes][F]) of the branch-stretch test."""
+        base = np.zeros(self.F)
+        best = np.zeros((self.n_nodes, self.F))
+        steps = np.zeros((self.n_nodes, self.F), dtype=np.int32)
+        tp = None
+        if tested is not None:
+            tested = np.ascontiguousarray(tested, dtype=np.uint8)
+            assert tested.shape == (self.F,)
+            tp = tested.ctypes.data_as(C.POINTER(C.c_uint8))
+        self._ck(self.L.cafe_gpu_likelihood_ratio_test(self.h, tp, _d(base), _d(best), _i(steps)), "likelihood_ratio_test")
+        return base, best, steps
 
     def family_likelihoods(self):
         out = np.zeros((self.F, self.R))

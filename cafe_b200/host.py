@@ -58,6 +58,10 @@ def load_library():
     H.cafe_host_family_likelihoods.argtypes = [vp, _dp, C.c_long]
     H.cafe_host_get_cond_dist.argtypes = [vp, _dp, C.c_long, _ip, _ip]
     H.cafe_host_get_max_pvalues.argtypes = [vp, _dp, C.c_int]
+    H.cafe_host_set_max_pvalues.argtypes = [vp, _dp, C.c_int]
+    H.cafe_host_chi2cdf.restype = C.c_double
+    H.cafe_host_chi2cdf.argtypes = [C.c_double, C.c_int]
+    H.cafe_host_likelihood_ratio_test.argtypes = [vp, _dp, C.c_long, _ip, _ip]
     return H
 
 
@@ -250,11 +254,29 @@ class Session:
             raise CafeHostError("no conditional distribution")
         return buf[: rows.value * cols.value].reshape(rows.value, cols.value).copy()
 
+    def set_max_pvalues(self, pv):
+        pv = np.ascontiguousarray(pv, dtype=np.float64)
+        self.H.cafe_host_set_max_pvalues(self.h, _d(pv), len(pv))
+
+    def likelihood_ratio_test(self):
+        """cafe_likelihood_ratio_test (cafe/cafe_main.c:398-431): likelihoodRatios [nodes][families]."""
+        F = self.num_families()
+        buf = np.zeros(F * 4096)
+        nodes = C.c_int()
+        fams = C.c_int()
+        if self.H.cafe_host_likelihood_ratio_test(self.h, _d(buf), buf.size, C.byref(nodes), C.byref(fams)) < 0:
+            raise CafeHostError(self.H.cafe_host_last_error().decode())
+        return buf[: nodes.value * fams.value].reshape(nodes.value, fams.value).copy()
+
     def max_pvalues(self):
         F = self.num_families()
         out = np.zeros(F)
         n = self.H.cafe_host_get_max_pvalues(self.h, _d(out), F)
         return out[:n]
+
+
+def chi2cdf(x: float, df: int = 1) -> float:
+    return load_library().cafe_host_chi2cdf(float(x), int(df))
 
 
 def srand(seed: int):

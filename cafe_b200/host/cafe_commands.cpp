@@ -341,6 +341,25 @@ int cafe_cmd_report(Globals& globals, std::vector<std::string> tokens) {
     if (!ofst) throw std::runtime_error("ERROR(report): Cannot open " + tokens[1] + ".pvalues in write mode.\n");
     ofst << "ID\tFamily-wide P-value\n";
     for (size_t i = 0; i < param->pfamily->flist.size(); ++i) ofst << param->pfamily->flist[i].id << "\t" << param->max_pvalues[i] << "\n";
+    // report_parameters, reports.cpp:604-616: `likelihood` runs the branch-stretch likelihood-ratio test (reports.cpp:684-685)
+    bool likelihood = false;
+    for (size_t i = 2; i < tokens.size(); ++i) {
+        std::string o = tokens[i];
+        for (char& c : o) c = (char)std::tolower((unsigned char)c);
+        if (o == "likelihood") likelihood = true;
+        if (o == "branchcutting" || o == "lh2") throw std::runtime_error("report: " + o + " is not built (SURVEY.md 8f)");
+    }
+    if (likelihood) {
+        cafe_likelihood_ratio_test(param, param->max_pvalues.data());
+        std::ofstream lr((tokens[1] + ".likelihood_ratios").c_str());
+        if (!lr) throw std::runtime_error("ERROR(report): Cannot open " + tokens[1] + ".likelihood_ratios in write mode.\n");
+        lr << "ID\tLikelihood Ratio per node (nlist order)\n";
+        for (size_t i = 0; i < param->pfamily->flist.size(); ++i) {
+            lr << param->pfamily->flist[i].id << "\t(";
+            for (size_t b = 0; b < param->likelihoodRatios.size(); ++b) lr << (b ? "," : "") << param->likelihoodRatios[b][i];
+            lr << ")\n";
+        }
+    }
     cafe_log(param, "Report Done\n");
     return 0;
 }

@@ -49,6 +49,19 @@ double pvalue(double v, const double* cd, int size) {
     return (lo + (cd[lo] <= v ? 1 : 0) + (hi - lo) / 2.0) / size;
 }
 
+double chi2cdf(double x, int df) {
+    const double shape = df / 2.0, scaled = x / 2;
+    double sum = 1 / shape, term = 1 / shape;
+    int i = 1;
+    for (; i < 1000; ++i) {
+        term *= scaled / (shape + i);
+        if (term < 1e-8) break;  // __EPS__, libcommon/mathfunc.h:12
+        sum += term;
+    }
+    const double log_lower = (i == 1000) ? gammaln(shape) : std::log(sum) + shape * std::log(scaled) - scaled;
+    return std::exp(log_lower - gammaln(shape));
+}
+
 std::vector<double> lnc_table(int size) {
     const int rows = 2 * size, cols = size + 1;
     std::vector<double> T((size_t)rows * cols);

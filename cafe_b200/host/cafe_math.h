@@ -18,6 +18,10 @@ double unifrnd();
 // libcommon/mathfunc.c:663-689
 double pvalue(double v, const double* conddist, int size);
 
+// chi2cdf -> gamcdf -> gammainc -> incgammaln_lower, libcommon/mathfunc.c:128-151,260-263,284-287: the series-only lower incomplete
+// gamma (at most 999 terms, first term below 1e-8 stops it; a series that never stops yields exactly 1)
+double chi2cdf(double x, int df);
+
 // Dense lnC table for the GPU matrix builder: row-major [2*size][size+1], T[n][x] = chooseln(n, x)
 // — the values libtree/chooseln_cache.h:27-41 memoises lazily.
 std::vector<double> lnc_table(int size);

@@ -539,6 +539,32 @@ void cafe_family_pvalues(pCafeParam param, std::vector<double>& max_pvalues) {
     for (size_t i = 0; i < max_pvalues.size(); ++i) max_pvalues[i] = pu[g_eng.family_unique[i]];
 }
 
+void cafe_likelihood_ratio_test(pCafeParam param, double* maximumPvalues) {
+    cafe_log(param, "Running Likelihood Ratio Test....\n");
+    std::vector<double> unit_prior(param->pcafe->rfsize, 1.0);
+    cafe_gpu_sync_state(param->pfamily, param->pcafe, param->prior_rfsize ? param->prior_rfsize : unit_prior.data());
+    if (!g_eng.matrices_valid) reset_birthdeath_cache(param->pcafe, 0, &param->family_size);
+    const int nnodes = param->pcafe->num_nodes();
+    const size_t nrows = param->pfamily->flist.size(), U = g_eng.unique_first.size();
+    std::vector<uint8_t> tested(U);
+    for (size_t u = 0; u < U; ++u) tested[u] = !(maximumPvalues[g_eng.unique_first[u]] > param->pvalue);  // cafe_main.c:358
+    std::vector<double> base(U), best((size_t)nnodes * U);
+    gpu_check(cafe_gpu_likelihood_ratio_test(g_eng.ctx, tested.data(), base.data(), best.data(), nullptr), "likelihood_ratio_test");
+    param->likelihoodRatios.assign(nnodes, std::vector<double>(nrows, -1.0));
+    const int root = param->pcafe->root;
+    for (int b = 0; b < nnodes; ++b) {
+        if (b == root) continue;  // cafe_main.c:369-373
+        std::vector<double> ratio(U, -1.0);
+        for (size_t u = 0; u < U; ++u) {
+            if (!tested[u]) continue;
+            const double prevlh = best[(size_t)b * U + u], maxlh = base[u];
+            ratio[u] = (prevlh == maxlh) ? 1 : 1 - cafe::chi2cdf(2 * (std::log(prevlh) - std::log(maxlh)), 1);  // :388
+        }
+        for (size_t i = 0; i < nrows; ++i) param->likelihoodRatios[b][i] = ratio[g_eng.family_unique[i]];  // :419-427
+    }
+    cafe_log(param, "Done : Likelihood Ratio test\n");
+}
+
 void write_pvalues(std::ostream& ost, const matrix& cd, int count) {
     ost << std::setw(10) << std::setprecision(9);
     for (const auto& row : cd) {

@@ -53,6 +53,7 @@ struct CafeParam {  // libtree/family.h:115-172 (fields used by the lambda / lam
     int quiet = 0;
     std::vector<std::vector<double>> cond_dist;  // ConditionalDistribution::matrix
     std::vector<double> max_pvalues;             // viterbi.maximumPvalues
+    std::vector<std::vector<double>> likelihoodRatios;  // [node][family], libtree/family.h:169
     int objective_calls = 0;
 };
 typedef CafeParam* pCafeParam;
@@ -104,6 +105,10 @@ void best_lambda_mu_by_fminsearch(pCafeParam param, int lambda_len, int mu_len, 
 typedef std::vector<std::vector<double>> matrix;
 matrix cafe_conditional_distribution(pCafeTree pTree, family_size_range* range, int numthreads, int num_random_samples);
 void cafe_family_pvalues(pCafeParam param, std::vector<double>& max_pvalues);
+// cafe/cafe_main.c:398-431 (+ the per-family body :342-396) — branch-stretch likelihood-ratio test of `report ... likelihood`:
+// fills param->likelihoodRatios[b][i]; -1 for the root's row and for families whose maximumPvalues[i] > param->pvalue;
+// duplicates copy their first occurrence.  All families at once through cafe_gpu_likelihood_ratio_test.
+void cafe_likelihood_ratio_test(pCafeParam param, double* maximumPvalues);
 // cafe/pvalue.cpp:63-93, cafe/cafe_commands.cpp:1373-1396 — text format of `pvalue -o / -i`
 void write_pvalues(std::ostream& ost, const matrix& cd, int count);
 matrix read_pvalues(std::istream& ist, int count);

@@ -26,6 +26,7 @@ const char* cafe_host_last_error() { return g_host_err.c_str(); }
 double cafe_host_gammaln(double a) { return cafe::gammaln(a); }
 double cafe_host_chooseln(double n, double r) { return cafe::chooseln(n, r); }
 double cafe_host_poisspdf(int x, double l) { return cafe::poisspdf(x, l); }
+double cafe_host_chi2cdf(double x, int df) { return cafe::chi2cdf(x, df); }
 double cafe_host_pvalue(double v, const double* cd, int n) { return cafe::pvalue(v, cd, n); }
 void cafe_host_lnc_table(int size, double* out) {
     std::vector<double> T = cafe::lnc_table(size);
@@ -221,6 +222,26 @@ int cafe_host_get_max_pvalues(void* h, double* out, int cap) {
     if ((int)p.max_pvalues.size() > cap) return -1;
     std::copy(p.max_pvalues.begin(), p.max_pvalues.end(), out);
     return (int)p.max_pvalues.size();
+}
+int cafe_host_set_max_pvalues(void* h, const double* in, int n) {
+    CafeParam& p = static_cast<Globals*>(h)->param;
+    p.max_pvalues.assign(in, in + n);
+    return n;
+}
+// cafe_likelihood_ratio_test with the family p-values of the last report (or all families when none were computed);
+// out row-major [nodes][families]
+int cafe_host_likelihood_ratio_test(void* h, double* out, long cap, int* nodes, int* families) {
+    HOST_TRY
+    CafeParam& p = static_cast<Globals*>(h)->param;
+    std::vector<double> mp = p.max_pvalues;
+    if (mp.size() != p.pfamily->flist.size()) mp.assign(p.pfamily->flist.size(), 0.0);
+    cafe_likelihood_ratio_test(&p, mp.data());
+    *nodes = (int)p.likelihoodRatios.size();
+    *families = (int)p.pfamily->flist.size();
+    if ((long)*nodes * *families > cap) { g_host_err = "cap too small"; return -1; }
+    for (int b = 0; b < *nodes; ++b) std::copy(p.likelihoodRatios[b].begin(), p.likelihoodRatios[b].end(), out + (size_t)b * *families);
+    return 0;
+    HOST_CATCH(-1)
 }
 
 }  // extern "C"

@@ -162,6 +162,22 @@ int cafe_gpu_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_lik
  * cut-off - that filter is the caller's.) */
 int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* branch_pvalues_out);
 
+/* Branch-stretch likelihood-ratio test (cafe_likelihood_ratio_test / __cafe_likelihood_ratio_test_thread_func,
+ * cafe/cafe_main.c:342-431, run by `report ... likelihood`, cafe/reports.cpp:684-685) for every family with the current rates and
+ * matrices.  For each non-root branch b (nlist order) the branch is lengthened by rint(0.15 * length) for as long as the family's
+ * maximum root likelihood grows (:377-386; the lengthened branch's matrix is keyed (int length, lambda_b, mu_b),
+ * libtree/birthdeath.c:363-370).  Outputs, row-major [n_nodes][n_families]:
+ *   best_max_likelihood_out[b][f] = the reference's `prevlh` when the loop stops (-1 in the root's row),
+ *   steps_out[b][f] (nullable)    = number of lengthenings that raised the likelihood,
+ *   base_max_likelihood_out[f] (nullable) = `maxlh` of the unlengthened tree.
+ * The caller forms likelihoodRatios[b][f] = best == base ? 1 : 1 - chi2cdf(2 * (log best - log base), 1)   (:388).
+ * tested (nullable = all): 0 skips a family — the reference's `maximumPvalues[i] > param->pvalue` filter (:358-362), whose rows
+ * the caller sets to -1; skipped families report best = base.  Like the reference, the first tested family starts from the parsed
+ * branch lengths and all later ones from the (int)-truncated lengths (the length is restored through an int, :350,:390).
+ * Afterwards the context is back at the tree's own keys; cafe_gpu_family_results needs a new cafe_gpu_score. */
+int cafe_gpu_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, double* base_max_likelihood_out,
+                                   double* best_max_likelihood_out, int32_t* steps_out);
+
 /* K4: conditional distribution (cafe/conditional_distribution.cpp:10-120): for every root size
  * s = root_min..root_max, n_samples simulated families (cafe/cafe_tree.c:533-569), each pruned with
  * root range {s} and the range.max ratchet of conditional_distribution.cpp:29; rows sorted ascending.

@@ -79,6 +79,11 @@ def lib():
     L.orc_family_pvalue.restype = C.c_double
     L.orc_family_pvalue.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _dpp, C.c_int, _ip,
                                     _dp, C.c_int, C.c_int, _dp, _ip]
+    L.orc_chi2cdf.restype = C.c_double
+    L.orc_chi2cdf.argtypes = [C.c_double, C.c_int]
+    L.orc_lrt_family.restype = C.c_int
+    L.orc_lrt_family.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, _dp, _dp, _dp, _ip, _dpp, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _ip]
     return L
 
 
@@ -141,6 +146,9 @@ def ref():
     R.refshim_load_families.restype = C.c_int
     R.refshim_load_families.argtypes = [C.c_char_p, C.c_int, _ip, _ip, _ip, C.c_int, _ip, _ip]
     R.refshim_session_free.argtypes = [C.c_void_p]
+    R.refshim_chi2cdf.restype = C.c_double
+    R.refshim_chi2cdf.argtypes = [C.c_double, C.c_int]
+    R.refshim_likelihood_ratio_test.argtypes = [C.c_void_p, _dp, C.c_double, _dp]
     R.refshim_fminsearch.argtypes = [MATH_FUNC, C.c_void_p, C.c_int, _dp, C.c_double, C.c_double, _dp, _dp, _ip]
     return R
 
@@ -326,6 +334,36 @@ def viterbi_branch_pvalues(tree: FlatTree, mats, sizes, range_max):
     out = np.zeros(tree.n_nodes)
     lib().orc_viterbi_branch_pvalues(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S, _iptr(sizes), range_max, _dptr(out))
     return out
+
+
+def chi2cdf(x, df=1):
+    return lib().orc_chi2cdf(float(x), int(df))
+
+
+def lrt_family(tree: FlatTree, mats, lam_per_node, mu_per_node, branchlength, counts_by_leaf, rng, leaf_err=None):
+    """Branch-stretch likelihood-ratio test of one family (cafe/cafe_main.c:342-396).  `branchlength` (float64 array) is updated in
+    place the way the reference's tree copy is (restored through an int).  Returns (ratios, best likelihood, steps) per node."""
+    S = next(m for m in mats if m is not None).shape[0]
+    lc = np.full(tree.n_nodes, -1, dtype=np.int32)
+    lc[0::2] = counts_by_leaf
+    mp, keep = _matrix_ptrs(mats)
+    E = 0
+    ep = None
+    if leaf_err is not None:
+        ep, keep2 = _matrix_ptrs(leaf_err)
+        E = next(m for m in leaf_err if m is not None).shape[0]
+    lam = np.ascontiguousarray(lam_per_node, dtype=np.float64)
+    mu = np.ascontiguousarray(mu_per_node, dtype=np.float64)
+    assert branchlength.dtype == np.float64 and branchlength.flags.c_contiguous
+    ratios = np.zeros(tree.n_nodes)
+    best = np.zeros(tree.n_nodes)
+    steps = np.zeros(tree.n_nodes, dtype=np.int32)
+    rc = lib().orc_lrt_family(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S, _dptr(lam), _dptr(mu),
+                              _dptr(branchlength), _iptr(lc), ep, E, rng[0], rng[1], rng[2], rng[3], _dptr(ratios), _dptr(best),
+                              _iptr(steps))
+    if rc != 0:
+        raise ValueError("leaf count outside the likelihood vector")
+    return ratios, best, steps
 
 
 def score(tree: FlatTree, mats, counts, rng, prior, ref_idx=None, leaf_err=None, want_L=False):

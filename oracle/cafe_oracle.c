@@ -490,3 +490,105 @@ void orc_viterbi_branch_pvalues(int n_nodes, const int *left, const int *right, 
     }
     (void)root;
 }
+
+/* ------------------------------------------------------------------ likelihood-ratio test (branch stretch) */
+
+#define ORC_EPS 1e-8 /* libcommon/mathfunc.h:12 */
+
+/* incgammaln_lower + gammaincln + gammainc + gamcdf + chi2cdf, libcommon/mathfunc.c:128-151,260-263,284-287:
+ * series only, at most 999 terms, stop at the first term below 1e-8; a series that never stops gives exactly 1. */
+double orc_chi2cdf(double x, int df)
+{
+    const double a = df / 2.0;
+    const double xs = x / 2;
+    double p = 1 / a, t = 1 / a;
+    int i;
+    for (i = 1; i < 1000; i++) {
+        t *= xs / (a + i);
+        if (t < ORC_EPS) break;
+        p += t;
+    }
+    double lower = (i == 1000) ? orc_gammaln(a) : log(p) + a * log(xs) - xs;
+    return exp(lower - orc_gammaln(a));
+}
+
+/* birthdeath_cache_get_matrix, libtree/birthdeath.c:363-382: matrices of lengthened branches are memoised by (int t, lambda, mu)
+ * (the sequence of lengths does not depend on the family, so every family after the first hits the cache). */
+typedef struct { int t, maxfs; double lambda, mu; double *M; } orc_cached_matrix;
+static orc_cached_matrix *g_lrt_cache = NULL;
+static int g_lrt_cache_n = 0, g_lrt_cache_cap = 0;
+
+void orc_lrt_cache_clear(void)
+{
+    for (int i = 0; i < g_lrt_cache_n; i++) free(g_lrt_cache[i].M);
+    free(g_lrt_cache);
+    g_lrt_cache = NULL;
+    g_lrt_cache_n = g_lrt_cache_cap = 0;
+}
+
+static const double *lrt_cached_matrix(int t, double lambda, double mu, int maxfs)
+{
+    for (int i = 0; i < g_lrt_cache_n; i++) {
+        const orc_cached_matrix *c = &g_lrt_cache[i];
+        if (c->t == t && c->maxfs == maxfs && c->lambda == lambda && c->mu == mu) return c->M;
+    }
+    if (g_lrt_cache_n == g_lrt_cache_cap) {
+        g_lrt_cache_cap = g_lrt_cache_cap ? 2 * g_lrt_cache_cap : 64;
+        g_lrt_cache = (orc_cached_matrix *)realloc(g_lrt_cache, sizeof(orc_cached_matrix) * (size_t)g_lrt_cache_cap);
+    }
+    orc_cached_matrix *c = &g_lrt_cache[g_lrt_cache_n++];
+    c->t = t; c->maxfs = maxfs; c->lambda = lambda; c->mu = mu;
+    c->M = (double *)malloc(sizeof(double) * (size_t)(maxfs + 1) * (maxfs + 1));
+    orc_bd_matrix((double)t, lambda, mu, maxfs, c->M);
+    return c->M;
+}
+
+/* __cafe_likelihood_ratio_test_thread_func, cafe/cafe_main.c:342-396, body for ONE family that passed the
+ * maximumPvalues filter (:358-362).  For every non-root node b in nlist order: start from the family's maximum root likelihood,
+ * lengthen the branch above b by rint(0.15 * length) (:380) for as long as the maximum root likelihood grows (:377-386; the matrix
+ * of the lengthened branch is keyed by the (int) length, libtree/birthdeath.c:363-370), then
+ *   ratio[b] = prev == maxlh ? 1 : 1 - chi2cdf(2 * (log(prev) - log(maxlh)), 1)     (:388), -1 at the root (:369-373).
+ * branchlength[] is IN/OUT like the thread's tree copy: the reference restores the length through an `int old_bl` (:350,:375,:390),
+ * so after the first family every non-root length is truncated.  best_out / steps_out (optional): prevlh at the stop and the
+ * number of lengthenings that raised the likelihood. */
+int orc_lrt_family(int n_nodes, const int *left, const int *right, int root, const double *const *node_matrix, int S,
+                   const double *lambda, const double *mu, double *branchlength, const int *leaf_count,
+                   const double *const *leaf_err, int E, int range_min, int range_max, int root_min, int root_max,
+                   double *ratios_out, double *best_out, int *steps_out)
+{
+    const int rf = root_max - root_min + 1;
+    double *L = (double *)malloc(sizeof(double) * (size_t)rf);
+    const double **mats = (const double **)malloc(sizeof(double *) * (size_t)n_nodes);
+    memcpy(mats, node_matrix, sizeof(double *) * (size_t)n_nodes);
+    int rc = orc_prune(n_nodes, left, right, root, mats, S, leaf_count, leaf_err, E, range_min, range_max, root_min, root_max, L);
+    if (rc) { free(L); free(mats); return rc; }
+    double maxlh = L[0];
+    for (int i = 1; i < rf; i++) if (L[i] > maxlh) maxlh = L[i]; /* __max, libcommon/mathfunc.c */
+    for (int b = 0; b < n_nodes; b++) {
+        if (b == root) {
+            ratios_out[b] = -1;
+            if (best_out) best_out[b] = -1;
+            if (steps_out) steps_out[b] = 0;
+            continue;
+        }
+        const int old_bl = (int)branchlength[b];
+        double prevlh = -1, nextlh = maxlh;
+        int steps = -1;
+        while (prevlh < nextlh) {
+            prevlh = nextlh;
+            steps++;
+            branchlength[b] += rint(branchlength[b] * 0.15);
+            mats[b] = lrt_cached_matrix(orc_key_branchlength(branchlength[b]), lambda[b], mu[b], S - 1);
+            orc_prune(n_nodes, left, right, root, mats, S, leaf_count, leaf_err, E, range_min, range_max, root_min, root_max, L);
+            nextlh = L[0];
+            for (int i = 1; i < rf; i++) if (L[i] > nextlh) nextlh = L[i];
+        }
+        ratios_out[b] = (prevlh == maxlh) ? 1 : 1 - orc_chi2cdf(2 * (log(prevlh) - log(maxlh)), 1);
+        if (best_out) best_out[b] = prevlh;
+        if (steps_out) steps_out[b] = steps;
+        branchlength[b] = old_bl;
+        mats[b] = node_matrix[b];
+    }
+    free(L); free(mats);
+    return 0;
+}

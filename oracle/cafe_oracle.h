@@ -124,6 +124,18 @@ int orc_viterbi(int n_nodes, const int *left, const int *right, int root, const 
 void orc_viterbi_branch_pvalues(int n_nodes, const int *left, const int *right, int root, const double *const *node_matrix,
                                 int S, const int *sizes, int range_max, double *out);
 
+/* libcommon/mathfunc.c:128-151,260-263,284-287 — chi2cdf through the series-only incomplete gamma */
+double orc_chi2cdf(double x, int df);
+
+/* __cafe_likelihood_ratio_test_thread_func, cafe/cafe_main.c:342-396, for ONE family that passed the p-value filter: per non-root
+ * branch, lengthen by rint(0.15*length) while the maximum root likelihood grows; ratios_out[b] = 1 or
+ * 1 - chi2cdf(2*(log best - log base), 1), -1 at the root.  branchlength[] is in/out (the reference restores lengths through an int). */
+void orc_lrt_cache_clear(void); /* frees the memoised matrices of lengthened branches (birthdeath.c:363-382) */
+int orc_lrt_family(int n_nodes, const int *left, const int *right, int root, const double *const *node_matrix, int S,
+                   const double *lambda, const double *mu, double *branchlength, const int *leaf_count,
+                   const double *const *leaf_err, int E, int range_min, int range_max, int root_min, int root_max,
+                   double *ratios_out, double *best_out /* optional */, int *steps_out /* optional */);
+
 #ifdef __cplusplus
 }
 #endif

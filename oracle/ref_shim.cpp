@@ -369,6 +369,36 @@ int refshim_fminsearch(math_func f, void* args, int n, const double* x0, double 
     return 0;
 }
 
+double refshim_chi2cdf(double x, int df) { return chi2cdf(x, df); }
+
+// cafe_likelihood_ratio_test (cafe/cafe_main.c:398-431) with num_threads = 1 on the session's tree, families and current
+// matrices (refshim_reset_cache first); out is row-major [n_nodes][F].
+// Reference defect, fenced: the test works on cafe_tree_copy(param->pcafe), and cafe_tree_node_copy (cafe_tree.c:485-494)
+// copies lambda but not mu - the copy's nodes get the TREE-level pcafe->mu (cafe_tree.c:39), which cafe_tree_new leaves at 0,
+// so the lengthened branches would be keyed (t, lambda, 0) whatever the model (and mu = 0 makes log(alpha) = -inf, NaN entries).
+// The shim sets the tree-level mu to the nodes' common mu first, so the copy carries the rates the caller set; callers
+// therefore use one mu for all nodes here.
+void refshim_likelihood_ratio_test(void* h, const double* max_pvalues, double pvalue_cutoff, double* out) {
+    Session* s = (Session*)h;
+    s->tree->mu = node_at(s, 0)->birth_death_probabilities.mu;
+    CafeParam param;
+    memset(&param, 0, sizeof(param));
+    param.pcafe = s->tree;
+    param.pfamily = s->family;
+    param.num_threads = 1;
+    param.pvalue = pvalue_cutoff;
+    param.quiet = 1;
+    param.flog = stdout;
+    const int F = s->family->flist->size, n = refshim_n_nodes(h);
+    std::vector<double> mp(max_pvalues, max_pvalues + F);
+    cafe_likelihood_ratio_test(&param, mp.data());
+    for (int b = 0; b < n; b++) {
+        memcpy(out + (size_t)b * F, param.likelihoodRatios[b], sizeof(double) * F);
+        free(param.likelihoodRatios[b]);
+    }
+    free(param.likelihoodRatios);
+}
+
 void refshim_session_free(void* h) {
     Session* s = (Session*)h;
     if (s->family) cafe_family_free(s->family);

@@ -131,6 +131,13 @@ def main():
     for f in range(len(counts)):
         pv[f] = R.refshim_family_pvalue(h, f, d(cd), Rr, N, None, None)
     np.savez_compressed(os.path.join(OUT, "cond_dist.npz"), cd=cd, uniforms=u, pvalues=pv, lam=np.array(0.005), n_samples=np.array(N))
+
+    # ---- branch-stretch likelihood-ratio test (cafe_likelihood_ratio_test, cafe_main.c:398-431) at lambda = 0.005 on the
+    #      families whose p-value above is <= 0.05; one thread.  The shim makes the tree copy carry mu = -1 (see ref_shim.cpp).
+    cutoff = 0.05
+    lr = np.zeros((n, len(counts)))
+    R.refshim_likelihood_ratio_test(h, d(pv), cutoff, d(lr))
+    np.savez_compressed(os.path.join(OUT, "lrt.npz"), ratios=lr, max_pvalues=pv, cutoff=np.array(cutoff), lam=np.array(0.005))
     R.refshim_session_free(h)
 
     # ---- error model file -> dense matrix (reader + column-sum fix), range.max = 140 as in test4

@@ -37,6 +37,14 @@ def test_math_bitwise_vs_oracle():
         assert (r["root_min"], r["root_max"], r["min"], r["max"]) == (a.value, b.value, c.value, d.value)
 
 
+def test_chi2cdf_bitwise_vs_oracle():
+    # the series-only incomplete gamma of the likelihood-ratio test (libcommon/mathfunc.c:128-151), incl. the never-converging tail
+    rng = np.random.RandomState(2)
+    for x in np.r_[rng.uniform(0, 40, 200), 1e-300, 1e-9, 3.841458820694124, 500.0, 1999.0, 2100.0, 1e5]:
+        assert chost.chi2cdf(x, 1) == oracle.chi2cdf(x, 1)
+    assert abs(chost.chi2cdf(3.841458820694124, 1) - 0.95) < 1e-6
+
+
 def test_pvalue_bitwise_vs_oracle():
     H = chost.load_library()
     rng = np.random.RandomState(1)
