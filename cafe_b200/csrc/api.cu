@@ -536,15 +536,15 @@ int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* 
     return run_viterbi(ctx, node_sizes_out, nullptr, true, branch_pvalues_out);
 }
 
-int cafe_gpu_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, double* base_max_likelihood_out,
-                                   double* best_max_likelihood_out, int32_t* steps_out) {
+int cafe_gpu_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, const double* lengthened_mu_per_node,
+                                   double* base_max_likelihood_out, double* best_max_likelihood_out, int32_t* steps_out) {
     if (!ctx || !best_max_likelihood_out) return CAFE_GPU_ERR_ARG;
     int rc = check_ready(ctx, "likelihood_ratio_test");
     if (rc) return rc;
     if (ctx->shard_world > 1) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "likelihood_ratio_test: matrices must be unsharded (cafe_gpu_set_key_shard(ctx, 0, 1))");
     rc = ensure_vec_buffers(ctx, ctx->F_pad);
     if (rc) return rc;
-    return run_lrt_branch_stretch(ctx, tested, base_max_likelihood_out, best_max_likelihood_out, steps_out);
+    return run_lrt_branch_stretch(ctx, tested, lengthened_mu_per_node, base_max_likelihood_out, best_max_likelihood_out, steps_out);
 }
 
 int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {

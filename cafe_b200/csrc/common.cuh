@@ -169,7 +169,8 @@ void fused2_release(cafe_gpu_ctx* ctx);
 int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
                                  double* cd_out);                       // conddist.cu    (K4)
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out);  // pvalue.cu (K5)
-int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, double* base_out, double* best_out, int32_t* steps_out);  // lrt.cu
+int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const double* lengthened_mu, double* base_out, double* best_out,
+                           int32_t* steps_out);                     // lrt.cu
 int build_one_matrix(cafe_gpu_ctx* ctx, int key);                       // api.cu (K1 for one key)
 int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool forced, double* branch_pv_out);  // viterbi.cu
 

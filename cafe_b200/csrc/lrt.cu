@@ -45,7 +45,8 @@ struct LrtBuffers {
 }  // namespace
 
 
-int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, double* base_out, double* best_out, int32_t* steps_out) {
+int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const double* lengthened_mu, double* base_out, double* best_out,
+                           int32_t* steps_out) {
     const int F = ctx->F, n = ctx->n_nodes;
     const int D = (int)ctx->keys.size();
     if ((size_t)D + 1 > ctx->mat_cap) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "lrt: no room for one more matrix");
@@ -105,7 +106,8 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, double* bas
             for (int iter = 0; iter < 100000; ++iter) {
                 bl += rint(bl * 0.15);                                             // cafe_main.c:380
                 ctx->keys = keys0;
-                ctx->keys.push_back(BdKey{(int)bl, ctx->lambda[b], ctx->mu[b]});   // birthdeath_cache_get_matrix, birthdeath.c:363-370
+                // birthdeath_cache_get_matrix, birthdeath.c:363-370
+                ctx->keys.push_back(BdKey{(int)bl, ctx->lambda[b], lengthened_mu ? lengthened_mu[b] : ctx->mu[b]});
                 ctx->node_key = node_key0;
                 ctx->node_key[b] = D;
                 rc = build_schedule(ctx);

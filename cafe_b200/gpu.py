@@ -69,7 +69,7 @@ def load_library():
     L.cafe_gpu_viterbi.argtypes = [vp, _ip, _dp]
     L.cafe_gpu_viterbi_report.argtypes = [vp, _ip, _dp]
     L.cafe_gpu_family_results.argtypes = [vp, _dp, _dp, _ip]
-    L.cafe_gpu_likelihood_ratio_test.argtypes = [vp, C.POINTER(C.c_uint8), _dp, _dp, _ip]
+    L.cafe_gpu_likelihood_ratio_test.argtypes = [vp, C.POINTER(C.c_uint8), _dp, _dp, _dp, _ip]
     L.cafe_gpu_family_likelihoods.argtypes = [vp, _dp]
     L.cafe_gpu_conditional_distribution.argtypes = [vp, C.c_int, _dp, C.c_uint64, _dp]
     L.cafe_gpu_conditional_distribution_rows.argtypes = [vp, C.c_int, _dp, C.c_uint64, C.c_int, C.c_int, _dp]
@@ -240,7 +240,7 @@ class CafeGpu:
         self._ck(self.L.cafe_gpu_viterbi_report(self.h, _i(sizes), _d(pv)), "viterbi_report")
         return sizes, pv
 
-    def likelihood_ratio_test(self, tested=None):
+    def likelihood_ratio_test(self, tested=None, lengthened_mu=None):
         """(base max likelihood [F], best max likelihood [n_nodes][F], steps [n_nodes][F]) of the branch-stretch test."""
         base = np.zeros(self.F)
         best = np.zeros((self.n_nodes, self.F))
@@ -250,7 +250,12 @@ class CafeGpu:
             tested = np.ascontiguousarray(tested, dtype=np.uint8)
             assert tested.shape == (self.F,)
             tp = tested.ctypes.data_as(C.POINTER(C.c_uint8))
-        self._ck(self.L.cafe_gpu_likelihood_ratio_test(self.h, tp, _d(base), _d(best), _i(steps)), "likelihood_ratio_test")
+        mp = None
+        if lengthened_mu is not None:
+            lengthened_mu = np.ascontiguousarray(lengthened_mu, dtype=np.float64)
+            assert lengthened_mu.shape == (self.n_nodes,)
+            mp = _d(lengthened_mu)
+        self._ck(self.L.cafe_gpu_likelihood_ratio_test(self.h, tp, mp, _d(base), _d(best), _i(steps)), "likelihood_ratio_test")
         return base, best, steps
 
     def family_likelihoods(self):

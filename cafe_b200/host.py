@@ -61,7 +61,7 @@ def load_library():
     H.cafe_host_set_max_pvalues.argtypes = [vp, _dp, C.c_int]
     H.cafe_host_chi2cdf.restype = C.c_double
     H.cafe_host_chi2cdf.argtypes = [C.c_double, C.c_int]
-    H.cafe_host_likelihood_ratio_test.argtypes = [vp, _dp, C.c_long, _ip, _ip]
+    H.cafe_host_likelihood_ratio_test.argtypes = [vp, C.c_int, _dp, C.c_long, _ip, _ip]
     return H
 
 
@@ -258,13 +258,14 @@ class Session:
         pv = np.ascontiguousarray(pv, dtype=np.float64)
         self.H.cafe_host_set_max_pvalues(self.h, _d(pv), len(pv))
 
-    def likelihood_ratio_test(self):
-        """cafe_likelihood_ratio_test (cafe/cafe_main.c:398-431): likelihoodRatios [nodes][families]."""
+    def likelihood_ratio_test(self, tree_level_mu=False):
+        """cafe_likelihood_ratio_test (cafe/cafe_main.c:398-431): likelihoodRatios [nodes][families].  tree_level_mu=True keys the
+        lengthened branches with mu = 0 like the stock reference binary (its tree copy drops the nodes' mu)."""
         F = self.num_families()
         buf = np.zeros(F * 4096)
         nodes = C.c_int()
         fams = C.c_int()
-        if self.H.cafe_host_likelihood_ratio_test(self.h, _d(buf), buf.size, C.byref(nodes), C.byref(fams)) < 0:
+        if self.H.cafe_host_likelihood_ratio_test(self.h, int(tree_level_mu), _d(buf), buf.size, C.byref(nodes), C.byref(fams)) < 0:
             raise CafeHostError(self.H.cafe_host_last_error().decode())
         return buf[: nodes.value * fams.value].reshape(nodes.value, fams.value).copy()
 

@@ -347,6 +347,7 @@ int cafe_cmd_report(Globals& globals, std::vector<std::string> tokens) {
         std::string o = tokens[i];
         for (char& c : o) c = (char)std::tolower((unsigned char)c);
         if (o == "likelihood") likelihood = true;
+        if (o == "likelihood-stock") { likelihood = true; param->lrt_tree_level_mu = 1; }  // the stock binary's numbers (cafe_param.h)
         if (o == "branchcutting" || o == "lh2") throw std::runtime_error("report: " + o + " is not built (SURVEY.md 8f)");
     }
     if (likelihood) {

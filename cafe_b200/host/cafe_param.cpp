@@ -549,7 +549,9 @@ void cafe_likelihood_ratio_test(pCafeParam param, double* maximumPvalues) {
     std::vector<uint8_t> tested(U);
     for (size_t u = 0; u < U; ++u) tested[u] = !(maximumPvalues[g_eng.unique_first[u]] > param->pvalue);  // cafe_main.c:358
     std::vector<double> base(U), best((size_t)nnodes * U);
-    gpu_check(cafe_gpu_likelihood_ratio_test(g_eng.ctx, tested.data(), base.data(), best.data(), nullptr), "likelihood_ratio_test");
+    const std::vector<double> tree_mu(nnodes, 0.0);  // pcafe->mu as cafe_tree_new(..., 0, 0) leaves it (cafe_commands.cpp:1171)
+    gpu_check(cafe_gpu_likelihood_ratio_test(g_eng.ctx, tested.data(), param->lrt_tree_level_mu ? tree_mu.data() : nullptr, base.data(),
+                                             best.data(), nullptr), "likelihood_ratio_test");
     param->likelihoodRatios.assign(nnodes, std::vector<double>(nrows, -1.0));
     const int root = param->pcafe->root;
     for (int b = 0; b < nnodes; ++b) {

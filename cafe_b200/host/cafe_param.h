@@ -54,6 +54,9 @@ struct CafeParam {  // libtree/family.h:115-172 (fields used by the lambda / lam
     std::vector<std::vector<double>> cond_dist;  // ConditionalDistribution::matrix
     std::vector<double> max_pvalues;             // viterbi.maximumPvalues
     std::vector<std::vector<double>> likelihoodRatios;  // [node][family], libtree/family.h:169
+    // 1: key the lengthened branches of the likelihood-ratio test with the tree-level mu (0 after cafe_tree_new), as the stock
+    // reference does because cafe_tree_node_copy drops the nodes' mu (cafe/cafe_tree.c:485-494); 0: the nodes' own mu
+    int lrt_tree_level_mu = 0;
     int objective_calls = 0;
 };
 typedef CafeParam* pCafeParam;

@@ -230,9 +230,10 @@ int cafe_host_set_max_pvalues(void* h, const double* in, int n) {
 }
 // cafe_likelihood_ratio_test with the family p-values of the last report (or all families when none were computed);
 // out row-major [nodes][families]
-int cafe_host_likelihood_ratio_test(void* h, double* out, long cap, int* nodes, int* families) {
+int cafe_host_likelihood_ratio_test(void* h, int tree_level_mu, double* out, long cap, int* nodes, int* families) {
     HOST_TRY
     CafeParam& p = static_cast<Globals*>(h)->param;
+    p.lrt_tree_level_mu = tree_level_mu;
     std::vector<double> mp = p.max_pvalues;
     if (mp.size() != p.pfamily->flist.size()) mp.assign(p.pfamily->flist.size(), 0.0);
     cafe_likelihood_ratio_test(&p, mp.data());

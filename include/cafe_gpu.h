@@ -174,9 +174,13 @@ int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* 
  * tested (nullable = all): 0 skips a family — the reference's `maximumPvalues[i] > param->pvalue` filter (:358-362), whose rows
  * the caller sets to -1; skipped families report best = base.  Like the reference, the first tested family starts from the parsed
  * branch lengths and all later ones from the (int)-truncated lengths (the length is restored through an int, :350,:390).
+ * lengthened_mu_per_node (nullable = the nodes' own mu): the mu the LENGTHENED branch is keyed with.  The reference runs this test
+ * on cafe_tree_copy(param->pcafe), and cafe_tree_node_copy (cafe/cafe_tree.c:485-494) copies lambda but not mu: the copy's nodes
+ * carry the tree-level pcafe->mu (cafe_tree.c:39), which cafe_tree_new leaves at 0.  Passing zeros reproduces the stock binary's
+ * numbers (keys (t, lambda, 0): log(alpha) = -inf, the NaN entries clamp to 1); NULL runs the algorithm as written.
  * Afterwards the context is back at the tree's own keys; cafe_gpu_family_results needs a new cafe_gpu_score. */
-int cafe_gpu_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, double* base_max_likelihood_out,
-                                   double* best_max_likelihood_out, int32_t* steps_out);
+int cafe_gpu_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, const double* lengthened_mu_per_node,
+                                   double* base_max_likelihood_out, double* best_max_likelihood_out, int32_t* steps_out);
 
 /* K4: conditional distribution (cafe/conditional_distribution.cpp:10-120): for every root size
  * s = root_min..root_max, n_samples simulated families (cafe/cafe_tree.c:533-569), each pruned with

@@ -148,7 +148,7 @@ def ref():
     R.refshim_session_free.argtypes = [C.c_void_p]
     R.refshim_chi2cdf.restype = C.c_double
     R.refshim_chi2cdf.argtypes = [C.c_double, C.c_int]
-    R.refshim_likelihood_ratio_test.argtypes = [C.c_void_p, _dp, C.c_double, _dp]
+    R.refshim_likelihood_ratio_test.argtypes = [C.c_void_p, _dp, C.c_double, C.c_int, _dp]
     R.refshim_fminsearch.argtypes = [MATH_FUNC, C.c_void_p, C.c_int, _dp, C.c_double, C.c_double, _dp, _dp, _ip]
     return R
 
@@ -342,7 +342,9 @@ def chi2cdf(x, df=1):
 
 def lrt_family(tree: FlatTree, mats, lam_per_node, mu_per_node, branchlength, counts_by_leaf, rng, leaf_err=None):
     """Branch-stretch likelihood-ratio test of one family (cafe/cafe_main.c:342-396).  `branchlength` (float64 array) is updated in
-    place the way the reference's tree copy is (restored through an int).  Returns (ratios, best likelihood, steps) per node."""
+    place the way the reference's tree copy is (restored through an int).  mu_per_node keys the LENGTHENED branches only (`mats`
+    are the tree's own matrices): zeros restate the stock binary (its tree copy carries the tree-level mu = 0), the nodes' own mu
+    the algorithm as written.  Returns (ratios, best likelihood, steps) per node."""
     S = next(m for m in mats if m is not None).shape[0]
     lc = np.full(tree.n_nodes, -1, dtype=np.int32)
     lc[0::2] = counts_by_leaf

@@ -556,6 +556,9 @@ int orc_lrt_family(int n_nodes, const int *left, const int *right, int root, con
                    const double *const *leaf_err, int E, int range_min, int range_max, int root_min, int root_max,
                    double *ratios_out, double *best_out, int *steps_out)
 {
+    /* mu[] is the mu the LENGTHENED branch is keyed with.  The stock reference runs on cafe_tree_copy(param->pcafe), whose nodes
+     * carry the tree-level pcafe->mu (cafe_tree.c:39; cafe_tree_node_copy :485-494 copies lambda only) = 0 after cafe_tree_new, not
+     * the node's own mu: pass zeros to restate the stock binary, the nodes' mu to restate the algorithm as written. */
     const int rf = root_max - root_min + 1;
     double *L = (double *)malloc(sizeof(double) * (size_t)rf);
     const double **mats = (const double **)malloc(sizeof(double *) * (size_t)n_nodes);

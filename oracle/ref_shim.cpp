@@ -378,9 +378,10 @@ double refshim_chi2cdf(double x, int df) { return chi2cdf(x, df); }
 // so the lengthened branches would be keyed (t, lambda, 0) whatever the model (and mu = 0 makes log(alpha) = -inf, NaN entries).
 // The shim sets the tree-level mu to the nodes' common mu first, so the copy carries the rates the caller set; callers
 // therefore use one mu for all nodes here.
-void refshim_likelihood_ratio_test(void* h, const double* max_pvalues, double pvalue_cutoff, double* out) {
+// keep_node_mu = 0 runs the stock behaviour (tree-level mu as cafe_tree_new left it: 0).
+void refshim_likelihood_ratio_test(void* h, const double* max_pvalues, double pvalue_cutoff, int keep_node_mu, double* out) {
     Session* s = (Session*)h;
-    s->tree->mu = node_at(s, 0)->birth_death_probabilities.mu;
+    s->tree->mu = keep_node_mu ? node_at(s, 0)->birth_death_probabilities.mu : 0;
     CafeParam param;
     memset(&param, 0, sizeof(param));
     param.pcafe = s->tree;

@@ -136,8 +136,11 @@ def main():
     #      families whose p-value above is <= 0.05; one thread.  The shim makes the tree copy carry mu = -1 (see ref_shim.cpp).
     cutoff = 0.05
     lr = np.zeros((n, len(counts)))
-    R.refshim_likelihood_ratio_test(h, d(pv), cutoff, d(lr))
-    np.savez_compressed(os.path.join(OUT, "lrt.npz"), ratios=lr, max_pvalues=pv, cutoff=np.array(cutoff), lam=np.array(0.005))
+    R.refshim_likelihood_ratio_test(h, d(pv), cutoff, 1, d(lr))
+    lr_stock = np.zeros((n, len(counts)))   # the unmodified behaviour: lengthened branches keyed with the tree-level mu = 0
+    R.refshim_likelihood_ratio_test(h, d(pv), cutoff, 0, d(lr_stock))
+    np.savez_compressed(os.path.join(OUT, "lrt.npz"), ratios=lr, ratios_stock=lr_stock, max_pvalues=pv, cutoff=np.array(cutoff),
+                        lam=np.array(0.005))
     R.refshim_session_free(h)
 
     # ---- error model file -> dense matrix (reader + column-sum fix), range.max = 140 as in test4

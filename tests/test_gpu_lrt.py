@@ -33,9 +33,10 @@ def _ratio(best, base):
     return 1.0 if best == base else 1 - chost.chi2cdf(2 * (np.log(best) - np.log(base)), 1)
 
 
-def _check(p, tested=None):
+def _check(p, tested=None, stock_mu=False):
     g = p.make_gpu()
-    base, best, steps = g.likelihood_ratio_test(tested)
+    mu_len = np.zeros(p.otree.n_nodes) if stock_mu else p.mu_node
+    base, best, steps = g.likelihood_ratio_test(tested, mu_len if stock_mu else None)
     score_after = g.score()[0]           # the context is back at the tree's own matrices
     g.close()
     assert np.isclose(score_after, p.oracle_score(want_L=False)["score"], rtol=1e-12, atol=1e-6)
@@ -51,7 +52,7 @@ def _check(p, tested=None):
             assert np.array_equal(best[:, f][np.arange(t.n_nodes) != t.root], np.full(t.n_nodes - 1, base[f]))
             assert not steps[:, f].any()
             continue
-        r_o, best_o, steps_o = oracle.lrt_family(t, mats, p.lam_node, p.mu_node, bl, p.counts[f], p.ranges, leaf_err=le)
+        r_o, best_o, steps_o = oracle.lrt_family(t, mats, p.lam_node, mu_len, bl, p.counts[f], p.ranges, leaf_err=le)
         assert best[t.root, f] == -1 and r_o[t.root] == -1
         for b in range(t.n_nodes):
             if b == t.root:
@@ -76,6 +77,12 @@ def test_lrt_example_tree():
 def test_lrt_two_classes_lambda_mu():
     # per-node (lambda, mu): the lengthened branch keeps ITS node's rates (the reference's tree copy drops mu, see oracle/ref_shim.cpp)
     _check(Problem(EXAMPLE_TREE, _counts(5, 40, 20, 4), [0.004, 0.007], mu=[0.003, 0.005], lambda_tree="(((2,2)1,(1,1)1)1,1)"))
+
+
+def test_lrt_stock_reference_mu():
+    # the unmodified binary keys lengthened branches (t, lambda, 0): 0/1 matrices out of clamped NaNs; same numbers here
+    _check(Problem(EXAMPLE_TREE, _counts(5, 48, 25, 5), 0.005), stock_mu=True)
+    _check(Problem(random_tree(9, 2), _counts(9, 30, 20, 6), 0.004, mu=0.003), stock_mu=True)
 
 
 @pytest.mark.parametrize("n_leaves,seed", [(3, 2), (13, 4), (20, 5)])
@@ -153,9 +160,13 @@ def test_lrt_reference_golden_through_the_host_mirror(tmp_path):
     assert s.command("lambda -l %.10g" % float(g["lam"])) == 0
     s.set_max_pvalues(g["max_pvalues"])
     lr = s.likelihood_ratio_test()
+    lr_stock = s.likelihood_ratio_test(tree_level_mu=True)
     s.close()
-    ref = g["ratios"]
-    assert lr.shape == ref.shape
-    assert np.array_equal(lr == -1, ref == -1)          # root row and filtered families
-    assert np.array_equal(lr == 1, ref == 1)            # "no lengthening helped"
-    assert np.abs(lr - ref).max() <= 1e-8
+    # "ratios": the reference with its tree copy carrying the nodes' mu (oracle/ref_shim.cpp); "ratios_stock": the unmodified
+    # behaviour, the numbers `report <name> likelihood` of the stock binary prints
+    for got, ref in ((lr, g["ratios"]), (lr_stock, g["ratios_stock"])):
+        assert got.shape == ref.shape
+        assert np.array_equal(got == -1, ref == -1)          # root row and filtered families
+        assert np.array_equal(got == 1, ref == 1)            # "no lengthening helped"
+        assert np.abs(got - ref).max() <= 1e-8
+    assert np.abs(lr - lr_stock).max() > 1e-3

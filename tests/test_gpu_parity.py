@@ -34,6 +34,7 @@ def small_counts(n_leaves, F, hi, seed):
     (10, 0.02, 0.01, 3), (1, 0.01, -1, 20), (68, 0.006335, -1, 140), (93, 0.005, -1, 250),
     (17, 0.004, 0.003, 250), (6, 0.002, 0.002, 84), (93, 0.02, -1, 30), (0.9, 0.1, -1, 10),
     (40, 0.001, 0.0015, 500),
+    (7, 0.005, 0.0, 40),   # mu = 0: log(alpha) = -inf, the NaN sums clamp to 1 (the stock likelihood-ratio test keys these)
 ])
 def test_k1_matrix_vs_oracle(t, lam, mu, maxfs):
     # a 2-leaf tree whose two branches carry the key under test
