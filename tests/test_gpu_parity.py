@@ -337,6 +337,84 @@ def test_k2_config2_full_size_properties():
     assert rel_err(ml[idx], o["maxlik"], 1e-290).max() <= TOL_L
 
 
+def _terms_of(make_problem, counts, env=None, want_mats=False):
+    """(problem, score, first zero, log-posterior terms, max likelihoods, argmax[, GPU-built matrix per node]) of one evaluation,
+    optionally under A/B environment switches."""
+    import os
+    saved = {}
+    for k, v in (env or {}).items():
+        saved[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        p = make_problem(counts)
+        g = p.make_gpu()
+        s, fz = g.score()
+        lp, ml, am = g.family_results()
+        mats = None
+        if want_mats:
+            mats = [None if v == p.otree.root else g.get_matrix(v) for v in range(p.otree.n_nodes)]
+        g.close()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return p, s, fz, lp, ml, am, mats
+
+
+def _full_size_properties(make_problem, counts, n_v1, n_pernode, n_oracle):
+    """The full-size checks of test_k2_config2_full_size_properties for any workload.  The oracle sample prunes with the
+    matrices the GPU built (K1 has its own S = 501 oracle test above), so the CPU never builds S = 501 matrices here."""
+    p, s, fz, lp, ml, am, mats = _terms_of(make_problem, counts, want_mats=True)
+    assert fz == -1 and np.isfinite(lp).all()
+    assert abs(s - float(lp.sum())) <= score_tol(s)                                   # (d) score == sum of the family terms
+    _, _, _, lp1, ml1, am1, _ = _terms_of(make_problem, counts[:n_v1], env={"CAFE_GPU_FUSED_V1": "1"})
+    assert np.array_equal(ml[:n_v1], ml1) and np.array_equal(am[:n_v1], am1)          # (b) the three CUDA paths agree
+    assert np.abs(lp[:n_v1] - lp1).max() <= 1e-12
+    _, _, _, lp2, ml2, am2, _ = _terms_of(make_problem, counts[:n_pernode], env={"CAFE_GPU_NO_FUSED": "1"})
+    assert np.array_equal(ml[:n_pernode], ml2) and np.array_equal(am[:n_pernode], am2)
+    assert np.abs(lp[:n_pernode] - lp2).max() <= 1e-12
+    perm = np.random.RandomState(5).permutation(len(counts))                           # (c) position independence
+    _, _, _, lp3, ml3, am3, _ = _terms_of(make_problem, counts[perm])
+    assert np.array_equal(ml[perm], ml3) and np.array_equal(am[perm], am3) and np.array_equal(lp[perm], lp3)
+    idx = np.random.RandomState(6).choice(len(counts), n_oracle, replace=False)       # (a) oracle sample
+    o = oracle.score(p.otree, mats, counts[idx], p.ranges, p.prior, leaf_err=p.oracle_leaf_err())
+    assert np.abs(lp[idx] - o["logpost"]).max() <= TOL_LOGPOST
+    assert rel_err(ml[idx], o["maxlik"], 1e-290).max() <= TOL_L
+    return p
+
+
+def test_k2_config3_full_size_properties():
+    # BASELINE configs[2]: 200 k families x 50 taxa, max size 400 (W=481, R=500, S=501), lambda and mu free
+    from cafe_b200 import synth
+    nw = synth.random_tree(50, 1)
+    counts, lam0 = synth.simulate_table(nw, 200000, 400, seed=11)
+    assert counts.shape == (200000, 50) and counts.max() == 400
+    # prior: Poisson(60) - with the Poisson(8) of the config-2 test the prior underflows to 0 at root sizes near 400 and the family
+    # that carries the table's maximum gets log(0), as it would in the reference
+    p = _full_size_properties(lambda c: Problem(nw, c, lam0, mu=0.8 * lam0, prior_lambda=60.0, ranges=(0, 480, 1, 500)),
+                              counts, n_v1=20000, n_pernode=2048, n_oracle=24)
+    assert p.otree.n_nodes == 99
+
+
+def test_k2_config4_full_size_properties():
+    # BASELINE configs[3]: 100 k families x 100 taxa, max size 200, 4 lambda classes on branch subsets, error model on every leaf
+    from cafe_b200 import synth
+    nw = synth.random_tree(100, 1)
+    counts, lam0 = synth.simulate_table(nw, 100000, 200, seed=12)
+    assert counts.shape == (100000, 100) and counts.max() == 200
+    E = _band_error_matrix(251, 0.0274)
+
+    def make(c):
+        q = Problem(nw, c, lam0, prior_lambda=8.0, ranges=(0, 250, 1, 250), err={k: E for k in range(100)})
+        n = q.otree.n_nodes
+        q.lam_node = np.array([lam0, 1.3 * lam0, 0.7 * lam0, 1.1 * lam0])[np.arange(n) % 4]   # `lambda -t` with classes 1..4
+        return q
+
+    _full_size_properties(make, counts, n_v1=20000, n_pernode=2048, n_oracle=24)
+
+
 def test_k1_key_shard_two_contexts_match_unsharded():
     # cafe_gpu_set_key_shard: two contexts stand in for two ranks; the "all-gather" is two device copies through torch
     import torch
