@@ -136,3 +136,37 @@ def test_k4_rows_split_equals_whole_distribution():
     assert np.array_equal(parts, whole)
     assert g.conditional_distribution_rows(64, 3, 3, seed=11).shape == (0, 64)
     g.close()
+
+
+def test_k4_k5_config5_full_size_properties():
+    # BASELINE configs[4]: the conditional distribution with 1000 draws per root size (R = 500 rows at max size 400, 50 taxa) and
+    # family p-values for 200 k families.  Too big for the CPU oracle as a whole: (a) rows ascending, finite, in [0, 1];
+    # (b) the rows two ranks would compute equal the whole; (c) the device generator gives the same distribution again for the
+    # same seed and a different one for another seed; (d) a family sample's p-values against the oracle fed with the GPU's own
+    # distribution and matrices; (e) p-values do not depend on the position of a family in the table.
+    from cafe_b200 import synth
+    nw = synth.random_tree(50, 1)
+    counts, lam0 = synth.simulate_table(nw, 200000, 400, seed=11)
+    p = Problem(nw, counts, lam0, prior_lambda=60.0, ranges=(0, 480, 1, 500))
+    g = p.make_gpu()
+    n = 1000
+    cd = g.conditional_distribution(n, seed=7)
+    assert cd.shape == (500, n)
+    assert np.isfinite(cd).all() and cd.min() >= 0 and cd.max() <= 1 and (np.diff(cd, axis=1) >= 0).all()
+    assert (cd[:12, -1] > 0).all()     # (with 50 leaves the probability of any one leaf pattern underflows to 0 at large root sizes)
+    rows = np.concatenate([g.conditional_distribution_rows(n, 0, 250, seed=7), g.conditional_distribution_rows(n, 250, 500, seed=7)])
+    assert np.array_equal(rows, cd)
+    assert not np.array_equal(g.conditional_distribution_rows(n, 100, 102, seed=8), cd[100:102])
+    pv = g.pvalues(cd)
+    assert pv.shape == (200000,) and pv.min() >= 0 and pv.max() <= 1
+    assert len(np.unique(pv)) > 10 and (pv < 0.01).mean() < 0.1   # families simulated from the model itself: not piled up at 0
+    mats = [None if v == p.otree.root else g.get_matrix(v) for v in range(p.otree.n_nodes)]
+    idx = np.random.RandomState(3).choice(len(counts), 16, replace=False)
+    ref = np.array([oracle.family_pvalue(p.otree, mats, counts[f], cd)[0] for f in idx])
+    assert np.abs(pv[idx] - ref).max() <= 1.0 / n + 1e-12
+    assert (pv[idx] == ref).mean() >= 0.8
+    g.close()
+    perm = np.random.RandomState(5).permutation(len(counts))[:50000]
+    g2 = Problem(nw, counts[perm], lam0, prior_lambda=60.0, ranges=(0, 480, 1, 500)).make_gpu()
+    assert np.array_equal(g2.pvalues(cd), pv[perm])
+    g2.close()
