@@ -74,13 +74,20 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
     for (int f = 0; f < F; ++f) mask_rest[f] = (!tested || tested[f]) ? 1 : 0;
     if (first_tested >= 0) mask_first[first_tested] = 1;
 
-    const std::vector<BdKey> keys0 = ctx->keys;
-    const std::vector<int> node_key0 = ctx->node_key;
-    auto restore = [&]() {
-        ctx->keys = keys0;
-        ctx->node_key = node_key0;
-        return build_schedule(ctx);
-    };
+    // the tree's own keys come back on every way out
+    struct KeyGuard {
+        cafe_gpu_ctx* ctx;
+        const std::vector<BdKey> keys0;
+        const std::vector<int> node_key0;
+        ~KeyGuard() {
+            ctx->keys = keys0;
+            ctx->node_key = node_key0;
+            build_schedule(ctx);
+            ctx->results_valid = false;  // d_maxlik holds the last lengthened tree, not the tree's own
+        }
+    } guard{ctx, ctx->keys, ctx->node_key};
+    const std::vector<BdKey>& keys0 = guard.keys0;
+    const std::vector<int>& node_key0 = guard.node_key0;
 
     for (int b = 0; b < n; ++b) {
         double* best_row = best_out + (size_t)b * F;
@@ -113,14 +120,13 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
                 rc = build_schedule(ctx);
                 if (!rc) rc = build_one_matrix(ctx, D);
                 if (!rc) rc = launch_prune(ctx, nullptr);
-                if (rc) { restore(); return rc; }
-                cudaMemsetAsync(B.d_count, 0, sizeof(int), ctx->stream);
+                if (rc) return rc;
+                CAFE_CK(ctx, cudaMemsetAsync(B.d_count, 0, sizeof(int), ctx->stream));
                 k_lrt_step<<<blocks, threads, 0, ctx->stream>>>(ctx->d_maxlik, F, B.d_prev, B.d_steps, B.d_active, B.d_count);
                 ctx->launches++;
                 int growing = 0;
-                cudaError_t e = cudaMemcpyAsync(&growing, B.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-                if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-                if (e != cudaSuccess) { restore(); CAFE_CK(ctx, e); }
+                CAFE_CK(ctx, cudaMemcpyAsync(&growing, B.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
                 if (growing == 0) break;
             }
         }
@@ -128,7 +134,5 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
         if (steps_row) CAFE_CK(ctx, cudaMemcpyAsync(steps_row, B.d_steps, F * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    rc = restore();
-    ctx->results_valid = false;  // d_maxlik holds the last lengthened tree, not the tree's own
-    return rc;
+    return CAFE_GPU_OK;
 }

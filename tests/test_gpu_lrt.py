@@ -161,6 +161,16 @@ def test_lrt_reference_golden_through_the_host_mirror(tmp_path):
     s.set_max_pvalues(g["max_pvalues"])
     lr = s.likelihood_ratio_test()
     lr_stock = s.likelihood_ratio_test(tree_level_mu=True)
+    # the command itself: `report <name> likelihood` draws its own conditional distribution, filters on ITS family p-values and
+    # writes one line per family
+    rep = str(tmp_path / "rep")
+    assert s.command("report %s likelihood" % rep) == 0
+    lr_cmd = s.likelihood_ratio_test()          # same p-values as the report just used
+    lines = open(rep + ".likelihood_ratios").read().strip().split("\n")[1:]
+    assert [ln.split("\t")[0] for ln in lines] == [str(i) for i in z["ids"]]
+    written = np.array([[float(x) for x in ln.split("\t")[1].strip("()").split(",")] for ln in lines]).T
+    assert written.shape == lr_cmd.shape and np.allclose(written, lr_cmd, rtol=1e-5, atol=1e-12)
+    assert s.command("report %s branchcutting" % rep) != 0       # segfaults inside the reference; rejected here
     s.close()
     # "ratios": the reference with its tree copy carrying the nodes' mu (oracle/ref_shim.cpp); "ratios_stock": the unmodified
     # behaviour, the numbers `report <name> likelihood` of the stock binary prints
