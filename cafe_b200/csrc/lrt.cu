@@ -4,8 +4,9 @@
 // the reference lengthens b by rint(0.15 * length) for as long as the family's maximum root likelihood grows, pruning the whole
 // tree again after every step.  The sequence of lengths does not depend on the family, so here one step is ONE batched
 // evaluation: K1 builds the single matrix of the lengthened branch (key (int t', lambda_b, mu_b) appended behind the tree's keys,
-// the other matrices stay), K2 prunes every family, and k_lrt_step advances the per-family state (previous best, still growing?)
-// on the device; the host reads back one counter per step and stops when no family is still growing.
+// the other matrices stay), K2 prunes the families that are still growing (packed into a table of their own - most families stop
+// after one or two steps), and k_lrt_step advances the per-family state (previous best, step count) on the device; the host reads
+// back one flag per surviving family and stops when none is left.
 #include <algorithm>
 #include <cmath>
 
@@ -20,26 +21,35 @@ __global__ void k_lrt_begin_branch(const double* __restrict__ base, int F, doubl
     steps[f] = 0;
 }
 
-// one `while (prevlh < nextlh)` turn of cafe_main.c:377-386 for every family that is still growing
-__global__ void k_lrt_step(const double* __restrict__ maxlik, int F, double* __restrict__ prev, int* __restrict__ steps,
-                           unsigned char* __restrict__ active, int* __restrict__ n_growing) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F || !active[f]) return;
-    const double next = maxlik[f];
-    if (prev[f] < next) {
+// the families that are still growing, packed: counts_c[leaf][i] = counts[leaf][idx[i]] (leaf-major, same leaf stride)
+__global__ void k_lrt_gather_counts(const int* __restrict__ counts, size_t leaf_stride, const int* __restrict__ idx, int n_active,
+                                    int* __restrict__ counts_c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_active) return;
+    const size_t row = (size_t)blockIdx.y * leaf_stride;
+    counts_c[row + i] = counts[row + idx[i]];
+}
+
+// one `while (prevlh < nextlh)` turn of cafe_main.c:377-386 for the packed families: maxlik[i] belongs to family idx[i]
+__global__ void k_lrt_step(const double* __restrict__ maxlik, const int* __restrict__ idx, int n_active, double* __restrict__ prev,
+                           int* __restrict__ steps, unsigned char* __restrict__ keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_active) return;
+    const int f = idx[i];
+    const double next = maxlik[i];
+    const bool grew = prev[f] < next;
+    if (grew) {
         prev[f] = next;
         steps[f]++;
-        atomicAdd(n_growing, 1);
-    } else {
-        active[f] = 0;
     }
+    keep[i] = grew ? 1 : 0;
 }
 
 struct LrtBuffers {
     double *d_base = nullptr, *d_prev = nullptr;
-    int *d_steps = nullptr, *d_count = nullptr;
-    unsigned char* d_active = nullptr;
-    ~LrtBuffers() { cudaFree(d_base); cudaFree(d_prev); cudaFree(d_steps); cudaFree(d_count); cudaFree(d_active); }
+    int *d_steps = nullptr, *d_idx = nullptr, *d_counts_c = nullptr;
+    unsigned char* d_keep = nullptr;
+    ~LrtBuffers() { cudaFree(d_base); cudaFree(d_prev); cudaFree(d_steps); cudaFree(d_idx); cudaFree(d_counts_c); cudaFree(d_keep); }
 };
 
 }  // namespace
@@ -54,8 +64,11 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
     CAFE_CK(ctx, cudaMalloc(&B.d_base, F * sizeof(double)));
     CAFE_CK(ctx, cudaMalloc(&B.d_prev, F * sizeof(double)));
     CAFE_CK(ctx, cudaMalloc(&B.d_steps, F * sizeof(int)));
-    CAFE_CK(ctx, cudaMalloc(&B.d_count, sizeof(int)));
-    CAFE_CK(ctx, cudaMalloc(&B.d_active, F));
+    CAFE_CK(ctx, cudaMalloc(&B.d_idx, F * sizeof(int)));
+    CAFE_CK(ctx, cudaMalloc(&B.d_keep, F));
+    const size_t counts_ints = (size_t)ctx->n_leaves * ctx->F_pad;
+    CAFE_CK(ctx, cudaMalloc(&B.d_counts_c, counts_ints * sizeof(int)));
+    CAFE_CK(ctx, cudaMemsetAsync(B.d_counts_c, 0, counts_ints * sizeof(int), ctx->stream));
     const int threads = 256, blocks = (F + threads - 1) / threads;
 
     // the unlengthened tree: maxlh of cafe_main.c:365
@@ -70,22 +83,26 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
     int first_tested = -1;
     for (int f = 0; f < F && first_tested < 0; ++f)
         if (!tested || tested[f]) first_tested = f;
-    std::vector<unsigned char> mask_rest(F), mask_first(F, 0);
-    for (int f = 0; f < F; ++f) mask_rest[f] = (!tested || tested[f]) ? 1 : 0;
-    if (first_tested >= 0) mask_first[first_tested] = 1;
+    std::vector<int> all_tested;
+    for (int f = 0; f < F; ++f)
+        if (!tested || tested[f]) all_tested.push_back(f);
 
-    // the tree's own keys come back on every way out
+    // the tree's own keys and the full family table come back on every way out
     struct KeyGuard {
         cafe_gpu_ctx* ctx;
         const std::vector<BdKey> keys0;
         const std::vector<int> node_key0;
+        int* const d_counts0;
+        const int F0;
         ~KeyGuard() {
             ctx->keys = keys0;
             ctx->node_key = node_key0;
+            ctx->d_counts = d_counts0;
+            ctx->F = F0;
             build_schedule(ctx);
             ctx->results_valid = false;  // d_maxlik holds the last lengthened tree, not the tree's own
         }
-    } guard{ctx, ctx->keys, ctx->node_key};
+    } guard{ctx, ctx->keys, ctx->node_key, ctx->d_counts, ctx->F};
     const std::vector<BdKey>& keys0 = guard.keys0;
     const std::vector<int>& node_key0 = guard.node_key0;
 
@@ -104,13 +121,15 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
         for (int variant = 0; variant < (two_starts ? 2 : 1); ++variant) {
             // variant 0: everyone from the truncated length (minus the first tested family when the parsed length is fractional)
             // variant 1: the first tested family from the parsed length
-            std::vector<unsigned char> mask = (variant == 0) ? mask_rest : mask_first;
-            if (variant == 0 && two_starts) mask[first_tested] = 0;
-            if (std::none_of(mask.begin(), mask.end(), [](unsigned char m) { return m != 0; })) continue;
-            CAFE_CK(ctx, cudaMemcpyAsync(B.d_active, mask.data(), F, cudaMemcpyHostToDevice, ctx->stream));
-            CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));  // `mask` is pageable and dies with this scope
+            // Only the families that are still growing are pruned again: they are packed into a table of their own (a family's
+            // result does not depend on its position, tests/test_gpu_parity.py), so a step costs K2 over the survivors only.
+            std::vector<int> idx;
+            if (variant == 1) idx.push_back(first_tested);
+            else for (int f : all_tested) if (!(two_starts && f == first_tested)) idx.push_back(f);
+            std::vector<unsigned char> keep;
             double bl = (variant == 0) ? truncated : parsed;
-            for (int iter = 0; iter < 100000; ++iter) {
+            for (int iter = 0; iter < 100000 && !idx.empty(); ++iter) {
+                const int n_active = (int)idx.size();
                 bl += rint(bl * 0.15);                                             // cafe_main.c:380
                 ctx->keys = keys0;
                 // birthdeath_cache_get_matrix, birthdeath.c:363-370
@@ -119,15 +138,27 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
                 ctx->node_key[b] = D;
                 rc = build_schedule(ctx);
                 if (!rc) rc = build_one_matrix(ctx, D);
-                if (!rc) rc = launch_prune(ctx, nullptr);
                 if (rc) return rc;
-                CAFE_CK(ctx, cudaMemsetAsync(B.d_count, 0, sizeof(int), ctx->stream));
-                k_lrt_step<<<blocks, threads, 0, ctx->stream>>>(ctx->d_maxlik, F, B.d_prev, B.d_steps, B.d_active, B.d_count);
+                CAFE_CK(ctx, cudaMemcpyAsync(B.d_idx, idx.data(), n_active * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                const dim3 ggrid((n_active + threads - 1) / threads, ctx->n_leaves);
+                k_lrt_gather_counts<<<ggrid, threads, 0, ctx->stream>>>(guard.d_counts0, ctx->F_pad, B.d_idx, n_active, B.d_counts_c);
                 ctx->launches++;
-                int growing = 0;
-                CAFE_CK(ctx, cudaMemcpyAsync(&growing, B.d_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                ctx->d_counts = B.d_counts_c;
+                ctx->F = n_active;
+                rc = launch_prune(ctx, nullptr);
+                ctx->d_counts = guard.d_counts0;
+                ctx->F = F;
+                if (rc) return rc;
+                k_lrt_step<<<(n_active + threads - 1) / threads, threads, 0, ctx->stream>>>(ctx->d_maxlik, B.d_idx, n_active, B.d_prev,
+                                                                                              B.d_steps, B.d_keep);
+                ctx->launches++;
+                keep.resize(n_active);
+                CAFE_CK(ctx, cudaMemcpyAsync(keep.data(), B.d_keep, n_active, cudaMemcpyDeviceToHost, ctx->stream));
                 CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
-                if (growing == 0) break;
+                int kept = 0;
+                for (int i = 0; i < n_active; ++i)
+                    if (keep[i]) idx[kept++] = idx[i];
+                idx.resize(kept);
             }
         }
         CAFE_CK(ctx, cudaMemcpyAsync(best_row, B.d_prev, F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

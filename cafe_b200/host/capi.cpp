@@ -233,10 +233,12 @@ int cafe_host_set_max_pvalues(void* h, const double* in, int n) {
 int cafe_host_likelihood_ratio_test(void* h, int tree_level_mu, double* out, long cap, int* nodes, int* families) {
     HOST_TRY
     CafeParam& p = static_cast<Globals*>(h)->param;
-    p.lrt_tree_level_mu = tree_level_mu;
     std::vector<double> mp = p.max_pvalues;
     if (mp.size() != p.pfamily->flist.size()) mp.assign(p.pfamily->flist.size(), 0.0);
-    cafe_likelihood_ratio_test(&p, mp.data());
+    const int saved = p.lrt_tree_level_mu;
+    p.lrt_tree_level_mu = tree_level_mu;
+    try { cafe_likelihood_ratio_test(&p, mp.data()); } catch (...) { p.lrt_tree_level_mu = saved; throw; }
+    p.lrt_tree_level_mu = saved;
     *nodes = (int)p.likelihoodRatios.size();
     *families = (int)p.pfamily->flist.size();
     if ((long)*nodes * *families > cap) { g_host_err = "cap too small"; return -1; }
