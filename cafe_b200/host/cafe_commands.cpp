@@ -323,12 +323,23 @@ int cafe_cmd_pvalue(Globals& globals, std::vector<std::string> tokens) {
     return 0;
 }
 
-// The p-value part of cafe_do_report (reports.cpp:650-708): matrices at the current lambda, conditional
-// distribution, family-wide p-values.  Output: "<report>.pvalues" with one "ID<TAB>p" line per family.
+// cafe_do_report (reports.cpp:650-708): matrices at the current lambda, conditional distribution, then cafe_viterbi (family-wide
+// p-values, Viterbi reconstruction, branch p-values), optionally the likelihood-ratio test, and the text report "<name>.cafe" in
+// the reference's format (cafe_report_text).  "<name>.pvalues" (one "ID<TAB>p" line per family) is kept as a convenience.
+// Options: `likelihood` = the test with the nodes' own mu; `likelihood-stock` = keyed like the stock binary (cafe_param.h);
+// `branchcutting` / `lh2` fail inside the reference itself and are rejected; html/json formats are not built.
 int cafe_cmd_report(Globals& globals, std::vector<std::string> tokens) {
     pCafeParam param = &globals.param;
     prereqs(param, true, true, true);
     if (tokens.size() < 2) throw std::runtime_error("Usage(report): report <name>\n");
+    bool likelihood = false;
+    for (size_t i = 2; i < tokens.size(); ++i) {  // report_parameters, reports.cpp:604-616
+        std::string o = tokens[i];
+        for (char& c : o) c = (char)std::tolower((unsigned char)c);
+        if (o == "likelihood") { likelihood = true; param->lrt_tree_level_mu = 0; }
+        if (o == "likelihood-stock") { likelihood = true; param->lrt_tree_level_mu = 1; }
+        if (o == "branchcutting" || o == "lh2" || o == "html" || o == "json") throw std::runtime_error("report: " + o + " is not built (SURVEY.md 8f)");
+    }
     cafe_shell_set_lambdas(param, param->input.parameters);
     reset_birthdeath_cache(param->pcafe, param->parameterized_k_value, &param->family_size);
     if (param->cond_dist.empty()) {
@@ -341,26 +352,13 @@ int cafe_cmd_report(Globals& globals, std::vector<std::string> tokens) {
     if (!ofst) throw std::runtime_error("ERROR(report): Cannot open " + tokens[1] + ".pvalues in write mode.\n");
     ofst << "ID\tFamily-wide P-value\n";
     for (size_t i = 0; i < param->pfamily->flist.size(); ++i) ofst << param->pfamily->flist[i].id << "\t" << param->max_pvalues[i] << "\n";
-    // report_parameters, reports.cpp:604-616: `likelihood` runs the branch-stretch likelihood-ratio test (reports.cpp:684-685)
-    bool likelihood = false;
-    for (size_t i = 2; i < tokens.size(); ++i) {
-        std::string o = tokens[i];
-        for (char& c : o) c = (char)std::tolower((unsigned char)c);
-        if (o == "likelihood") likelihood = true;
-        if (o == "likelihood-stock") { likelihood = true; param->lrt_tree_level_mu = 1; }  // the stock binary's numbers (cafe_param.h)
-        if (o == "branchcutting" || o == "lh2") throw std::runtime_error("report: " + o + " is not built (SURVEY.md 8f)");
-    }
-    if (likelihood) {
-        cafe_likelihood_ratio_test(param, param->max_pvalues.data());
-        std::ofstream lr((tokens[1] + ".likelihood_ratios").c_str());
-        if (!lr) throw std::runtime_error("ERROR(report): Cannot open " + tokens[1] + ".likelihood_ratios in write mode.\n");
-        lr << "ID\tLikelihood Ratio per node (nlist order)\n";
-        for (size_t i = 0; i < param->pfamily->flist.size(); ++i) {
-            lr << param->pfamily->flist[i].id << "\t(";
-            for (size_t b = 0; b < param->likelihoodRatios.size(); ++b) lr << (b ? "," : "") << param->likelihoodRatios[b][i];
-            lr << ")\n";
-        }
-    }
+    viterbi_parameters viterbi;
+    cafe_viterbi(param, viterbi);
+    if (likelihood) cafe_likelihood_ratio_test(param, param->max_pvalues.data());
+    cafe_log(param, "Building Text report: %s\n", tokens[1].c_str());
+    std::ofstream report((tokens[1] + ".cafe").c_str());
+    if (!report) throw std::runtime_error("ERROR(report) : Cannot open " + tokens[1] + " in write mode.\n");
+    cafe_report_text(report, param, viterbi);
     cafe_log(param, "Report Done\n");
     return 0;
 }

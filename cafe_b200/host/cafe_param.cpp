@@ -539,6 +539,24 @@ void cafe_family_pvalues(pCafeParam param, std::vector<double>& max_pvalues) {
     for (size_t i = 0; i < max_pvalues.size(); ++i) max_pvalues[i] = pu[g_eng.family_unique[i]];
 }
 
+void cafe_viterbi_all(pCafeParam param, std::vector<int>& node_sizes, std::vector<double>& branch_pvalues) {
+    std::vector<double> unit_prior(param->pcafe->rfsize, 1.0);
+    cafe_gpu_sync_state(param->pfamily, param->pcafe, param->prior_rfsize ? param->prior_rfsize : unit_prior.data());
+    if (!g_eng.matrices_valid) reset_birthdeath_cache(param->pcafe, 0, &param->family_size);
+    const int nnodes = param->pcafe->num_nodes();
+    const size_t nrows = param->pfamily->flist.size(), U = g_eng.unique_first.size();
+    std::vector<int32_t> su(U * nnodes);
+    std::vector<double> pu(U * nnodes);
+    gpu_check(cafe_gpu_viterbi_report(g_eng.ctx, su.data(), pu.data()), "viterbi_report");
+    node_sizes.resize(nrows * nnodes);
+    branch_pvalues.resize(nrows * nnodes);
+    for (size_t i = 0; i < nrows; ++i) {
+        const size_t u = g_eng.family_unique[i];
+        std::copy(su.begin() + u * nnodes, su.begin() + (u + 1) * nnodes, node_sizes.begin() + i * nnodes);
+        std::copy(pu.begin() + u * nnodes, pu.begin() + (u + 1) * nnodes, branch_pvalues.begin() + i * nnodes);
+    }
+}
+
 void cafe_likelihood_ratio_test(pCafeParam param, double* maximumPvalues) {
     cafe_log(param, "Running Likelihood Ratio Test....\n");
     std::vector<double> unit_prior(param->pcafe->rfsize, 1.0);

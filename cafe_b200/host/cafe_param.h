@@ -112,6 +112,20 @@ void cafe_family_pvalues(pCafeParam param, std::vector<double>& max_pvalues);
 // fills param->likelihoodRatios[b][i]; -1 for the root's row and for families whose maximumPvalues[i] > param->pvalue;
 // duplicates copy their first occurrence.  All families at once through cafe_gpu_likelihood_ratio_test.
 void cafe_likelihood_ratio_test(pCafeParam param, double* maximumPvalues);
+// Viterbi pass + text report of `report` (cafe/viterbi.h, cafe/viterbi.cpp:88-173,570-595, cafe/reports.cpp:157-194,230-500)
+struct change { int expand = 0, remain = 0, decrease = 0; };  // cafe/viterbi.h
+struct viterbi_parameters {
+    int num_nodes = 0, num_rows = 0;
+    std::vector<std::vector<int>> node_sizes;         // [family][node]: viterbiNodeFamilysizes + the observed leaves
+    std::vector<std::vector<double>> viterbiPvalues;  // [family][2j+k] for child k of internal node 2j+1; -1 when filtered
+    std::vector<double> maximumPvalues;
+    std::vector<double> averageExpansion;             // [2j+k]
+    std::vector<change> expandRemainDecrease;         // [2j+k]
+};
+// cafe_gpu_viterbi_report for every family: node sizes and per-branch p-values, row-major [family][node]
+void cafe_viterbi_all(pCafeParam param, std::vector<int>& node_sizes, std::vector<double>& branch_pvalues);
+void cafe_viterbi(pCafeParam param, viterbi_parameters& viterbi);  // needs param->max_pvalues (cafe_family_pvalues)
+void cafe_report_text(std::ostream& ost, pCafeParam param, const viterbi_parameters& viterbi);
 // cafe/pvalue.cpp:63-93, cafe/cafe_commands.cpp:1373-1396 — text format of `pvalue -o / -i`
 void write_pvalues(std::ostream& ost, const matrix& cd, int count);
 matrix read_pvalues(std::istream& ist, int count);

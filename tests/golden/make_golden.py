@@ -118,6 +118,19 @@ def main():
     ex["two_class_score"] = np.array(float(m4[-1]))
     np.savez_compressed(os.path.join(OUT, "example.npz"), **ex)
 
+    # ---- the text report of the stock binary (`report <name> [likelihood]`, reports.cpp:650-708): 100 draws per root size,
+    #      family p-value cut-off 0.05, generator re-seeded right before the report
+    def run_report(opt):
+        with tempfile.TemporaryDirectory() as td:
+            subprocess.run(["cp", os.path.join(REF, "example", "example_data.tab"), td], check=True)
+            open(os.path.join(td, "s.sh"), "w").write("\n".join([
+                "seed 10", "load -i example_data.tab -t 1 -p 0.05 -r 100", f"tree {EX_TREE}", "lambda -l 0.005", "seed 10",
+                f"report out {opt}".strip()]) + "\n")
+            subprocess.run([oracle.ref_binary(), "s.sh"], cwd=td, capture_output=True, text=True)
+            return open(os.path.join(td, "out.cafe")).read()
+    open(os.path.join(OUT, "report_plain.cafe"), "w").write(run_report(""))
+    open(os.path.join(OUT, "report_likelihood.cafe"), "w").write(run_report("likelihood"))
+
     # ---- conditional distribution + family p-values at lambda = 0.005 (1 thread, seed 10)
     R.refshim_set_rates(h, d(np.full(n, 0.005)), d(np.full(n, -1.0)))
     R.refshim_reset_cache(h)
