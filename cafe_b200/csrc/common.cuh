@@ -139,7 +139,6 @@ struct cafe_gpu_ctx {
     double* h_score = nullptr;    // pinned [2]
     bool results_valid = false;
 
-    bool prefer_per_node = false;  // launch_prune: take the per-node kernels (lrt.cu, when only a few families are left)
     void* fused_state = nullptr;   // prune_fused.cu private state (device schedule, scratch)
     void* fused2_state = nullptr;  // prune_fused2.cu private state
 

@@ -9,7 +9,6 @@
 // back one flag per surviving family and stops when none is left.
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -71,8 +70,6 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
     CAFE_CK(ctx, cudaMalloc(&B.d_counts_c, counts_ints * sizeof(int)));
     CAFE_CK(ctx, cudaMemsetAsync(B.d_counts_c, 0, counts_ints * sizeof(int), ctx->stream));
     const int threads = 256, blocks = (F + threads - 1) / threads;
-    const char* pn = std::getenv("CAFE_GPU_LRT_PER_NODE_MAX");  // tuning knob; default measured in profiles/r1_lrt_timing.jsonl
-    const int per_node_max = pn ? std::atoi(pn) : 0;
 
     // the unlengthened tree: maxlh of cafe_main.c:365
     int rc = launch_prune(ctx, nullptr);
@@ -102,7 +99,6 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
             ctx->node_key = node_key0;
             ctx->d_counts = d_counts0;
             ctx->F = F0;
-            ctx->prefer_per_node = false;
             build_schedule(ctx);
             ctx->results_valid = false;  // d_maxlik holds the last lengthened tree, not the tree's own
         }
@@ -149,11 +145,7 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
                 ctx->launches++;
                 ctx->d_counts = B.d_counts_c;
                 ctx->F = n_active;
-                // the persistent fused kernel has a latency floor of ~0.8 ms (one tile pair walks the whole tree serially); below
-                // a few hundred families one small launch per node is faster, and the paths are bit-identical
-                ctx->prefer_per_node = n_active <= per_node_max;
                 rc = launch_prune(ctx, nullptr);
-                ctx->prefer_per_node = false;
                 ctx->d_counts = guard.d_counts0;
                 ctx->F = F;
                 if (rc) return rc;

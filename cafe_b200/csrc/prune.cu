@@ -312,7 +312,7 @@ static LeafSrc make_leaf_src(cafe_gpu_ctx* ctx, int leaf, int key) {
 
 int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     if (ctx->timing) CAFE_CK(ctx, cudaEventRecord(ctx->quad(ctx->ring_k2)[2], ctx->stream));
-    const bool no_fused = ctx->prefer_per_node || std::getenv("CAFE_GPU_NO_FUSED") != nullptr;  // A/B switch for tests and profiling (read per call)
+    const bool no_fused = std::getenv("CAFE_GPU_NO_FUSED") != nullptr;  // A/B switches for tests and profiling (read per call)
     const bool fused_v1 = std::getenv("CAFE_GPU_FUSED_V1") != nullptr;  // first-generation fused kernel
     if (!no_fused && !fused_v1 && fused2_supported(ctx)) {
         // fused persistent kernel, one CTA per SM: whole tree + root reduction in one launch

@@ -128,6 +128,10 @@ k_viterbi_backtrack(const int* __restrict__ prefix, int n_prefix, const int* __r
         } else {
             const int par = parent[v];
             const int base = (par == root) ? root_min : range_min;
+            // A family with an empty root range (all counts 0: root 1..rint(1.25*0), viterbi.cpp / cafe_family.c:236-255) never
+            // writes the back-pointers of the root's children (:289-303 loops over no root size); the reference then reads
+            // whatever the previous family left there, 0 in a freshly allocated tree.  We return that 0.
+            if (par == root && R <= 0) { sz[v] = range_min; continue; }
             sz[v] = vit[(size_t)v * node_stride + (size_t)f * Vp + (sz[par] - base)] + range_min;
         }
     }

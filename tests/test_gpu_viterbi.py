@@ -97,8 +97,9 @@ def _check_report(p):
 
 def test_viterbi_report_forced_ranges_and_branch_pvalues():
     counts = _counts(5, 64, 25, 13)
-    counts[0] = 0            # an all-zero family: empty forced root range
+    counts[0] = 0            # almost empty
     counts[0, 0] = 1
+    counts[1] = 0            # an all-zero family: empty forced root range (root children reconstruct to 0, root to root_min)
     mx = int(counts.max())
     rg = chost.init_family_size(mx)
     _check_report(Problem(EXAMPLE_TREE, counts, 0.005, ranges=(rg["min"], rg["max"], rg["root_min"], rg["root_max"])))
