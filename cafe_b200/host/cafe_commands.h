@@ -1,7 +1,7 @@
 // cafe_commands.h — the command entry points that reach the likelihood path, with the reference's
 // signature `int cafe_cmd_X(Globals&, std::vector<std::string> tokens)` (cafe/cafe_commands.h:27) and
-// argument meaning: seed, load, tree, lambda, lambdamu, errormodel, pvalue, report (family p-values
-// only), source.  Everything else of the reference's shell is out of scope.
+// argument meaning: seed, load, tree, lambda, lambdamu, errormodel, pvalue, report (text format, optional likelihood-ratio
+// test), source.  Everything else of the reference's shell is out of scope.
 #pragma once
 #include <map>
 #include <string>
@@ -36,6 +36,6 @@ int cafe_cmd_lambda(Globals& globals, std::vector<std::string> tokens);      // 
 int cafe_cmd_lambdamu(Globals& globals, std::vector<std::string> tokens);    // lambdamu.cpp:218
 int cafe_cmd_errormodel(Globals& globals, std::vector<std::string> tokens);  // cafe_commands.cpp:1608
 int cafe_cmd_pvalue(Globals& globals, std::vector<std::string> tokens);      // cafe_commands.cpp:1365
-int cafe_cmd_report(Globals& globals, std::vector<std::string> tokens);      // cafe_commands.cpp:1010 (p-value part)
+int cafe_cmd_report(Globals& globals, std::vector<std::string> tokens);      // cafe_commands.cpp:1010, reports.cpp:650-708
 int cafe_cmd_source(Globals& globals, std::vector<std::string> tokens);      // cafe_commands.cpp:367
 int cafe_shell_dispatch_command(Globals& globals, const char* cmd);          // cafe_commands.cpp:504
