@@ -59,6 +59,7 @@ def load_library():
     H.cafe_host_get_cond_dist.argtypes = [vp, _dp, C.c_long, _ip, _ip]
     H.cafe_host_get_max_pvalues.argtypes = [vp, _dp, C.c_int]
     H.cafe_host_set_max_pvalues.argtypes = [vp, _dp, C.c_int]
+    H.cafe_host_report_text_from.argtypes = [vp, _dp, C.c_int, _ip, _dp, _dp, _dp, C.c_char_p]
     H.cafe_host_chi2cdf.restype = C.c_double
     H.cafe_host_chi2cdf.argtypes = [C.c_double, C.c_int]
     H.cafe_host_likelihood_ratio_test.argtypes = [vp, C.c_int, _dp, C.c_long, _ip, _ip]
@@ -253,6 +254,18 @@ class Session:
         if self.H.cafe_host_get_cond_dist(self.h, _d(buf), buf.size, C.byref(rows), C.byref(cols)) != 0:
             raise CafeHostError("no conditional distribution")
         return buf[: rows.value * cols.value].reshape(rows.value, cols.value).copy()
+
+    def report_text_from(self, lambdas, sizes, branch_pv, max_pv, path, likelihood_ratios=None):
+        """Write the text report (cafe_report_text) from given per-family results; no device work."""
+        lam = np.ascontiguousarray(lambdas, dtype=np.float64)
+        sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+        bpv = np.ascontiguousarray(branch_pv, dtype=np.float64)
+        mpv = np.ascontiguousarray(max_pv, dtype=np.float64)
+        lr = None if likelihood_ratios is None else np.ascontiguousarray(likelihood_ratios, dtype=np.float64)
+        rc = self.H.cafe_host_report_text_from(self.h, _d(lam), len(lam), _i(sizes), _d(bpv), _d(mpv),
+                                               None if lr is None else _d(lr), str(path).encode())
+        if rc < 0:
+            raise CafeHostError(self.H.cafe_host_last_error().decode())
 
     def set_max_pvalues(self, pv):
         pv = np.ascontiguousarray(pv, dtype=np.float64)

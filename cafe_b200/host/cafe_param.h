@@ -125,6 +125,8 @@ struct viterbi_parameters {
 // cafe_gpu_viterbi_report for every family: node sizes and per-branch p-values, row-major [family][node]
 void cafe_viterbi_all(pCafeParam param, std::vector<int>& node_sizes, std::vector<double>& branch_pvalues);
 void cafe_viterbi(pCafeParam param, viterbi_parameters& viterbi);  // needs param->max_pvalues (cafe_family_pvalues)
+void cafe_viterbi_from(pCafeParam param, const std::vector<int>& node_sizes, const std::vector<double>& branch_pvalues,
+                       viterbi_parameters& viterbi);  // the host part of cafe_viterbi (no device work)
 void cafe_report_text(std::ostream& ost, pCafeParam param, const viterbi_parameters& viterbi);
 // cafe/pvalue.cpp:63-93, cafe/cafe_commands.cpp:1373-1396 — text format of `pvalue -o / -i`
 void write_pvalues(std::ostream& ost, const matrix& cd, int count);

@@ -223,6 +223,35 @@ int cafe_host_get_max_pvalues(void* h, double* out, int cap) {
     std::copy(p.max_pvalues.begin(), p.max_pvalues.end(), out);
     return (int)p.max_pvalues.size();
 }
+// The text report from given per-family results (no device work): sizes / branch_pv row-major [families][nodes], max_pv [families],
+// lr nullable [nodes][families].  Lets the CPU tests pin the writer against the stock binary's report with the oracle's numbers.
+int cafe_host_report_text_from(void* h, const double* lambda, int num_lambdas, const int* sizes, const double* branch_pv,
+                               const double* max_pv, const double* lr, const char* path) {
+    HOST_TRY
+    CafeParam& p = static_cast<Globals*>(h)->param;
+    if (!p.pcafe || !p.pfamily) { g_host_err = "load and tree first"; return -1; }
+    const size_t F = p.pfamily->flist.size(), n = p.pcafe->num_nodes();
+    p.max_pvalues.assign(max_pv, max_pv + F);
+    viterbi_parameters v;
+    cafe_viterbi_from(&p, std::vector<int>(sizes, sizes + F * n), std::vector<double>(branch_pv, branch_pv + F * n), v);
+    std::vector<double> lam(lambda, lambda + num_lambdas);
+    double* const saved_lambda = p.lambda;
+    const int saved_n = p.num_lambdas;
+    const auto saved_lr = p.likelihoodRatios;
+    p.lambda = lam.data();
+    p.num_lambdas = num_lambdas;
+    p.likelihoodRatios.clear();
+    if (lr)
+        for (size_t b = 0; b < n; ++b) p.likelihoodRatios.emplace_back(lr + b * F, lr + (b + 1) * F);
+    std::ofstream out(path);
+    if (out) cafe_report_text(out, &p, v);
+    p.lambda = saved_lambda;
+    p.num_lambdas = saved_n;
+    p.likelihoodRatios = saved_lr;
+    if (!out) { g_host_err = "cannot open report file"; return -1; }
+    return 0;
+    HOST_CATCH(-1)
+}
 int cafe_host_set_max_pvalues(void* h, const double* in, int n) {
     CafeParam& p = static_cast<Globals*>(h)->param;
     p.max_pvalues.assign(in, in + n);

@@ -45,17 +45,16 @@ void write_doubles(std::ostream& ost, const std::vector<double>& items) {  // re
 
 // cafe_viterbi (viterbi.cpp:144-173) = viterbi_section for every family (:88-117): forced range, family p-values (already in
 // maximumPvalues), Viterbi reconstruction, size deltas (:570-595), branch p-values or -1 when the family is filtered.
-void cafe_viterbi(pCafeParam param, viterbi_parameters& viterbi) {
-    cafe_log(param, "Running Viterbi algorithm....\n");
+// cafe_viterbi_from is the host part: it arranges reconstructed sizes and branch p-values ([family][node]) the way
+// viterbi_parameters holds them.
+void cafe_viterbi_from(pCafeParam param, const std::vector<int>& sizes, const std::vector<double>& branch_pv, viterbi_parameters& viterbi) {
     const int nnodes = param->pcafe->num_nodes();
     const size_t nrows = param->pfamily->flist.size();
     if (param->max_pvalues.size() != nrows) throw std::runtime_error("cafe_viterbi: family p-values not computed");
+    if (sizes.size() != nrows * nnodes || branch_pv.size() != nrows * nnodes) throw std::runtime_error("cafe_viterbi: wrong array sizes");
     viterbi.num_nodes = nnodes;
     viterbi.num_rows = (int)nrows;
     viterbi.maximumPvalues = param->max_pvalues;
-    std::vector<int> sizes;
-    std::vector<double> branch_pv;
-    cafe_viterbi_all(param, sizes, branch_pv);  // [family][node]
     viterbi.node_sizes.assign(nrows, std::vector<int>(nnodes));
     viterbi.viterbiPvalues.assign(nrows, std::vector<double>(nnodes > 1 ? nnodes - 1 : 0, -1.0));
     viterbi.averageExpansion.assign(nnodes - 1, 0.0);
@@ -79,6 +78,14 @@ void cafe_viterbi(pCafeParam param, viterbi_parameters& viterbi) {
         }
     }
     for (double& a : viterbi.averageExpansion) a /= (double)nrows;  // viterbi.cpp:166-169
+}
+
+void cafe_viterbi(pCafeParam param, viterbi_parameters& viterbi) {
+    cafe_log(param, "Running Viterbi algorithm....\n");
+    std::vector<int> sizes;
+    std::vector<double> branch_pv;
+    cafe_viterbi_all(param, sizes, branch_pv);  // [family][node], cafe_gpu_viterbi_report
+    cafe_viterbi_from(param, sizes, branch_pv, viterbi);
 }
 
 // operator<<(ostream&, const Report&), text format (reports.cpp:447-500) with the family lines of :339-357

@@ -83,11 +83,11 @@ def test_lambda_tree_labels():
         chost.parse_lambda_tree(EX_TREE, "((1,1)1,1)")
 
 
-def write_table(path, species, rows, sep="\t"):
+def write_table(path, species, rows, sep="\t", ids=None):
     with open(path, "w") as f:
         f.write(sep.join(["Desc", "Family ID"] + species) + "\n")
         for i, r in enumerate(rows):
-            f.write(sep.join(["d%d" % i, "ID%d" % i] + [str(x) for x in r]) + "\n")
+            f.write(sep.join(["d%d" % i, ids[i] if ids else "ID%d" % i] + [str(x) for x in r]) + "\n")
 
 
 def test_family_loader_and_dedup(tmp_path, ref_lib):
@@ -213,3 +213,33 @@ def test_session_species_mapping_and_errors(tmp_path):
     assert s2.command("tree (A:1,B:1,C:1)") != 0     # not binary
     assert s2.command("lambda -s") != 0              # no table, no tree
     s2.close()
+
+
+@pytest.mark.parametrize("golden,with_lr", [("report_plain.cafe", False), ("report_likelihood.cafe", True)])
+def test_text_report_writer_with_oracle_numbers_equals_the_stock_binary(tmp_path, golden, with_lr):
+    # cafe_report_text (host/reports.cpp) fed with the ORACLE's Viterbi reconstruction, branch p-values (forced per-family ranges)
+    # and the golden family p-values / likelihood ratios must reproduce, character for character, the report the stock reference
+    # binary wrote for example_data.tab (tests/golden/make_golden.py): pins the writer and, once more, the oracle's Viterbi.
+    z = np.load(os.path.join(GOLD, "example.npz"))
+    cdz = np.load(os.path.join(GOLD, "cond_dist.npz"))
+    lrz = np.load(os.path.join(GOLD, "lrt.npz"))
+    counts = z["counts"]
+    p = str(tmp_path / "example_data.tab")
+    write_table(p, [str(s) for s in z["species_leaf_order"]], counts, ids=[str(i) for i in z["ids"]])
+    t = oracle.parse_newick(EX_TREE)
+    n = t.n_nodes
+    ranges = tuple(int(x) for x in z["ranges"])
+    mats = oracle.node_matrices(t, [0.005] * n, [-1.0] * n, max(ranges[1], ranges[3]))
+    sizes = np.zeros((len(counts), n), dtype=np.int32)
+    bpv = np.zeros((len(counts), n))
+    for f, c in enumerate(counts):
+        fr = oracle.forced_range(c)
+        sizes[f], _ = oracle.viterbi(t, mats, c, fr)
+        bpv[f] = oracle.viterbi_branch_pvalues(t, mats, sizes[f], fr[1])
+    s = chost.Session(quiet=True)
+    assert s.command("load -i %s -t 1 -p 0.05 -r 100" % p) == 0
+    assert s.command("tree " + EX_TREE) == 0
+    out = str(tmp_path / "out.cafe")
+    s.report_text_from([0.005], sizes, bpv, cdz["pvalues"], out, likelihood_ratios=lrz["ratios_stock"] if with_lr else None)
+    s.close()
+    assert open(out).read() == open(os.path.join(GOLD, golden)).read()
