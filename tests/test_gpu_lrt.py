@@ -180,3 +180,26 @@ def test_lrt_reference_golden_through_the_host_mirror(tmp_path):
         assert np.array_equal(got == 1, ref == 1)            # "no lengthening helped"
         assert np.abs(got - ref).max() <= 1e-8
     assert np.abs(lr - lr_stock).max() > 1e-3
+
+
+def test_lrt_error_states():
+    from cafe_b200 import gpu as cgpu
+    p = Problem(EXAMPLE_TREE, _counts(5, 16, 20, 2), 0.005)
+    g = p.make_gpu()
+    g.set_rates(p.lam_node, p.mu_node)                       # new rates, matrices not rebuilt yet
+    with pytest.raises(cgpu.CafeGpuError, match="build_matrices"):
+        g.likelihood_ratio_test()
+    g.build_matrices()
+    g.set_key_shard(0, 2)                                    # K1 sharded over two ranks: the test needs all matrices locally
+    g.build_matrices()
+    with pytest.raises(cgpu.CafeGpuError):
+        g.likelihood_ratio_test()
+    g.set_key_shard(0, 1)
+    g.build_matrices()
+    base, best, steps = g.likelihood_ratio_test(np.zeros(16, dtype=np.uint8))   # nobody tested: nothing to do
+    root = p.otree.root
+    assert not steps.any() and np.array_equal(np.delete(best, root, axis=0), np.tile(base, (p.otree.n_nodes - 1, 1)))
+    assert (best[root] == -1).all()
+    s_after, _ = g.score()
+    assert abs(s_after - p.oracle_score(want_L=False)["score"]) < 1e-6
+    g.close()
