@@ -80,9 +80,14 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
     // the thread's tree copy keeps the parsed (double) lengths only until the first tested family has gone over a branch: the
     // length is restored through `int old_bl` (cafe_main.c:350,375,390).  So the first tested family starts from the parsed
     // length, every later one from the truncated length.
+    // tested[f] == 2 marks a tested family that is NOT the table's first tested one even if it is the first of this context
+    // (a later shard of a table split over ranks): it starts from the truncated lengths like every later family.
     int first_tested = -1;
-    for (int f = 0; f < F && first_tested < 0; ++f)
-        if (!tested || tested[f]) first_tested = f;
+    for (int f = 0; f < F; ++f)
+        if (!tested || tested[f]) {
+            if (!tested || tested[f] == 1) first_tested = f;
+            break;
+        }
     std::vector<int> all_tested;
     for (int f = 0; f < F; ++f)
         if (!tested || tested[f]) all_tested.push_back(f);

@@ -109,6 +109,36 @@ def conditional_distribution_sharded(g, n_samples: int, seed: int, rank: int, wo
     return gather_rows(g.conditional_distribution_rows(n_samples, lo, hi, seed=seed), g.R, rank, world_size, group)
 
 
+def likelihood_ratio_test_sharded(g, tested_local, n_total: int, rank: int, world_size: int, lengthened_mu=None, group=None):
+    """The branch-stretch likelihood-ratio test (cafe_gpu_likelihood_ratio_test) with the families split over the ranks like the
+    score: every rank tests the families of its shard (the context `g` holds exactly those), no collective on the data path; one
+    all-gather of a flag per rank settles which shard owns the table's first tested family - only that family starts from the
+    parsed branch lengths (cafe/cafe_main.c:350,390), so the other shards mark theirs with 2 - and one all-gather brings the rows
+    together.  tested_local: uint8 per family of this shard (1 test, 0 skip).  Returns (base [n_total], best [n_nodes][n_total],
+    steps [n_nodes][n_total]) on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    tested_local = np.ascontiguousarray(tested_local, dtype=np.uint8).copy()
+    multi = dist.is_available() and dist.is_initialized() and world_size > 1
+    if multi:
+        use_cuda = dist.get_backend(group) == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+        mine = torch.tensor([1 if tested_local.any() else 0], dtype=torch.int32, device=dev)
+        flags = torch.empty(world_size, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(flags, mine, group=group)
+        if bool(flags[:rank].any().item()):
+            tested_local[tested_local == 1] = 2          # an earlier shard owns the first tested family
+    base, best, steps = g.likelihood_ratio_test(tested_local, lengthened_mu)
+    if not multi:
+        return base, best, steps
+    # rows = families for the gather: [F_local][1 + 2 * n_nodes]
+    local = np.concatenate([base[:, None], best.T, steps.T.astype(np.float64)], axis=1)
+    full = gather_rows(local, n_total, rank, world_size, group)
+    n_nodes = best.shape[0]
+    return full[:, 0].copy(), full[:, 1:1 + n_nodes].T.copy(), full[:, 1 + n_nodes:].T.astype(np.int32)
+
+
 def finish_score(s, z):
     """Host-side decode of reduce_score's result: (-inf, index) when some family had zero likelihood."""
     s, z = float(s), float(z)

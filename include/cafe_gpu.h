@@ -171,7 +171,8 @@ int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* 
  *   steps_out[b][f] (nullable)    = number of lengthenings that raised the likelihood,
  *   base_max_likelihood_out[f] (nullable) = `maxlh` of the unlengthened tree.
  * The caller forms likelihoodRatios[b][f] = best == base ? 1 : 1 - chi2cdf(2 * (log best - log base), 1)   (:388).
- * tested (nullable = all): 0 skips a family — the reference's `maximumPvalues[i] > param->pvalue` filter (:358-362), whose rows
+ * tested (nullable = all): 1 tests a family, 2 tests it as a family that is not the table's first tested one (see below; for the
+ * later shards of a table split over several contexts), 0 skips a family — the reference's `maximumPvalues[i] > param->pvalue` filter (:358-362), whose rows
  * the caller sets to -1; skipped families report best = base.  Like the reference, the first tested family starts from the parsed
  * branch lengths and all later ones from the (int)-truncated lengths (the length is restored through an int, :350,:390).
  * lengthened_mu_per_node (nullable = the nodes' own mu): the mu the LENGTHENED branch is keyed with.  The reference runs this test

@@ -123,3 +123,75 @@ def test_row_sharded_matrix_gather():
     mp.spawn(_rows_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     expect = np.arange(21, dtype=np.float64).reshape(7, 3).tolist()
     assert out[0] == expect and out[1] == expect
+
+
+# ------------------------------------------------------------------ likelihood-ratio test, families sharded
+LRT_TREE = "(((chimp:6.6,human:6.6):81.2,(mouse:17.4,rat:17.4):70.4):6.9,dog:93.7)"   # fractional lengths: the first-family quirk matters
+
+
+class _OracleLrtContext:
+    """Stands in for a C-ABI context that holds one shard: likelihood_ratio_test with the ABI's semantics (tested 0 / 1 / 2),
+    computed by the oracle (which tests/test_oracle.py pins against the compiled reference)."""
+
+    def __init__(self, tree, mats, lam, mu, counts, ranges):
+        self.t, self.mats, self.lam, self.mu, self.counts, self.ranges = tree, mats, lam, mu, counts, ranges
+
+    def likelihood_ratio_test(self, tested=None, lengthened_mu=None):
+        t = self.t
+        F = len(self.counts)
+        tested = np.ones(F, dtype=np.uint8) if tested is None else tested
+        base = np.zeros(F); best = np.zeros((t.n_nodes, F)); steps = np.zeros((t.n_nodes, F), dtype=np.int32)
+        bl = np.array(t.branchlength, dtype=np.float64)
+        first_done = False
+        for f in range(F):
+            base[f] = oracle.prune(t, self.mats, self.counts[f], self.ranges).max()
+            if not tested[f]:
+                best[:, f] = base[f]; best[t.root, f] = -1
+                continue
+            if not first_done and tested[f] == 2:
+                bl = np.floor(bl)             # not the table's first tested family: truncated lengths from the start
+            first_done = True
+            _, b, s = oracle.lrt_family(t, self.mats, self.lam, self.mu if lengthened_mu is None else lengthened_mu, bl,
+                                        self.counts[f], self.ranges)
+            best[:, f] = b; steps[:, f] = s
+        return base, best, steps
+
+
+def _lrt_problem():
+    t = oracle.parse_newick(LRT_TREE)
+    rng = np.random.RandomState(9)
+    counts = np.maximum(0, rng.randint(1, 14, size=(11, 1)) + rng.randint(-3, 4, size=(11, 5))).astype(np.int32)
+    counts[6, 1] += 20
+    ranges = (0, 60, 1, 40)
+    lam = np.full(t.n_nodes, 0.005); mu = np.full(t.n_nodes, -1.0)
+    mats = oracle.node_matrices(t, lam, mu, 60)
+    tested = np.ones(11, dtype=np.uint8)
+    tested[[0, 1, 7]] = 0                      # the first tested family (2) sits in shard 0, shard 1 starts with a tested one
+    return t, counts, ranges, lam, mu, mats, tested
+
+
+def _lrt_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    t, counts, ranges, lam, mu, mats, tested = _lrt_problem()
+    lo, hi = sharding.shard_bounds(len(counts), world, rank)
+    g = _OracleLrtContext(t, mats, lam, mu, counts[lo:hi], ranges)
+    out[rank] = sharding.likelihood_ratio_test_sharded(g, tested[lo:hi], len(counts), rank, world)
+    dist.destroy_process_group()
+
+
+def test_likelihood_ratio_test_sharded_equals_single_rank():
+    t, counts, ranges, lam, mu, mats, tested = _lrt_problem()
+    single = _OracleLrtContext(t, mats, lam, mu, counts, ranges).likelihood_ratio_test(tested)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_lrt_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in range(2):
+        for a, b in zip(out[r], single):
+            assert np.array_equal(a, b)
+    assert single[2].max() >= 2
+    # without the marker the second shard's first family would start from the parsed lengths: make sure the case is exercised
+    lo, hi = sharding.shard_bounds(len(counts), 2, 1)
+    wrong = _OracleLrtContext(t, mats, lam, mu, counts[lo:hi], ranges).likelihood_ratio_test(tested[lo:hi])
+    assert not np.array_equal(wrong[1], single[1][:, lo:hi])
