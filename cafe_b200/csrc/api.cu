@@ -41,8 +41,14 @@ int cafe_gpu_create(cafe_gpu_ctx** out, int device) {
     ctx->stream = ctx->own_stream;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    cudaMalloc(&ctx->d_score, 2 * sizeof(double));
-    cudaMallocHost(&ctx->h_score, 2 * sizeof(double));
+    if (cudaMalloc(&ctx->d_score, 2 * sizeof(double)) != cudaSuccess || cudaMalloc(&ctx->d_score_final, 2 * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_score, 2 * sizeof(double)) != cudaSuccess) {
+        g_create_error = std::string("cafe_gpu_create: allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        cudaFree(ctx->d_score); cudaFree(ctx->d_score_final);
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return CAFE_GPU_ERR_CUDA;
+    }
     *out = ctx;
     return CAFE_GPU_OK;
 }
@@ -51,11 +57,32 @@ static void free_err_models(cafe_gpu_ctx* ctx) {
     for (auto& e : ctx->errs) { cudaFree(e.d_rowptr); cudaFree(e.d_col); cudaFree(e.d_val); }
     ctx->errs.clear();
 }
+// drop the error models no leaf refers to any more (a session re-uploads its models whenever they change)
+static void gc_err_models(cafe_gpu_ctx* ctx) {
+    std::vector<int> remap(ctx->errs.size(), -1);
+    std::vector<ErrModelDev> kept;
+    for (int& e : ctx->leaf_err) {
+        if (e < 0) continue;
+        if (remap[e] < 0) { remap[e] = (int)kept.size(); kept.push_back(ctx->errs[e]); }
+        e = remap[e];
+    }
+    for (size_t i = 0; i < ctx->errs.size(); ++i)
+        if (remap[i] < 0) { cudaFree(ctx->errs[i].d_rowptr); cudaFree(ctx->errs[i].d_col); cudaFree(ctx->errs[i].d_val); }
+    ctx->errs.swap(kept);
+}
 
+static void destroy_one(cafe_gpu_ctx* ctx);
 void cafe_gpu_destroy(cafe_gpu_ctx* ctx) {
     if (!ctx) return;
+    for (cafe_gpu_ctx* p : ctx->peers) destroy_one(p);
+    ctx->peers.clear();
+    destroy_one(ctx);
+}
+static void destroy_one(cafe_gpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    comm_release(ctx);
+    cudaFree(ctx->d_score_all); cudaFree(ctx->d_score_final);
     cudaFree(ctx->d_lnc); cudaFree(ctx->d_lncT); cudaFree(ctx->d_counts); cudaFree(ctx->d_mult); cudaFree(ctx->d_first);
     cudaFree(ctx->d_logprior); cudaFree(ctx->d_prior_mant); cudaFree(ctx->d_prior_exp); cudaFree(ctx->d_keyparams); cudaFree(ctx->d_M); cudaFree(ctx->d_MT); cudaFree(ctx->d_vec);
     cudaFree(ctx->d_logpost); cudaFree(ctx->d_maxlik); cudaFree(ctx->d_argmax); cudaFree(ctx->d_score);
@@ -63,6 +90,7 @@ void cafe_gpu_destroy(cafe_gpu_ctx* ctx) {
     free_err_models(ctx);
     fused_release(ctx);
     fused2_release(ctx);
+    fused3_release(ctx);
     for (cudaEvent_t e : ctx->ring) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -77,14 +105,14 @@ int cafe_gpu_set_stream(cafe_gpu_ctx* ctx, void* cuda_stream) {
     return CAFE_GPU_OK;
 }
 
-int cafe_gpu_synchronize(cafe_gpu_ctx* ctx) {
+static int one_synchronize(cafe_gpu_ctx* ctx) {
     if (!ctx) return CAFE_GPU_ERR_ARG;
     CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
     return CAFE_GPU_OK;
 }
 
 // ------------------------------------------------------------------------------------------- setup
-int cafe_gpu_set_tree(cafe_gpu_ctx* ctx, int n_nodes, const int32_t* left, const int32_t* right, const double* branchlength) {
+static int one_set_tree(cafe_gpu_ctx* ctx, int n_nodes, const int32_t* left, const int32_t* right, const double* branchlength) {
     if (!ctx || n_nodes < 3 || (n_nodes & 1) == 0 || !left || !right || !branchlength)
         CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_tree: need an odd number (>=3) of nodes and non-null arrays");
     ctx->n_nodes = n_nodes;
@@ -126,10 +154,17 @@ int cafe_gpu_set_tree(cafe_gpu_ctx* ctx, int n_nodes, const int32_t* left, const
     ctx->keys.clear(); ctx->node_key.clear(); ctx->ops.clear();
     ctx->matrices_valid = false; ctx->results_valid = false;
     ctx->leaf_err.assign(ctx->n_leaves, -1);
+    free_err_models(ctx);
+    // every buffer whose size depends on the number of leaves or nodes goes: the family table (n_leaves x F_pad), the
+    // matrices (capacity >= n_nodes - 1 keys, plus n_leaves error-leaf matrices behind the transposed copies)
+    cudaFree(ctx->d_counts); ctx->d_counts = nullptr; ctx->counts_cap = 0;
+    ctx->F = 0; ctx->h_counts.clear();
+    cudaFree(ctx->d_M); cudaFree(ctx->d_MT); ctx->d_M = ctx->d_MT = nullptr; ctx->mat_cap = 0;
+    cudaFree(ctx->d_keyparams); ctx->d_keyparams = nullptr; ctx->keys_cap = 0;
     return CAFE_GPU_OK;
 }
 
-int cafe_gpu_set_ranges(cafe_gpu_ctx* ctx, int range_min, int range_max, int root_min, int root_max) {
+static int one_set_ranges(cafe_gpu_ctx* ctx, int range_min, int range_max, int root_min, int root_max) {
     if (!ctx) return CAFE_GPU_ERR_ARG;
     if (range_min != 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "set_ranges: range_min must be 0 (init_family_size, cafe_family.c:357-364)");
     if (range_max < 1 || root_min < 0 || root_max < root_min) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_ranges: bad range");
@@ -144,10 +179,14 @@ int cafe_gpu_set_ranges(cafe_gpu_ctx* ctx, int range_min, int range_max, int roo
     // geometry changed: drop size-dependent buffers
     cudaFree(ctx->d_M); cudaFree(ctx->d_MT); ctx->d_M = ctx->d_MT = nullptr; ctx->mat_cap = 0;
     cudaFree(ctx->d_vec); ctx->d_vec = nullptr; ctx->vec_cap = 0;
+    // the prior arrays are sized by the old root range: a new cafe_gpu_set_prior is required (check_ready)
+    cudaFree(ctx->d_logprior); cudaFree(ctx->d_prior_mant); cudaFree(ctx->d_prior_exp);
+    ctx->d_logprior = ctx->d_prior_mant = nullptr; ctx->d_prior_exp = nullptr;
+    ctx->h_prior.clear();
     return CAFE_GPU_OK;
 }
 
-int cafe_gpu_set_lnc_table(cafe_gpu_ctx* ctx, const double* lnc, int rows, int cols) {
+static int one_set_lnc_table(cafe_gpu_ctx* ctx, const double* lnc, int rows, int cols) {
     if (!ctx || !lnc || rows < 2 || cols < 2) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_lnc_table: bad arguments");
     cudaFree(ctx->d_lnc); cudaFree(ctx->d_lncT); ctx->d_lnc = ctx->d_lncT = nullptr;
     size_t bytes = (size_t)rows * cols * sizeof(double);
@@ -164,7 +203,7 @@ int cafe_gpu_set_lnc_table(cafe_gpu_ctx* ctx, const double* lnc, int rows, int c
     return CAFE_GPU_OK;
 }
 
-int cafe_gpu_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, const int32_t* counts,
+static int one_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, const int32_t* counts,
                           const int32_t* multiplicity, const int32_t* first_index) {
     if (!ctx || n_families < 1 || !counts) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_families: bad arguments");
     if (ctx->n_nodes == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "set_families: set_tree first");
@@ -182,11 +221,16 @@ int cafe_gpu_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, const
         mult[f] = multiplicity ? multiplicity[f] : 1;
         first[f] = first_index ? first_index[f] : f;
     }
-    if (F_pad != ctx->F_pad) {
-        cudaFree(ctx->d_counts); cudaFree(ctx->d_mult); cudaFree(ctx->d_first);
-        cudaFree(ctx->d_logpost); cudaFree(ctx->d_maxlik); cudaFree(ctx->d_argmax);
-        ctx->d_counts = ctx->d_mult = ctx->d_first = ctx->d_argmax = nullptr; ctx->d_logpost = ctx->d_maxlik = nullptr;
+    if (T.size() > ctx->counts_cap) {
+        cudaFree(ctx->d_counts); ctx->d_counts = nullptr; ctx->counts_cap = 0;
         CAFE_CK(ctx, cudaMalloc(&ctx->d_counts, T.size() * sizeof(int)));
+        ctx->counts_cap = T.size();
+    }
+    if (F_pad != ctx->F_pad) {
+        cudaFree(ctx->d_mult); cudaFree(ctx->d_first);
+        cudaFree(ctx->d_logpost); cudaFree(ctx->d_maxlik); cudaFree(ctx->d_argmax);
+        ctx->d_mult = ctx->d_first = ctx->d_argmax = nullptr; ctx->d_logpost = ctx->d_maxlik = nullptr;
+        ctx->F_pad = 0;
         CAFE_CK(ctx, cudaMalloc(&ctx->d_mult, F_pad * sizeof(int)));
         CAFE_CK(ctx, cudaMalloc(&ctx->d_first, F_pad * sizeof(int)));
         CAFE_CK(ctx, cudaMalloc(&ctx->d_logpost, F_pad * sizeof(double)));
@@ -204,7 +248,7 @@ int cafe_gpu_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, const
     return CAFE_GPU_OK;
 }
 
-int cafe_gpu_set_prior(cafe_gpu_ctx* ctx, const double* prior, int len) {
+static int one_set_prior(cafe_gpu_ctx* ctx, const double* prior, int len) {
     if (!ctx || !prior) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_prior: bad arguments");
     if (!ctx->have_ranges) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "set_prior: set_ranges first");
     if (len < ctx->R) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_prior: need at least root_max-root_min+1 values");
@@ -232,13 +276,14 @@ int cafe_gpu_set_prior(cafe_gpu_ctx* ctx, const double* prior, int len) {
     return CAFE_GPU_OK;
 }
 
-int cafe_gpu_set_error_model(cafe_gpu_ctx* ctx, int leaf, const double* errormatrix, int dim) {
+static int one_set_error_model(cafe_gpu_ctx* ctx, int leaf, const double* errormatrix, int dim) {
     if (!ctx) return CAFE_GPU_ERR_ARG;
     if (ctx->n_nodes == 0 || !ctx->have_ranges) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "set_error_model: set_tree and set_ranges first");
     if (leaf >= ctx->n_leaves) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_error_model: leaf out of range");
     ctx->results_valid = false;
     if (!errormatrix) {
         if (leaf < 0) ctx->leaf_err.assign(ctx->n_leaves, -1); else ctx->leaf_err[leaf] = -1;
+        gc_err_models(ctx);
         return CAFE_GPU_OK;
     }
     if (dim < ctx->rmax + 1) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_error_model: dim must be >= range_max+1");
@@ -264,6 +309,7 @@ int cafe_gpu_set_error_model(cafe_gpu_ctx* ctx, int leaf, const double* errormat
     ctx->errs.push_back(E);
     int idx = (int)ctx->errs.size() - 1;
     if (leaf < 0) ctx->leaf_err.assign(ctx->n_leaves, idx); else ctx->leaf_err[leaf] = idx;
+    gc_err_models(ctx);
     return CAFE_GPU_OK;
 }
 
@@ -295,7 +341,7 @@ static BdKeyParams key_params(const BdKey& k) {
     return P;
 }
 
-int cafe_gpu_set_rates(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node) {
+static int one_set_rates(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node) {
     if (!ctx || !lambda_per_node || !mu_per_node) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_rates: bad arguments");
     if (ctx->n_nodes == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "set_rates: set_tree first");
     const int n = ctx->n_nodes;
@@ -345,7 +391,7 @@ static int ensure_matrix_buffers(cafe_gpu_ctx* ctx) {
     return CAFE_GPU_OK;
 }
 
-int cafe_gpu_build_matrices(cafe_gpu_ctx* ctx) {
+static int one_build_matrices(cafe_gpu_ctx* ctx) {
     if (!ctx) return CAFE_GPU_ERR_ARG;
     if (!ctx->have_ranges || ctx->keys.empty()) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "build_matrices: set_ranges and set_rates first");
     if (!ctx->d_lnc) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "build_matrices: set_lnc_table first");
@@ -387,6 +433,10 @@ int cafe_gpu_matrix_storage(cafe_gpu_ctx* ctx, void** d_M, void** d_MT, int64_t*
 int cafe_gpu_matrices_exchanged(cafe_gpu_ctx* ctx) {
     if (!ctx) return CAFE_GPU_ERR_ARG;
     if (!ctx->matrices_need_exchange) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "matrices_exchanged: no sharded build_matrices pending");
+    // the transposed copies of the keys other ranks built (this rank's own were transposed right after K1)
+    cudaSetDevice(ctx->device);
+    int rc = launch_transpose_keys(ctx, 0, ctx->key_lo, ctx->key_hi, (int)ctx->keys.size());
+    if (rc) return rc;
     ctx->matrices_need_exchange = false;
     ctx->matrices_valid = true;
     return CAFE_GPU_OK;
@@ -394,7 +444,7 @@ int cafe_gpu_matrices_exchanged(cafe_gpu_ctx* ctx) {
 
 int cafe_gpu_num_keys(const cafe_gpu_ctx* ctx) { return ctx ? (int)ctx->keys.size() : 0; }
 
-int cafe_gpu_get_matrix(cafe_gpu_ctx* ctx, int node, double* out, int out_dim) {
+static int one_get_matrix(cafe_gpu_ctx* ctx, int node, double* out, int out_dim) {
     if (!ctx || !out) return CAFE_GPU_ERR_ARG;
     if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "get_matrix: build_matrices first");
     if (node < 0 || node >= ctx->n_nodes || ctx->node_key[node] < 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "get_matrix: node has no branch");
@@ -473,46 +523,11 @@ static int score_device(cafe_gpu_ctx* ctx, double* d_out2) {
     return CAFE_GPU_OK;
 }
 
-int cafe_gpu_score(cafe_gpu_ctx* ctx, double* score_out, int32_t* first_zero_family) {
-    if (!ctx || !score_out) return CAFE_GPU_ERR_ARG;
-    int rc = score_device(ctx, ctx->d_score);
-    if (rc) return rc;
-    CAFE_CK(ctx, cudaMemcpyAsync(ctx->h_score, ctx->d_score, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (std::isinf(ctx->h_score[1])) {
-        *score_out = ctx->h_score[0];
-        if (first_zero_family) *first_zero_family = -1;
-        return CAFE_GPU_OK;
-    }
-    *score_out = -std::numeric_limits<double>::infinity();  // log(0), lambda.cpp:753-760
-    if (first_zero_family) *first_zero_family = (int32_t)ctx->h_score[1];
-    return CAFE_GPU_ZERO_LIKELIHOOD;
-}
 
-int cafe_gpu_objective(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node,
-                       double* score_out, int32_t* first_zero_family) {
-    int rc = cafe_gpu_set_rates(ctx, lambda_per_node, mu_per_node);
-    if (rc) return rc;
-    rc = cafe_gpu_build_matrices(ctx);
-    if (rc) return rc;
-    return cafe_gpu_score(ctx, score_out, first_zero_family);
-}
 
-int cafe_gpu_score_device(cafe_gpu_ctx* ctx, double* out_device) {
-    if (!ctx || !out_device) return CAFE_GPU_ERR_ARG;
-    return score_device(ctx, out_device);
-}
 
-int cafe_gpu_objective_device(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node, double* out_device) {
-    if (!out_device) return CAFE_GPU_ERR_ARG;
-    int rc = cafe_gpu_set_rates(ctx, lambda_per_node, mu_per_node);
-    if (rc) return rc;
-    rc = cafe_gpu_build_matrices(ctx);
-    if (rc) return rc;
-    return score_device(ctx, out_device);
-}
 
-int cafe_gpu_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, double* max_likelihood, int32_t* argmax_likelihood) {
+static int one_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, double* max_likelihood, int32_t* argmax_likelihood) {
     if (!ctx) return CAFE_GPU_ERR_ARG;
     if (!ctx->results_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "family_results: score first");
     if (log_max_posterior) CAFE_CK(ctx, cudaMemcpyAsync(log_max_posterior, ctx->d_logpost, ctx->F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -522,32 +537,31 @@ int cafe_gpu_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, double
     return CAFE_GPU_OK;
 }
 
-int cafe_gpu_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_likelihood_out) {
+static int one_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_likelihood_out) {
     if (!ctx || !node_sizes_out) return CAFE_GPU_ERR_ARG;
     int rc = check_ready(ctx, "viterbi");
     if (rc) return rc;
     return run_viterbi(ctx, node_sizes_out, max_likelihood_out, false, nullptr);
 }
 
-int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* branch_pvalues_out) {
+static int one_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* branch_pvalues_out) {
     if (!ctx || !node_sizes_out) return CAFE_GPU_ERR_ARG;
     int rc = check_ready(ctx, "viterbi_report");
     if (rc) return rc;
     return run_viterbi(ctx, node_sizes_out, nullptr, true, branch_pvalues_out);
 }
 
-int cafe_gpu_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, const double* lengthened_mu_per_node,
+static int one_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, const double* lengthened_mu_per_node,
                                    double* base_max_likelihood_out, double* best_max_likelihood_out, int32_t* steps_out) {
     if (!ctx || !best_max_likelihood_out) return CAFE_GPU_ERR_ARG;
     int rc = check_ready(ctx, "likelihood_ratio_test");
     if (rc) return rc;
-    if (ctx->shard_world > 1) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "likelihood_ratio_test: matrices must be unsharded (cafe_gpu_set_key_shard(ctx, 0, 1))");
     rc = ensure_vec_buffers(ctx, ctx->F_pad);
     if (rc) return rc;
     return run_lrt_branch_stretch(ctx, tested, lengthened_mu_per_node, base_max_likelihood_out, best_max_likelihood_out, steps_out);
 }
 
-int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {
+static int one_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {
     if (!ctx || !L_out) return CAFE_GPU_ERR_ARG;
     int rc = check_ready(ctx, "family_likelihoods");
     if (rc) return rc;
@@ -566,13 +580,8 @@ int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {
 }
 
 // ------------------------------------------------------------------------------------------- K4 / K5
-int cafe_gpu_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, double* cd_out) {
-    if (!ctx || !cd_out || n_samples < 1) return CAFE_GPU_ERR_ARG;
-    if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "conditional_distribution: build_matrices first");
-    return run_conditional_distribution(ctx, n_samples, uniforms, seed, 0, ctx->R, cd_out);
-}
 
-int cafe_gpu_conditional_distribution_rows(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
+static int one_conditional_distribution_rows(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
                                            double* cd_out) {
     if (!ctx || !cd_out || n_samples < 1) return CAFE_GPU_ERR_ARG;
     if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "conditional_distribution_rows: build_matrices first");
@@ -581,7 +590,7 @@ int cafe_gpu_conditional_distribution_rows(cafe_gpu_ctx* ctx, int n_samples, con
     return run_conditional_distribution(ctx, n_samples, uniforms, seed, row_lo, row_hi, cd_out);
 }
 
-int cafe_gpu_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* max_pvalue_out) {
+static int one_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* max_pvalue_out) {
     if (!ctx || !cd || !max_pvalue_out || cd_rows < 1 || n_samples < 1) return CAFE_GPU_ERR_ARG;
     if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "pvalues: build_matrices first");
     if (ctx->F == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "pvalues: set_families first");
@@ -589,41 +598,380 @@ int cafe_gpu_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_sam
 }
 
 // ------------------------------------------------------------------------------------------- bookkeeping
-int64_t cafe_gpu_launch_count(const cafe_gpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
-void cafe_gpu_reset_launch_count(cafe_gpu_ctx* ctx) { if (ctx) ctx->launches = 0; }
+int64_t cafe_gpu_launch_count(const cafe_gpu_ctx* ctx) {
+    if (!ctx) return 0;
+    int64_t n = ctx->launches;
+    for (const cafe_gpu_ctx* p : ctx->peers) n += p->launches;
+    return n;
+}
+void cafe_gpu_reset_launch_count(cafe_gpu_ctx* ctx) {
+    if (!ctx) return;
+    ctx->launches = 0;
+    for (cafe_gpu_ctx* p : ctx->peers) p->launches = 0;
+}
 int cafe_gpu_enable_timing(cafe_gpu_ctx* ctx, int on) {
     if (!ctx) return CAFE_GPU_ERR_ARG;
     if (on && ctx->ring.empty()) {
-        ctx->ring.resize(4 * cafe_gpu_ctx::kRing);
+        ctx->ring.resize((size_t)cafe_gpu_ctx::kEv * cafe_gpu_ctx::kRing);
         for (auto& e : ctx->ring) CAFE_CK(ctx, cudaEventCreate(&e));
     }
     ctx->timing = on != 0;
-    ctx->ring_k1 = ctx->ring_k2 = 0;
+    ctx->ring_k1 = ctx->ring_k2 = ctx->ring_x = ctx->ring_r = 0;
     return CAFE_GPU_OK;
 }
-int cafe_gpu_timing_collect(cafe_gpu_ctx* ctx, float* k1_ms, float* k2_ms, int cap) {
+int cafe_gpu_timing_collect4(cafe_gpu_ctx* ctx, float* k1_ms, float* exchange_ms, float* k2_ms, float* reduce_ms, int cap) {
     if (!ctx || cap < 0) return CAFE_GPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
     CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    int n = std::min(std::min(ctx->ring_k1, ctx->ring_k2), std::min(cap, (int)cafe_gpu_ctx::kRing));
-    int first = std::min(ctx->ring_k1, ctx->ring_k2) - n;
+    const int done = std::min(ctx->ring_k1, ctx->ring_k2);
+    const bool multi = ctx->ring_x == ctx->ring_k1 && ctx->ring_r == ctx->ring_k2 && ctx->comm_world > 1;
+    int n = std::min(done, std::min(cap, (int)cafe_gpu_ctx::kRing));
+    int first = done - n;
     for (int i = 0; i < n; ++i) {
-        cudaEvent_t* q = ctx->quad(first + i);
-        if (k1_ms) CAFE_CK(ctx, cudaEventElapsedTime(&k1_ms[i], q[0], q[1]));
-        if (k2_ms) CAFE_CK(ctx, cudaEventElapsedTime(&k2_ms[i], q[2], q[3]));
+        const int e = first + i;
+        if (k1_ms) CAFE_CK(ctx, cudaEventElapsedTime(&k1_ms[i], ctx->evt(e, EV_K1_BEGIN), ctx->evt(e, EV_K1_END)));
+        if (k2_ms) CAFE_CK(ctx, cudaEventElapsedTime(&k2_ms[i], ctx->evt(e, EV_K2_BEGIN), ctx->evt(e, EV_K2_END)));
+        if (exchange_ms) { exchange_ms[i] = 0.f; if (multi) CAFE_CK(ctx, cudaEventElapsedTime(&exchange_ms[i], ctx->evt(e, EV_XCHG_BEGIN), ctx->evt(e, EV_XCHG_END))); }
+        if (reduce_ms) { reduce_ms[i] = 0.f; if (multi) CAFE_CK(ctx, cudaEventElapsedTime(&reduce_ms[i], ctx->evt(e, EV_RED_BEGIN), ctx->evt(e, EV_RED_END))); }
     }
-    ctx->ring_k1 = ctx->ring_k2 = 0;
+    ctx->ring_k1 = ctx->ring_k2 = ctx->ring_x = ctx->ring_r = 0;
     return n;
+}
+int cafe_gpu_timing_collect(cafe_gpu_ctx* ctx, float* k1_ms, float* k2_ms, int cap) {
+    return cafe_gpu_timing_collect4(ctx, k1_ms, nullptr, k2_ms, nullptr, cap);
 }
 
 double cafe_gpu_score_flops(const cafe_gpu_ctx* ctx) {
     if (!ctx || ctx->n_nodes == 0 || !ctx->have_ranges) return 0.0;
+    double peers = 0.0;
+    for (const cafe_gpu_ctx* p : ctx->peers) peers += cafe_gpu_score_flops(p);
     // internal edges only; 2*W*W per non-root parent, 2*R*W under the root
     double per_family = 0.0;
     for (int v = 0; v < ctx->n_nodes; ++v) {
         if (v == ctx->root || ctx->left[v] < 0) continue;  // v is an internal child => its edge is a real matvec
         per_family += (ctx->parent[v] == ctx->root) ? 2.0 * ctx->R * ctx->W : 2.0 * ctx->W * ctx->W;
     }
-    return per_family * ctx->F;
+    return per_family * ctx->F + peers;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// The public entry points: every call on a context fans out over its local contexts (itself, plus the peers of a leader
+// created by cafe_gpu_create_multi) with the right device current, and the evaluation calls run the NCCL exchange steps of
+// comm.cu when the context is a rank of a communicator.
+// =================================================================================================
+#include <thread>
+
+static std::vector<cafe_gpu_ctx*> locals_of(cafe_gpu_ctx* ctx) {
+    std::vector<cafe_gpu_ctx*> v{ctx};
+    v.insert(v.end(), ctx->peers.begin(), ctx->peers.end());
+    return v;
+}
+
+#define CAFE_NEED_LEADER(ctx)                                                                                      \
+    do {                                                                                                           \
+        if (!(ctx)) return CAFE_GPU_ERR_ARG;                                                                       \
+        if ((ctx)->leader) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "call this on the leader context of cafe_gpu_create_multi"); \
+    } while (0)
+
+// run fn(c) for every local context, in rank order, with c's device current; the first failure is reported on the leader
+template <typename Fn>
+static int each_local(cafe_gpu_ctx* ctx, Fn fn) {
+    for (cafe_gpu_ctx* c : locals_of(ctx)) {
+        cudaSetDevice(c->device);
+        const int rc = fn(c);
+        if (rc < 0) {
+            if (c != ctx) ctx->err = "device " + std::to_string(c->device) + ": " + c->err;
+            cudaSetDevice(ctx->device);
+            return rc;
+        }
+    }
+    cudaSetDevice(ctx->device);
+    return CAFE_GPU_OK;
+}
+// the same with one host thread per local context: for the calls that synchronise inside (whole passes over the families)
+template <typename Fn>
+static int each_local_parallel(cafe_gpu_ctx* ctx, Fn fn) {
+    std::vector<cafe_gpu_ctx*> L = locals_of(ctx);
+    if (L.size() == 1) { cudaSetDevice(ctx->device); return fn(ctx); }
+    std::vector<int> rc(L.size(), 0);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < L.size(); ++i)
+        th.emplace_back([&, i] { cudaSetDevice(L[i]->device); rc[i] = fn(L[i]); });
+    for (auto& t : th) t.join();
+    cudaSetDevice(ctx->device);
+    for (size_t i = 0; i < L.size(); ++i)
+        if (rc[i] < 0) {
+            if (L[i] != ctx) ctx->err = "device " + std::to_string(L[i]->device) + ": " + L[i]->err;
+            return rc[i];
+        }
+    return CAFE_GPU_OK;
+}
+
+// balanced contiguous slice of n items for rank r of w (sizes differ by at most one)
+static void shard_bounds(int n, int w, int r, int& lo, int& hi) {
+    const int base = n / w, extra = n % w;
+    lo = r * base + std::min(r, extra);
+    hi = lo + base + (r < extra ? 1 : 0);
+}
+
+extern "C" {
+
+int cafe_gpu_synchronize(cafe_gpu_ctx* ctx) {
+    CAFE_NEED_LEADER(ctx);
+    return each_local(ctx, [](cafe_gpu_ctx* c) { return one_synchronize(c); });
+}
+int cafe_gpu_set_tree(cafe_gpu_ctx* ctx, int n_nodes, const int32_t* left, const int32_t* right, const double* branchlength) {
+    CAFE_NEED_LEADER(ctx);
+    return each_local(ctx, [&](cafe_gpu_ctx* c) { return one_set_tree(c, n_nodes, left, right, branchlength); });
+}
+int cafe_gpu_set_ranges(cafe_gpu_ctx* ctx, int range_min, int range_max, int root_min, int root_max) {
+    CAFE_NEED_LEADER(ctx);
+    return each_local(ctx, [&](cafe_gpu_ctx* c) { return one_set_ranges(c, range_min, range_max, root_min, root_max); });
+}
+int cafe_gpu_set_lnc_table(cafe_gpu_ctx* ctx, const double* lnc, int rows, int cols) {
+    CAFE_NEED_LEADER(ctx);
+    return each_local(ctx, [&](cafe_gpu_ctx* c) { return one_set_lnc_table(c, lnc, rows, cols); });
+}
+int cafe_gpu_set_prior(cafe_gpu_ctx* ctx, const double* prior, int len) {
+    CAFE_NEED_LEADER(ctx);
+    return each_local(ctx, [&](cafe_gpu_ctx* c) { return one_set_prior(c, prior, len); });
+}
+int cafe_gpu_set_error_model(cafe_gpu_ctx* ctx, int leaf, const double* errormatrix, int dim) {
+    CAFE_NEED_LEADER(ctx);
+    return each_local(ctx, [&](cafe_gpu_ctx* c) { return one_set_error_model(c, leaf, errormatrix, dim); });
+}
+int cafe_gpu_set_rates(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node) {
+    CAFE_NEED_LEADER(ctx);
+    return each_local(ctx, [&](cafe_gpu_ctx* c) { return one_set_rates(c, lambda_per_node, mu_per_node); });
+}
+
+// The families of a multi-device context are split into contiguous, balanced slices in rank order (no cross-family state
+// except the sum and the first zero family, cafe/lambda.cpp:698-722).  With one process per GPU the caller passes its own slice.
+int cafe_gpu_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, const int32_t* counts, const int32_t* multiplicity,
+                          const int32_t* first_index) {
+    CAFE_NEED_LEADER(ctx);
+    if (ctx->peers.empty()) { cudaSetDevice(ctx->device); return one_set_families(ctx, n_families, n_leaves, counts, multiplicity, first_index); }
+    const int w = (int)ctx->peers.size() + 1;
+    if (n_families < w) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_families: fewer families than devices");
+    std::vector<int32_t> first_all;
+    if (!first_index) { first_all.resize(n_families); for (int f = 0; f < n_families; ++f) first_all[f] = f; first_index = first_all.data(); }
+    int r = 0;
+    return each_local(ctx, [&](cafe_gpu_ctx* c) {
+        int lo, hi;
+        shard_bounds(n_families, w, r++, lo, hi);
+        c->fam_lo = lo;
+        return one_set_families(c, hi - lo, n_leaves, counts + (size_t)lo * n_leaves, multiplicity ? multiplicity + lo : nullptr, first_index + lo);
+    });
+}
+
+int cafe_gpu_build_matrices(cafe_gpu_ctx* ctx) {
+    CAFE_NEED_LEADER(ctx);
+    int rc = each_local(ctx, [](cafe_gpu_ctx* c) {
+        if (c->comm_world > 1) { c->shard_rank = c->comm_rank; c->shard_world = c->comm_world; }  // K1 sharded over the ranks
+        return one_build_matrices(c);
+    });
+    if (rc || ctx->comm_world == 1) return rc;
+    std::vector<cafe_gpu_ctx*> L = locals_of(ctx);
+    rc = comm_exchange_matrices(L);
+    cudaSetDevice(ctx->device);
+    if (rc && L[0] != ctx) ctx->err = L[0]->err;
+    return rc;
+}
+
+int cafe_gpu_get_matrix(cafe_gpu_ctx* ctx, int node, double* out, int out_dim) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    return one_get_matrix(ctx, node, out, out_dim);
+}
+
+// K2 + K3 on every local context, then (with a communicator) the all-gather of the partial scores and the ordered final sum;
+// the result lands in every local context's d_score_final (comm) or d_score (single).
+static int score_all_device(cafe_gpu_ctx* ctx) {
+    int rc = each_local(ctx, [](cafe_gpu_ctx* c) { return score_device(c, c->d_score); });
+    if (rc || ctx->comm_world == 1) return rc;
+    std::vector<cafe_gpu_ctx*> L = locals_of(ctx);
+    rc = comm_reduce_scores(L);
+    cudaSetDevice(ctx->device);
+    return rc;
+}
+static int read_score(cafe_gpu_ctx* ctx, double* score_out, int32_t* first_zero_family) {
+    const double* src = ctx->comm_world > 1 ? ctx->d_score_final : ctx->d_score;
+    CAFE_CK(ctx, cudaMemcpyAsync(ctx->h_score, src, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (std::isinf(ctx->h_score[1])) {
+        *score_out = ctx->h_score[0];
+        if (first_zero_family) *first_zero_family = -1;
+        return CAFE_GPU_OK;
+    }
+    *score_out = -std::numeric_limits<double>::infinity();  // log(0), lambda.cpp:753-760
+    if (first_zero_family) *first_zero_family = (int32_t)ctx->h_score[1];
+    return CAFE_GPU_ZERO_LIKELIHOOD;
+}
+
+int cafe_gpu_score(cafe_gpu_ctx* ctx, double* score_out, int32_t* first_zero_family) {
+    CAFE_NEED_LEADER(ctx);
+    if (!score_out) return CAFE_GPU_ERR_ARG;
+    int rc = score_all_device(ctx);
+    if (rc) return rc;
+    return read_score(ctx, score_out, first_zero_family);
+}
+int cafe_gpu_objective(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node, double* score_out,
+                       int32_t* first_zero_family) {
+    int rc = cafe_gpu_set_rates(ctx, lambda_per_node, mu_per_node);
+    if (rc) return rc;
+    rc = cafe_gpu_build_matrices(ctx);
+    if (rc) return rc;
+    return cafe_gpu_score(ctx, score_out, first_zero_family);
+}
+int cafe_gpu_score_device(cafe_gpu_ctx* ctx, double* out_device) {
+    CAFE_NEED_LEADER(ctx);
+    if (!out_device) return CAFE_GPU_ERR_ARG;
+    int rc = score_all_device(ctx);
+    if (rc) return rc;
+    CAFE_CK(ctx, cudaMemcpyAsync(out_device, ctx->comm_world > 1 ? ctx->d_score_final : ctx->d_score, 2 * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+    return CAFE_GPU_OK;
+}
+int cafe_gpu_objective_device(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node, double* out_device) {
+    int rc = cafe_gpu_set_rates(ctx, lambda_per_node, mu_per_node);
+    if (rc) return rc;
+    rc = cafe_gpu_build_matrices(ctx);
+    if (rc) return rc;
+    return cafe_gpu_score_device(ctx, out_device);
+}
+
+// per-family outputs: every local context fills its slice of the leader's family order
+int cafe_gpu_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, double* max_likelihood, int32_t* argmax_likelihood) {
+    CAFE_NEED_LEADER(ctx);
+    return each_local(ctx, [&](cafe_gpu_ctx* c) {
+        const size_t o = ctx->peers.empty() ? 0 : (size_t)c->fam_lo;
+        return one_family_results(c, log_max_posterior ? log_max_posterior + o : nullptr, max_likelihood ? max_likelihood + o : nullptr,
+                                  argmax_likelihood ? argmax_likelihood + o : nullptr);
+    });
+}
+int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out) {
+    CAFE_NEED_LEADER(ctx);
+    if (!L_out) return CAFE_GPU_ERR_ARG;
+    return each_local_parallel(ctx, [&](cafe_gpu_ctx* c) {
+        const size_t o = ctx->peers.empty() ? 0 : (size_t)c->fam_lo;
+        return one_family_likelihoods(c, L_out + o * c->R);
+    });
+}
+int cafe_gpu_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_likelihood_out) {
+    CAFE_NEED_LEADER(ctx);
+    if (!node_sizes_out) return CAFE_GPU_ERR_ARG;
+    return each_local_parallel(ctx, [&](cafe_gpu_ctx* c) {
+        const size_t o = ctx->peers.empty() ? 0 : (size_t)c->fam_lo;
+        return one_viterbi(c, node_sizes_out + o * c->n_nodes, max_likelihood_out ? max_likelihood_out + o : nullptr);
+    });
+}
+int cafe_gpu_viterbi_report(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* branch_pvalues_out) {
+    CAFE_NEED_LEADER(ctx);
+    if (!node_sizes_out) return CAFE_GPU_ERR_ARG;
+    return each_local_parallel(ctx, [&](cafe_gpu_ctx* c) {
+        const size_t o = ctx->peers.empty() ? 0 : (size_t)c->fam_lo;
+        return one_viterbi_report(c, node_sizes_out + o * c->n_nodes, branch_pvalues_out ? branch_pvalues_out + o * c->n_nodes : nullptr);
+    });
+}
+int cafe_gpu_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* max_pvalue_out) {
+    CAFE_NEED_LEADER(ctx);
+    if (!max_pvalue_out) return CAFE_GPU_ERR_ARG;
+    return each_local_parallel(ctx, [&](cafe_gpu_ctx* c) {
+        const size_t o = ctx->peers.empty() ? 0 : (size_t)c->fam_lo;
+        return one_pvalues(c, cd, cd_rows, n_samples, max_pvalue_out + o);
+    });
+}
+
+// The branch-stretch test shards by families like the score.  Only the table's first tested family starts from the parsed
+// branch lengths (cafe/cafe_main.c:350,390), so the slices after the one that holds it mark their families 2.
+int cafe_gpu_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, const double* lengthened_mu_per_node,
+                                   double* base_max_likelihood_out, double* best_max_likelihood_out, int32_t* steps_out) {
+    CAFE_NEED_LEADER(ctx);
+    if (!best_max_likelihood_out) return CAFE_GPU_ERR_ARG;
+    if (ctx->peers.empty()) {
+        cudaSetDevice(ctx->device);
+        return one_likelihood_ratio_test(ctx, tested, lengthened_mu_per_node, base_max_likelihood_out, best_max_likelihood_out, steps_out);
+    }
+    std::vector<cafe_gpu_ctx*> L = locals_of(ctx);
+    int F_all = 0;
+    for (cafe_gpu_ctx* c : L) F_all += c->F;
+    int first_tested = -1;
+    for (int f = 0; f < F_all && first_tested < 0; ++f)
+        if (!tested || tested[f] == 1) first_tested = f;
+    const int n_nodes = ctx->n_nodes;
+    std::vector<std::vector<uint8_t>> t_loc(L.size());
+    std::vector<std::vector<double>> best_loc(L.size());
+    std::vector<std::vector<int32_t>> steps_loc(L.size());
+    for (size_t i = 0; i < L.size(); ++i) {
+        cafe_gpu_ctx* c = L[i];
+        t_loc[i].resize(c->F);
+        for (int f = 0; f < c->F; ++f) {
+            uint8_t t = tested ? tested[c->fam_lo + f] : 1;
+            if (t == 1 && first_tested >= 0 && c->fam_lo > first_tested) t = 2;
+            t_loc[i][f] = t;
+        }
+        best_loc[i].resize((size_t)n_nodes * c->F);
+        steps_loc[i].resize((size_t)n_nodes * c->F);
+    }
+    int rc = CAFE_GPU_OK;
+    {
+        std::vector<int> rcs(L.size(), 0);
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < L.size(); ++i)
+            th.emplace_back([&, i] {
+                cudaSetDevice(L[i]->device);
+                rcs[i] = one_likelihood_ratio_test(L[i], t_loc[i].data(), lengthened_mu_per_node,
+                                                   base_max_likelihood_out ? base_max_likelihood_out + L[i]->fam_lo : nullptr,
+                                                   best_loc[i].data(), steps_loc[i].data());
+            });
+        for (auto& t : th) t.join();
+        cudaSetDevice(ctx->device);
+        for (size_t i = 0; i < L.size(); ++i)
+            if (rcs[i] < 0 && rc == 0) { rc = rcs[i]; if (L[i] != ctx) ctx->err = L[i]->err; }
+    }
+    if (rc) return rc;
+    for (size_t i = 0; i < L.size(); ++i)
+        for (int b = 0; b < n_nodes; ++b)
+            for (int f = 0; f < L[i]->F; ++f) {
+                best_max_likelihood_out[(size_t)b * F_all + L[i]->fam_lo + f] = best_loc[i][(size_t)b * L[i]->F + f];
+                if (steps_out) steps_out[(size_t)b * F_all + L[i]->fam_lo + f] = steps_loc[i][(size_t)b * L[i]->F + f];
+            }
+    return CAFE_GPU_OK;
+}
+
+// The rows (root sizes) of the conditional distribution are independent: a multi-device context splits them over its
+// devices — the distributed form of the reference's pthreads over root sizes (cafe/conditional_distribution.cpp:86-120).
+int cafe_gpu_conditional_distribution_rows(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
+                                           double* cd_out) {
+    CAFE_NEED_LEADER(ctx);
+    if (!cd_out || n_samples < 1) return CAFE_GPU_ERR_ARG;
+    if (ctx->peers.empty()) {
+        cudaSetDevice(ctx->device);
+        return one_conditional_distribution_rows(ctx, n_samples, uniforms, seed, row_lo, row_hi, cd_out);
+    }
+    const int w = (int)ctx->peers.size() + 1;
+    std::vector<std::pair<int, int>> span(w);
+    for (int i = 0; i < w; ++i) { int lo, hi; shard_bounds(row_hi - row_lo, w, i, lo, hi); span[i] = {row_lo + lo, row_lo + hi}; }
+    std::vector<cafe_gpu_ctx*> L = locals_of(ctx);
+    std::vector<int> rcs(w, 0);
+    std::vector<std::thread> th;
+    for (int i = 0; i < w; ++i)
+        th.emplace_back([&, i] {
+            cudaSetDevice(L[i]->device);
+            rcs[i] = one_conditional_distribution_rows(L[i], n_samples, uniforms, seed, span[i].first, span[i].second,
+                                                       cd_out + (size_t)(span[i].first - row_lo) * n_samples);
+        });
+    for (auto& t : th) t.join();
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < w; ++i)
+        if (rcs[i] < 0) { if (L[i] != ctx) ctx->err = L[i]->err; return rcs[i]; }
+    return CAFE_GPU_OK;
+}
+int cafe_gpu_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, double* cd_out) {
+    if (!ctx) return CAFE_GPU_ERR_ARG;
+    return cafe_gpu_conditional_distribution_rows(ctx, n_samples, uniforms, seed, 0, ctx->R, cd_out);
 }
 
 }  // extern "C"

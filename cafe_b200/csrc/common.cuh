@@ -94,6 +94,7 @@ struct cafe_gpu_ctx {
     // families
     int F = 0, F_pad = 0;
     int* d_counts = nullptr;  // [n_leaves][F_pad]  (leaf-major: coalesced over families)
+    size_t counts_cap = 0;    // ints allocated for d_counts
     int* d_mult = nullptr;    // [F_pad]
     int* d_first = nullptr;   // [F_pad]
     std::vector<int> h_counts;  // [F][n_leaves] as given
@@ -141,19 +142,35 @@ struct cafe_gpu_ctx {
 
     void* fused_state = nullptr;   // prune_fused.cu private state (device schedule, scratch)
     void* fused2_state = nullptr;  // prune_fused2.cu private state
+    void* fused3_state = nullptr;  // prune_fused3.cu private state
+
+    // multi-GPU (comm.cu): a context is one rank of an NCCL communicator.  Either one process per GPU (cafe_gpu_comm_init:
+    // world ranks in world processes) or one process with several devices (cafe_gpu_create_multi: the leader context owns
+    // the contexts of the other devices in `peers`, every public call on the leader fans out).
+    void* nccl_comm = nullptr;            // ncclComm_t
+    int comm_rank = 0, comm_world = 1;
+    std::vector<cafe_gpu_ctx*> peers;     // leader only: the other local contexts, in rank order (ranks 1..n-1)
+    cafe_gpu_ctx* leader = nullptr;       // peers only
+    double* d_score_all = nullptr;        // [comm_world][2] gathered partial scores
+    double* d_score_final = nullptr;      // [2]
+    int fam_lo = 0;                       // in-process multi: first unique pattern of the leader's list held by this context
 
     // bookkeeping
     int64_t launches = 0;
     bool timing = false;
-    // ring of CUDA-event quads {K1 begin, K1 end, K2 begin, K2 end}, one quad per objective evaluation
+    // ring of CUDA-event octets, one per objective evaluation (see the EV_* indices below)
     static constexpr int kRing = 256;
-    std::vector<cudaEvent_t> ring;   // 4 * kRing events, created on enable_timing
+    static constexpr int kEv = 8;
+    std::vector<cudaEvent_t> ring;   // kEv * kRing events, created on enable_timing
     int ring_k1 = 0, ring_k2 = 0;    // evaluations recorded since the last collect
-    cudaEvent_t* quad(int i) { return &ring[4 * (i % kRing)]; }
+    int ring_x = 0, ring_r = 0;      // exchanges / reductions recorded (multi-GPU only)
+    cudaEvent_t evt(int i, int which) { return ring[kEv * (i % kRing) + which]; }
 };
+enum { EV_K1_BEGIN = 0, EV_K1_END, EV_K2_BEGIN, EV_K2_END, EV_XCHG_BEGIN, EV_XCHG_END, EV_RED_BEGIN, EV_RED_END };
 
 // kernels (defined in the .cu files of this directory); all launch on ctx->stream
-int launch_bd_matrices(cafe_gpu_ctx* ctx);                              // bd_matrix.cu   (K1)
+int launch_bd_matrices(cafe_gpu_ctx* ctx);                              // bd_matrix.cu   (K1: M and MT of the keys [key_lo, key_hi))
+int launch_transpose_keys(cafe_gpu_ctx* ctx, int lo, int hi, int lo2, int hi2);  // bd_matrix.cu (MT of the keys [lo,hi) and [lo2,hi2))
 int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out /*nullable*/);  // prune.cu       (K2)
 int launch_score_reduce(cafe_gpu_ctx* ctx, double* d_out2);             // reduce.cu      (K3)
 int build_schedule(cafe_gpu_ctx* ctx);                                  // prune.cu (host)
@@ -166,6 +183,9 @@ void fused_release(cafe_gpu_ctx* ctx);
 bool fused2_supported(const cafe_gpu_ctx* ctx);                         // prune_fused2.cu
 int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out);        // prune_fused2.cu (K2, one CTA per SM, default)
 void fused2_release(cafe_gpu_ctx* ctx);
+bool fused3_supported(const cafe_gpu_ctx* ctx);                         // prune_fused3.cu
+int launch_prune_fused3(cafe_gpu_ctx* ctx, double* d_Lroot_out);        // prune_fused3.cu (K2, one CTA per SM, de-phased groups, default)
+void fused3_release(cafe_gpu_ctx* ctx);
 int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
                                  double* cd_out);                       // conddist.cu    (K4)
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out);  // pvalue.cu (K5)
@@ -173,6 +193,10 @@ int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const doubl
                            int32_t* steps_out);                     // lrt.cu
 int build_one_matrix(cafe_gpu_ctx* ctx, int key);                       // api.cu (K1 for one key)
 int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool forced, double* branch_pv_out);  // viterbi.cu
+// comm.cu: NCCL plumbing (libnccl is loaded lazily with dlopen, a context without a communicator never touches it)
+int comm_exchange_matrices(std::vector<cafe_gpu_ctx*>& locals);   // in-place all-gather of d_M over the ranks + local transposes
+int comm_reduce_scores(std::vector<cafe_gpu_ctx*>& locals);      // all-gather of {partial score, first zero} + ordered final sum
+void comm_release(cafe_gpu_ctx* ctx);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -29,8 +29,11 @@ ABI_SYMBOLS = [
     "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_timing_collect", "cafe_gpu_score_flops",
     "cafe_gpu_score_device", "cafe_gpu_set_key_shard", "cafe_gpu_matrix_storage", "cafe_gpu_matrices_exchanged",
     "cafe_gpu_viterbi", "cafe_gpu_viterbi_report", "cafe_gpu_conditional_distribution_rows",
-    "cafe_gpu_likelihood_ratio_test",
+    "cafe_gpu_likelihood_ratio_test", "cafe_gpu_timing_collect4", "cafe_gpu_comm_unique_id", "cafe_gpu_comm_init",
+    "cafe_gpu_comm_size", "cafe_gpu_comm_rank", "cafe_gpu_create_multi", "cafe_gpu_num_devices",
 ]
+
+COMM_ID_BYTES = 128
 
 
 class CafeGpuError(RuntimeError):
@@ -79,6 +82,13 @@ def load_library():
     L.cafe_gpu_reset_launch_count.argtypes = [vp]
     L.cafe_gpu_enable_timing.argtypes = [vp, C.c_int]
     L.cafe_gpu_timing_collect.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
+    L.cafe_gpu_timing_collect4.argtypes = [vp] + [C.POINTER(C.c_float)] * 4 + [C.c_int]
+    L.cafe_gpu_comm_unique_id.argtypes = [vp, C.c_int]
+    L.cafe_gpu_comm_init.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int]
+    L.cafe_gpu_comm_size.argtypes = [vp]
+    L.cafe_gpu_comm_rank.argtypes = [vp]
+    L.cafe_gpu_create_multi.argtypes = [C.POINTER(vp), _ip, C.c_int]
+    L.cafe_gpu_num_devices.argtypes = [vp]
     L.cafe_gpu_score_flops.restype = C.c_double
     L.cafe_gpu_score_flops.argtypes = [vp]
     return L
@@ -92,13 +102,28 @@ def _i(a):
     return a.ctypes.data_as(_ip)
 
 
-class CafeGpu:
-    """One C-ABI context (one device, one stream)."""
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C-ABI: call on one rank, hand the bytes to every rank (cafe_gpu_comm_init)."""
+    L = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = L.cafe_gpu_comm_unique_id(buf, COMM_ID_BYTES)
+    if rc != 0:
+        raise CafeGpuError(f"cafe_gpu_comm_unique_id failed ({rc})")
+    return buf.raw
 
-    def __init__(self, device: int = -1):
+
+class CafeGpu:
+    """One C-ABI context: one device and one stream, or (devices=[...]) the leader of one context per device in this
+    process (cafe_gpu_create_multi), which shards the families and runs the NCCL exchange steps inside the library."""
+
+    def __init__(self, device: int = -1, devices=None):
         self.L = load_library()
         h = C.c_void_p()
-        rc = self.L.cafe_gpu_create(C.byref(h), device)
+        if devices is not None:
+            dv = np.ascontiguousarray(devices, dtype=np.int32)
+            rc = self.L.cafe_gpu_create_multi(C.byref(h), _i(dv), len(dv))
+        else:
+            rc = self.L.cafe_gpu_create(C.byref(h), device)
         if rc != 0:
             raise CafeGpuError(f"cafe_gpu_create failed ({rc}): {self.L.cafe_gpu_last_error(None).decode()}")
         self.h = h
@@ -126,6 +151,15 @@ class CafeGpu:
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.L.cafe_gpu_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """Make this context rank `rank` of an NCCL communicator of `world` contexts (one process per GPU).  From then on
+        build_matrices shards K1 over the ranks and score/objective return the all-reduced result on every rank."""
+        buf = C.create_string_buffer(unique_id, COMM_ID_BYTES)
+        self._ck(self.L.cafe_gpu_comm_init(self.h, buf, COMM_ID_BYTES, rank, world), "comm_init")
+
+    def num_devices(self):
+        return self.L.cafe_gpu_num_devices(self.h)
 
     def synchronize(self):
         self._ck(self.L.cafe_gpu_synchronize(self.h), "synchronize")
@@ -303,6 +337,13 @@ class CafeGpu:
         fp = C.POINTER(C.c_float)
         n = self._ck(self.L.cafe_gpu_timing_collect(self.h, k1.ctypes.data_as(fp), k2.ctypes.data_as(fp), cap), "timing_collect")
         return k1[:n].copy(), k2[:n].copy()
+
+    def timing_collect4(self, cap=256):
+        """(K1, matrix exchange, K2, score reduction) device times in ms per evaluation."""
+        a = [np.zeros(cap, dtype=np.float32) for _ in range(4)]
+        fp = C.POINTER(C.c_float)
+        n = self._ck(self.L.cafe_gpu_timing_collect4(self.h, *[x.ctypes.data_as(fp) for x in a], cap), "timing_collect4")
+        return tuple(x[:n].copy() for x in a)
 
     def score_flops(self):
         return float(self.L.cafe_gpu_score_flops(self.h))

@@ -128,7 +128,14 @@ void sync_error_models(pCafeFamily f, pCafeTree t) {
     for (int k = 0; k < t->num_leaves(); ++k) {
         int e = t->nlist[2 * k].errormodel;
         sig << e;
-        if (e >= 0 && f) sig << ":" << f->errors[e].errorfilename << ":" << f->errors[e].maxfamilysize;
+        if (e >= 0 && f) {
+            // file name, size and an FNV-1a hash of the matrix bits: a model edited in place is uploaded again
+            const ErrorStruct& em = f->errors[e];
+            uint64_t h = 1469598103934665603ULL;
+            const unsigned char* b = reinterpret_cast<const unsigned char*>(em.errormatrix.data());
+            for (size_t i = 0; i < em.errormatrix.size() * sizeof(double); ++i) { h ^= b[i]; h *= 1099511628211ULL; }
+            sig << ":" << em.errorfilename << ":" << em.maxfamilysize << ":" << h;
+        }
         sig << ";";
     }
     if (sig.str() == g_eng.err_signature) return;
@@ -160,9 +167,35 @@ void push_rates(pCafeTree t) {
 
 }  // namespace
 
+// Devices of the engine: the environment variable CAFE_GPUS is a count ("8" = devices 0..7) or a comma-separated list of
+// CUDA device indices ("0,2,5"); unset = the current device.  More than one device makes the engine a multi-device context
+// (cafe_gpu_create_multi): the family table is split over the devices and every objective evaluation of the lambda search
+// runs K1 / all-gather / K2 / score reduction on all of them (include/cafe_gpu.h, "Multi-GPU").
+static std::vector<int> engine_devices() {
+    std::vector<int> dev;
+    const char* e = std::getenv("CAFE_GPUS");
+    if (!e || !*e) return dev;
+    const std::string s(e);
+    if (s.find(',') == std::string::npos) {
+        const int n = std::atoi(s.c_str());
+        for (int i = 0; i < n; ++i) dev.push_back(i);
+        return dev;
+    }
+    size_t pos = 0;
+    while (pos < s.size()) {
+        size_t c = s.find(',', pos);
+        if (c == std::string::npos) c = s.size();
+        if (c > pos) dev.push_back(std::atoi(s.substr(pos, c - pos).c_str()));
+        pos = c + 1;
+    }
+    return dev;
+}
+
 cafe_gpu_ctx* cafe_gpu_engine() {
     if (!g_eng.ctx) {
-        int rc = cafe_gpu_create(&g_eng.ctx, -1);
+        const std::vector<int> dev = engine_devices();
+        int rc = dev.size() > 1 ? cafe_gpu_create_multi(&g_eng.ctx, dev.data(), (int)dev.size())
+                                : cafe_gpu_create(&g_eng.ctx, dev.empty() ? -1 : dev[0]);
         if (rc != 0) throw std::runtime_error(std::string("cafe_gpu_create failed: ") + cafe_gpu_last_error(nullptr));
     }
     return g_eng.ctx;

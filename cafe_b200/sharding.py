@@ -2,9 +2,11 @@
 
 Families are independent given the transition matrices (get_posterior has no cross-family state
 except the running sum and the first-zero exception, cafe/lambda.cpp:698-722), so every rank holds
-all D matrices and a contiguous slice of the unique patterns.  The only exchange step of one
-objective evaluation is the reduction of {partial score, first zero-likelihood family index}:
-ONE collective on a 2-double device buffer (sum of the first, min of the second).
+all D matrices and a contiguous slice of the unique patterns.  The exchange steps of one objective evaluation
+(all-gather of the K1-sharded matrices, reduction of {partial score, first zero-likelihood family index}) run inside
+libcafe_gpu.so over NCCL (csrc/comm.cu; attach_comm below hands over the communicator id).  The torch.distributed helpers
+here cover what sits around it: slicing the table, the host-side form of the reduction (gloo, for CPU tests), and the
+row/family gathers of the conditional distribution and the likelihood-ratio test.
 """
 from __future__ import annotations
 
@@ -61,22 +63,20 @@ def gather_chunks(full, rank: int, world_size: int, group=None):
     return full
 
 
-def objective_sharded(g, lam_node, mu_node, out2, rank: int, world_size: int, device, group=None):
-    """One objective evaluation with BOTH kernels sharded: every rank builds ceil(D/world) of the D distinct transition
-    matrices (K1), two in-place NCCL all-gathers over NVLink (M and its transposed copy) give every rank all of them, then
-    K2+K3 run on this rank's families and the 2-double reduction follows (reduce_score).  The matrices of BASELINE configs[1]
-    are 20 x 0.5 MB x 2, those of configs[2] 98 x 2 MB x 2.  g must have had set_key_shard(rank, world_size)."""
-    import torch
+def attach_comm(g, rank: int, world_size: int, group=None):
+    """Give context `g` an NCCL communicator INSIDE the C-ABI library (cafe_gpu_comm_init): rank 0 draws the unique id
+    (cafe_gpu_comm_unique_id), torch.distributed — any backend — only carries its 128 bytes to the other ranks.  From then on
+    g.objective / g.score / g.objective_device shard K1 over the ranks, all-gather the matrices, reduce the score and return the
+    same result on every rank; every collective runs on the context's own stream, ordered with its kernels."""
+    import torch.distributed as dist
 
-    g.set_rates(lam_node, mu_node)
-    g.build_matrices()
-    pm, pt, dpk, kpr = g.matrix_storage()
-    n = dpk * kpr * world_size
-    for ptr in (pm, pt):
-        gather_chunks(torch.as_tensor(_DeviceBuffer(ptr, n), device=device), rank, world_size, group)
-    g.matrices_exchanged()
-    g.score_device(out2.data_ptr())
-    return reduce_score(out2, group)
+    from . import gpu as cgpu
+
+    if world_size == 1:
+        return
+    box = [cgpu.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    g.comm_init(box[0], rank, world_size)
 
 
 def gather_rows(local_rows, n_rows: int, rank: int, world_size: int, group=None):

@@ -57,7 +57,7 @@ enum cafe_gpu_status {
 };
 
 /* ABI version of this header (bumped on incompatible change). */
-#define CAFE_GPU_ABI_VERSION 1
+#define CAFE_GPU_ABI_VERSION 2
 int cafe_gpu_abi_version(void);
 
 /* device < 0 selects the current CUDA device.  Fails (no CPU fallback) when there is none. */
@@ -120,22 +120,45 @@ int cafe_gpu_score(cafe_gpu_ctx* ctx, double* score_out, int32_t* first_zero_fam
 /* cafe_gpu_set_rates + cafe_gpu_build_matrices + cafe_gpu_score: one objective evaluation. */
 int cafe_gpu_objective(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node,
                        double* score_out, int32_t* first_zero_family);
-/* Same, asynchronous and device-resident: out_device[0] = partial score of this context's families,
- * out_device[1] = (double) smallest first_index with zero likelihood, or +inf.  No host
- * synchronisation; meant to be followed by one all-reduce (sum, min) across ranks. */
+/* Same, asynchronous and device-resident: out_device[0] = score (of this context's families; of all ranks' families when a
+ * communicator is attached), out_device[1] = (double) smallest first_index with zero likelihood, or +inf.  No host
+ * synchronisation. */
 int cafe_gpu_objective_device(cafe_gpu_ctx* ctx, const double* lambda_per_node, const double* mu_per_node,
                               double* out_device /* device pointer, 2 doubles */);
 
 /* Device-resident score of the current matrices (K2+K3 only): out_device as for cafe_gpu_objective_device. */
 int cafe_gpu_score_device(cafe_gpu_ctx* ctx, double* out_device /* device pointer, 2 doubles */);
 
-/* K1 sharded across ranks (one context per GPU, every rank with the same tree and rates).  After cafe_gpu_set_key_shard
- * (rank, world), cafe_gpu_build_matrices builds only this rank's contiguous chunk of keys_per_rank = ceil(D / world) distinct
- * keys; the caller then all-gathers the chunks IN PLACE over the two device buffers returned by cafe_gpu_matrix_storage
- * (chunk r = doubles [r * keys_per_rank * doubles_per_key, +keys_per_rank * doubles_per_key) of d_M and of d_MT, e.g. one
- * ncclAllGather each) and calls cafe_gpu_matrices_exchanged; scoring before that fails with CAFE_GPU_ERR_STATE.  The
- * reference builds all matrices in one `omp for` (libtree/birthdeath.c:331-343) — this is its distributed equivalent.
- * world == 1 restores the unsharded behaviour. */
+/* ---- Multi-GPU.  Families shard naturally: get_posterior has no cross-family state except the running sum and
+ * the first zero family (cafe/lambda.cpp:698-722).  With a communicator attached, one objective evaluation is: K1 on this
+ * rank's ceil(D / world) distinct keys -> ncclAllGather of the matrices in place (+ a local transpose of the received ones) ->
+ * K2 + K3 on this rank's families -> ncclAllGather of {partial score, first zero family} and a sum in rank order, all on the
+ * context's stream, so cafe_gpu_score / cafe_gpu_objective(_device) return the same all-reduced result on every rank.  This is
+ * the drop-in for the body of __cafe_best_lambda_search (cafe/lambda.cpp:726-769) on 1..8 GPUs.
+ *
+ * (a) one process per GPU (torchrun, mpirun): rank 0 calls cafe_gpu_comm_unique_id, the launcher hands the id_bytes (>= 128)
+ *     bytes to every rank, every rank calls cafe_gpu_comm_init on its context and passes ITS slice of the families to
+ *     cafe_gpu_set_families (first_index = indices into the whole table).
+ * (b) one process, several devices: cafe_gpu_create_multi returns a leader context that owns one context per device
+ *     (ncclCommInitAll).  Every call in this header made on the leader fans out: setters go to all devices,
+ *     cafe_gpu_set_families splits the table into contiguous balanced slices in device order, per-family outputs come back
+ *     in table order, the rows of the conditional distribution are split over the devices.  devices == NULL means 0..n-1.
+ * libnccl.so.2 is loaded on first use (dlopen); contexts without a communicator never touch it. */
+int cafe_gpu_comm_unique_id(void* id_out, int id_bytes);
+int cafe_gpu_comm_init(cafe_gpu_ctx* ctx, const void* id, int id_bytes, int rank, int world);
+int cafe_gpu_comm_size(const cafe_gpu_ctx* ctx);
+int cafe_gpu_comm_rank(const cafe_gpu_ctx* ctx);
+int cafe_gpu_create_multi(cafe_gpu_ctx** out, const int* devices, int n_devices);
+int cafe_gpu_num_devices(const cafe_gpu_ctx* ctx);
+
+/* K1 sharded across ranks with a collective of the CALLER's (when the library's own NCCL path above is not wanted).  After
+ * cafe_gpu_set_key_shard(rank, world), cafe_gpu_build_matrices builds only this rank's contiguous chunk of keys_per_rank =
+ * ceil(D / world) distinct keys; the caller all-gathers the chunks IN PLACE over the device buffer d_M returned by
+ * cafe_gpu_matrix_storage (chunk r = doubles [r * keys_per_rank * doubles_per_key, +keys_per_rank * doubles_per_key)) ON THE
+ * CONTEXT'S STREAM (cafe_gpu_set_stream) — or orders its own stream after the build and before the next call with events —
+ * and calls cafe_gpu_matrices_exchanged, which transposes the received matrices into d_MT locally; scoring before that fails
+ * with CAFE_GPU_ERR_STATE.  The reference builds all matrices in one `omp for` (libtree/birthdeath.c:331-343) — this is its
+ * distributed equivalent.  world == 1 restores the unsharded behaviour. */
 int cafe_gpu_set_key_shard(cafe_gpu_ctx* ctx, int rank, int world);
 int cafe_gpu_matrix_storage(cafe_gpu_ctx* ctx, void** d_M, void** d_MT, int64_t* doubles_per_key, int32_t* keys_per_rank);
 int cafe_gpu_matrices_exchanged(cafe_gpu_ctx* ctx);
@@ -216,6 +239,9 @@ int64_t cafe_gpu_launch_count(const cafe_gpu_ctx* ctx);
 void cafe_gpu_reset_launch_count(cafe_gpu_ctx* ctx);
 int cafe_gpu_enable_timing(cafe_gpu_ctx* ctx, int on);
 int cafe_gpu_timing_collect(cafe_gpu_ctx* ctx, float* k1_ms, float* k2_ms, int cap);
+/* The same with the two exchange steps of a multi-GPU evaluation (zeros without a communicator): K1 (incl. the local
+ * transposes), all-gather of the matrices, K2, reduction of the score.  Any pointer may be NULL. */
+int cafe_gpu_timing_collect4(cafe_gpu_ctx* ctx, float* k1_ms, float* exchange_ms, float* k2_ms, float* reduce_ms, int cap);
 /* Algorithmic fp64 flops of one cafe_gpu_score over the current families:
  * sum over internal edges of 2*W*W (2*R*W at the root), leaf edges excluded. */
 double cafe_gpu_score_flops(const cafe_gpu_ctx* ctx);

@@ -88,8 +88,10 @@ def lib():
 
 
 @lru_cache(maxsize=None)
-def ref():
-    path = os.path.join(HERE, "_ref", "libcafe_ref.so")
+def ref(openmp: bool = False):
+    """The compiled, unmodified reference (oracle/_ref, built by oracle/Makefile) or None.  openmp=True: the build with
+    -fopenmp, as the reference's own Makefile.in:13 compiles it (bench.py's reference arm)."""
+    path = os.path.join(HERE, "_ref", "libcafe_ref_omp.so" if openmp else "libcafe_ref.so")
     if not os.path.exists(path):
         return None
     R = C.CDLL(path)

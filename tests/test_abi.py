@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     L = cgpu.load_library()
     for s in header_symbols():
         assert hasattr(L, s), s
-    assert L.cafe_gpu_abi_version() == 1
+    assert L.cafe_gpu_abi_version() == 2
 
 
 def test_signatures_are_plain_c():

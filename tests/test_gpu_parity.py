@@ -416,7 +416,8 @@ def test_k2_config4_full_size_properties():
 
 
 def test_k1_key_shard_two_contexts_match_unsharded():
-    # cafe_gpu_set_key_shard: two contexts stand in for two ranks; the "all-gather" is two device copies through torch
+    # cafe_gpu_set_key_shard with a collective of the caller's: two contexts stand in for two ranks, the "all-gather" of d_M
+    # is two device copies through torch; cafe_gpu_matrices_exchanged transposes the received matrices into d_MT locally
     import torch
     from cafe_b200 import sharding
     counts = small_counts(5, 64, 22, 31)
@@ -438,12 +439,12 @@ def test_k1_key_shard_two_contexts_match_unsharded():
     for g in ctxs:
         pm, pt, dpk, kpr = g.matrix_storage()
         assert kpr == (D + 1) // 2
-        views.append([torch.as_tensor(sharding._DeviceBuffer(ptr, dpk * kpr * 2), device="cuda") for ptr in (pm, pt)])
+        g.synchronize()
+        views.append(torch.as_tensor(sharding._DeviceBuffer(pm, dpk * kpr * 2), device="cuda"))
     torch.cuda.synchronize()
-    chunk = views[0][0].numel() // 2
-    for which in range(2):
-        views[1][which][:chunk].copy_(views[0][which][:chunk])      # rank 0's chunk -> rank 1
-        views[0][which][chunk:].copy_(views[1][which][chunk:])      # rank 1's chunk -> rank 0
+    chunk = views[0].numel() // 2
+    views[1][:chunk].copy_(views[0][:chunk])      # rank 0's chunk -> rank 1
+    views[0][chunk:].copy_(views[1][chunk:])      # rank 1's chunk -> rank 0
     torch.cuda.synchronize()
     for g in ctxs:
         g.matrices_exchanged()

@@ -68,13 +68,21 @@ class Problem:
                             leaf_err=self.oracle_leaf_err(), want_L=want_L)
 
     # ---- C-ABI side ----
-    def make_gpu(self):
-        g = cgpu.CafeGpu()
+    def make_gpu(self, devices=None, comm=None, lo=None, hi=None):
+        """devices=[...]: a multi-device leader context (cafe_gpu_create_multi); comm=(id, rank, world) + [lo, hi): one rank of
+        a communicator holding that slice of the families."""
+        g = cgpu.CafeGpu(devices=devices) if devices is not None else cgpu.CafeGpu(-1 if comm is None else comm[1])
+        if comm is not None:
+            g.comm_init(*comm)
         t = self.tree
         g.set_tree(t.left, t.right, t.branchlength)
         g.set_ranges(*self.ranges)
         g.set_lnc_table(chost.lnc_table(self.maxfs))
-        g.set_families(self.counts, self.mult, self.first)
+        if lo is None:
+            g.set_families(self.counts, self.mult, self.first)
+        else:
+            first = np.arange(len(self.counts), dtype=np.int32) if self.first is None else self.first
+            g.set_families(self.counts[lo:hi], None if self.mult is None else self.mult[lo:hi], first[lo:hi])
         g.set_prior(self.prior)
         if self.err:
             for leaf, M in self.err.items():
