@@ -141,14 +141,13 @@ class ReferenceCpu:
             a = [C.c_int() for _ in range(4)]
             oracle.lib().orc_init_family_size(self.cfg["max_size"], *[C.byref(x) for x in a])  # root_min, root_max, min, max
             self.ranges = (a[2].value, a[3].value, a[0].value, a[1].value)
-            self.prior = oracle.prior_poisson(self.ranges[2], 8.0, 1000)
+            self.prior = bench_data.root_prior(self.cfg["max_size"], self.ranges[2], 1000)
             self.cores = 1
             return
         rg = (C.c_int * 4)()
         self.R.refshim_init_family_size(self.cfg["max_size"], rg)  # init_family_size, cafe_family.c:357-364
         self.ranges = (rg[2], rg[3], rg[0], rg[1])                 # min, max, root_min, root_max
-        self.prior = np.zeros(1000)
-        self.R.refshim_prior_poisson(self.ranges[2], 8.0, self.prior.ctypes.data_as(C.POINTER(C.c_double)))
+        self.prior = bench_data.root_prior(self.cfg["max_size"], self.ranges[2], 1000)  # the tables' own root distribution
 
     def threads(self, n):
         if self.gomp is not None:
@@ -266,7 +265,7 @@ class GpuProblem:
         rg = chost.init_family_size(self.cfg["max_size"])
         self.ranges = (rg["min"], rg["max"], rg["root_min"], rg["root_max"])
         self.R = self.ranges[3] - self.ranges[2] + 1
-        self.prior = chost.prior_poisson(self.ranges[2], 8.0, 1000)[: self.R]
+        self.prior = bench_data.root_prior(self.cfg["max_size"], self.ranges[2], self.R)  # the tables' own root distribution
         self.n = tree.n_nodes
         g = cgpu.CafeGpu(device)
         g.set_stream(stream_ptr)

@@ -110,9 +110,9 @@ def simulate_table(newick: str, n_families: int, max_size: int, lam0: float | No
             break
         B = max(4096, int(n_families * 0.4))
         # root sizes: mostly small families plus a flat tail that reaches max_size
-        small = 1 + rng.poisson(8.0, size=B)
+        small = 1 + rng.poisson(SMALL_MEAN, size=B)
         tail = rng.randint(1, max_size + 1, size=B)
-        root = np.where(rng.random_sample(B) < 0.85, small, tail)
+        root = np.where(rng.random_sample(B) < SMALL_FRACTION, small, tail)
         sizes = np.zeros((B, len(tr.kids)), dtype=np.int64)
         sizes[:, tr.root] = root
         for v in order:
@@ -149,6 +149,21 @@ def simulate_table(newick: str, n_families: int, max_size: int, lam0: float | No
     counts = np.concatenate(kept, axis=0)[:n_families].astype(np.int32)
     assert counts.max() == max_size and len(counts) == n_families
     return counts, lam0
+
+
+SMALL_FRACTION, SMALL_MEAN = 0.85, 8.0  # root sizes: 85 % 1 + Poisson(8), 15 % uniform on 1..max_size
+
+
+def root_prior(max_size: int, root_min: int, n: int) -> np.ndarray:
+    """The root-size distribution the tables are drawn from, prior[i] for root size root_min + i — what the reference's
+    `rootdist` / cafe_set_prior_rfsize_empirical stand for.  (A pure Poisson prior underflows to 0 long before size 400:
+    every large family would then score log 0.)"""
+    from scipy.special import gammaln
+    sz = root_min + np.arange(n, dtype=np.float64)
+    k = sz - 1.0
+    pois = np.where(k >= 0, np.exp(k * np.log(SMALL_MEAN) - SMALL_MEAN - gammaln(np.maximum(k, 0) + 1.0)), 0.0)
+    flat = np.where((sz >= 1) & (sz <= max_size), 1.0 / max_size, 0.0)
+    return SMALL_FRACTION * pois + (1.0 - SMALL_FRACTION) * flat
 
 
 def dedup(counts: np.ndarray):

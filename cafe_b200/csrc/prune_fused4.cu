@@ -1,0 +1,997 @@
+// prune_fused4.cu — K2, fourth generation of the fused persistent pruning kernel (the default path).
+//
+// Replaces, per objective evaluation, the reference's F x (2n-2) calls of square_matrix_multiply
+// (libtree/birthdeath.c:163-182) under compute_internal_node_likelihood (cafe/cafe_tree.c:226-271),
+// initialize_leaf_likelihoods (:191-211) and compute_posterior's root reduction (cafe/lambda.cpp:657-689).
+//
+// ONE CTA per SM, 12 warps:
+//
+//   warps 4..11  DMMA consumers, 2 M-groups x 4 N-warps (warp tile 48 families x 32 sizes), CTA tile 96 families x 128
+//                sizes; exactly two DMMA warps per SM sub-partition, one of each group.  Both groups consume one shared
+//                ring (the matrix tile B is fetched once per CTA).  The epilogue of a pass happens in REGISTERS: every lane
+//                loads the sibling factors of its own accumulator elements from global memory (a stored partial product,
+//                or the gathered row of a leaf sibling), multiplies, and stores the products to the node-vector slot.
+//                There is no C tile in shared memory, so the whole 227 KB carry the ring (7 stages of one K block), and
+//                group 1 runs `lag` ring stages behind group 0: the global-memory latency of one group's epilogue is
+//                covered by the other group's K loop instead of idling the fp64 pipe (prune_fused2.cu: shared-memory
+//                epilogue of both groups at the same time, 2-stage ring).
+//   warp 0       TMA producer (one lane): child vectors (A, 96 x 16 sizes) and matrix K-blocks (B, 128 rows x 16 sizes).
+//   warps 1..2   leaf-pair gatherers: a node whose two children are leaves has the vector M_a[.][c_a] * M_b[.][c_b]
+//                (cafe_tree.c:204-210); written one pair of tiles ahead into scratch slots of their own.
+//   warp 3       idle (exits after the prologue).
+//
+// Bit-for-bit the same arithmetic as prune_fused2.cu / prune_fused.cu / prune.cu (same DMMA order over K, one rounding
+// per product).
+#include <cuda.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <functional>
+
+#include "common.cuh"
+
+namespace fused4 {
+
+constexpr int GM = 2;                  // M-groups (consumer warpgroups): exactly two DMMA warps per SM sub-partition
+constexpr int HM = 48;                 // families per group
+constexpr int TILE_M = GM * HM;        // 96 families per CTA tile
+constexpr int TN = 128;                // output sizes per pass
+constexpr int BK = 16;                 // sizes per K block (16 doubles = 128 B = one swizzle row)
+constexpr int NSTAGE = 7;                // ring stages, each KB_PER_STAGE K blocks
+constexpr int KB_PER_STAGE = 1;
+constexpr int A_BYTES = TILE_M * 128;  // 12 KB
+constexpr int B_BYTES = TN * 128;      // 16 KB
+constexpr int SUB_BYTES = A_BYTES + B_BYTES;        // one K block: A | B
+constexpr int STAGE_BYTES = KB_PER_STAGE * SUB_BYTES;
+constexpr int N_CONSUMER_WARPS = 4 * GM;
+constexpr int THREADS = (N_CONSUMER_WARPS + 4) * 32;
+constexpr int MB = HM / 8, NB = 4, WCOLS = NB * 8;
+constexpr int N_GATHER_WARPS = 2;
+// The helper warps are warps 0..3 and the DMMA warps 4..11: the sub-partition arbiter prefers the highest warp id, so the
+// rarely-ready helpers never take an issue slot from a DMMA warp that is ready.
+constexpr int N_AUX_WARPS = 4;
+// register re-partition of the 384 x 168 launch allocation: 8*32*192 + 4*32*120 = 64512
+constexpr int REGS_CONSUMER = 192, REGS_AUX = 120;
+
+struct Op {              // one GEMM of the post-order schedule (a tree edge below an internal node)
+    int is_root;
+    int key;             // matrix of the GEMM child's branch
+    int a_kind;          // 0: child vector in slot in_slot, 1: child is a leaf pair (a1, a2), its vector in leaf-pair slot in_slot
+    int in_slot, out_slot;
+    int leaf_a1, key_a1, leaf_a2, key_a2;
+    int other_kind;      // 0 none, 1 leaf sibling, 2 multiply into out_slot
+    int leaf_o, key_o;
+};
+
+struct Params {
+    const Op* ops;
+    int n_ops, n_slots, n_cherry;   // per CTA and tile: n_slots node-vector slots; per CTA, pair parity and tile: n_cherry leaf-pair slots
+    int F, F_pad;
+    int W, R, root_min;
+    int Sp, Vp;
+    int n_mblocks;               // ceil(F / 8)
+    double* scratch;             // [grid][cta_rows][Vp]
+    const double* MT;            // [D][Sp][Sp] transposed matrices
+    const int* counts;           // [n_leaves][F_pad]
+    const double* logprior;      // [R]
+    const double* prior_mant;    // [R] prior = mant * 2^exp, mant in [1,2)  (host frexp; exp = -2^30 where the prior is 0)
+    const int* prior_exp;        // [R]
+    double* logpost;             // [F_pad]
+    double* maxlik;
+    int* argmax;
+    double* Lroot_out;           // nullable, [F][R]
+    int lag;                     // ring stages group 1 keeps behind group 0 at the start of every pass (0: lockstep)
+    int dbg;                     // debug ablations (CAFE_GPU_DBG, results are garbage): 1 no epilogue work, 2 no epilogue at all, 4 no store, 8 no ring (K loops on whatever is in shared memory)
+    long long* cta_times;        // nullable debug: [grid][4] = smid, start ns, end ns, 8-family blocks
+    long long* warp_prof;        // nullable debug: CTA 0, [16 warps][8] cycle sums (see consumer_main / producer_main)
+    long long* timeline;         // nullable debug: CTA 0, warps 0 and 4 (one sub-partition): [2][1024 items][4] clock stamps
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// Same for the helper warps, which are never latency critical: a long suspend-time hint keeps them asleep in hardware instead
+// of re-polling every few dozen cycles next to the DMMA warps of their SM sub-partition.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy accesses <-> async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16-byte / 8-byte asynchronous copies with zero fill of the bytes beyond src_bytes
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival once all cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int OPFLAGS_CAP = 1024;
+struct Ctl {
+    uint64_t full[NSTAGE];       // producer expect_tx
+    uint64_t empty[NSTAGE];      // 8 consumer warps
+    volatile unsigned prog[4];   // ring stages released so far by group 0's warp nw (group 1 keeps `lag` stages behind)
+    volatile int done[2];        // per tile of the pair: passes-of-warps finished (stored, fenced): 8 per finished op
+    volatile int cherry_count;   // leaf-pair vectors: 2 (gatherer warps) per finished vector, in (pair, op, tile) order
+    unsigned char opflags[OPFLAGS_CAP];  // per op: bit0 is_root, bit1 a_kind, bits 2-3 other_kind (what the consumers need)
+    double red_ml[GM][4][HM];    // root reduction across the 4 N-warps of a group
+    double red_mp[GM][4][HM];
+    int red_am[GM][4][HM];
+};
+__device__ __forceinline__ void group_bar(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+// This CTA's families: a contiguous range of 8-family blocks cut into an even number of tiles of <= 12 blocks;
+// tiles are processed two at a time (the op sequence of one interleaved with the other's) so that a vector is never
+// streamed right after it was stored.  Inside a tile, group g owns mbv(g) consecutive blocks.
+struct TilePlan {
+    int mb_lo, n_mb, n_tiles, n_pairs;
+    __device__ TilePlan(const Params& P) {
+        const int G = gridDim.x, c = blockIdx.x;
+        mb_lo = (int)((long long)P.n_mblocks * c / G);
+        n_mb = (int)((long long)P.n_mblocks * (c + 1) / G) - mb_lo;
+        n_tiles = (n_mb + TILE_M / 8 - 1) / (TILE_M / 8);
+        if (n_mb >= 2 && (n_tiles & 1)) ++n_tiles;
+        n_pairs = (n_tiles + 1) / 2;
+    }
+    // Tile sizes are even wherever possible (both groups of a tile then hold the same number of blocks and finish every ring
+    // stage together): all tiles get the even base size e, the first ones 2 more, and one tile the odd block if n_mb is odd.
+    __device__ bool tile(int t, int& mb0, int& m) const {
+        if (t >= n_tiles) return false;
+        const int e = (n_mb / n_tiles) & ~1;
+        const int r = n_mb - e * n_tiles;   // < 2 * n_tiles
+        const int n2 = r >> 1;              // tiles with e + 2 blocks
+        auto size = [&](int i) { return e + (i < n2 ? 2 : 0) + ((r & 1) && i == n2 ? 1 : 0); };
+        mb0 = mb_lo + e * t + 2 * min(t, n2) + ((r & 1) && t > n2 ? 1 : 0);
+        m = size(t);
+        return true;
+    }
+    __device__ static int mbv(int m, int g) { return (m + GM - 1 - g) / GM; }
+    __device__ static int pre(int m, int g) { return g == 0 ? 0 : mbv(m, 0); }
+    // family of tile row r (clamped into [0, F) so that gathers of unused rows stay in bounds)
+    // family of tile row r, or -1 for a row without a family
+    __device__ static int family_or_neg(int mb0, int m, int r, int F) {
+        const int g = r / HM, lr = r - g * HM;
+        const int f = (mb0 + pre(m, g)) * 8 + lr;
+        return (lr < mbv(m, g) * 8 && f < F) ? f : -1;
+    }
+    __device__ static int family(int mb0, int m, int r, int F) {
+        const int g = r / HM, lr = r - g * HM;
+        const int f = (mb0 + pre(m, g)) * 8 + lr;
+        return (lr < mbv(m, g) * 8 && f < F) ? f : (F - 1);
+    }
+};
+
+// Scratch rows of one CTA: [2 tiles][n_slots] node vectors, then [2 pair parities][2 tiles][n_cherry] leaf-pair vectors, 96 rows each.
+__device__ __forceinline__ int cta_rows(const Params& P) { return (2 * P.n_slots + 4 * P.n_cherry) * TILE_M; }
+__device__ __forceinline__ int cherry_row(const Params& P, int pair, int h, int c) {
+    return (2 * P.n_slots + ((pair & 1) * 2 + h) * P.n_cherry + c) * TILE_M;
+}
+
+__device__ __forceinline__ void advance(uint32_t& stage, uint32_t& phase) {
+    if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+}
+
+// ================================ TMA producer (one lane) ================================ ================================
+template <bool PROF>
+__device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUtensorMap* tmB, const Params& P,
+                                              unsigned char* stage_base, Ctl* ctl) {
+    const TilePlan plan(P);
+    const int scratch_row0 = blockIdx.x * cta_rows(P);
+    const int n_kblocks = (P.W + BK - 1) / BK;
+    if (P.dbg & 8) return;
+    uint32_t stage = 0, phase = 0;
+    int ops_done_base = 0;
+    const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
+    long long t_wait_done = 0, t_wait_empty = 0;
+    const long long t_begin = prof ? clock64() : 0;
+    int cherry_units = 0;  // leaf-pair vectors needed so far, in the gatherers' order (pair, op, tile)
+    for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        for (int oi = 0; oi < P.n_ops; ++oi) {
+            const Op op = P.ops[oi];
+            const int r0 = op.is_root ? P.root_min : 0;
+            const int nrows = op.is_root ? P.R : P.W;
+            const int n_chunks = (nrows + TN - 1) / TN;
+            for (int h = 0; h < 2; ++h) {
+                if (2 * pair + h >= plan.n_tiles) continue;
+                if (op.a_kind == 0) {
+                    // the vector to stream was stored by an earlier op of this tile: wait until it is visible
+                    const long long t0 = prof ? clock64() : 0;
+                    while (ctl->done[h] < N_CONSUMER_WARPS * (ops_done_base + oi)) { __nanosleep(20); }
+                    __threadfence_block();
+                    fence_proxy_async();
+                    if (prof) t_wait_done += clock64() - t0;
+                } else {
+                    // a leaf-pair vector: written by the two gatherers, normally a whole pair of tiles ahead
+                    ++cherry_units;
+                    while (ctl->cherry_count < 2 * cherry_units) { __nanosleep(20); }
+                    __threadfence_block();
+                    fence_proxy_async();
+                }
+                const int a_row = scratch_row0 + (op.a_kind == 0 ? (h * P.n_slots + op.in_slot) * TILE_M : cherry_row(P, pair, h, op.in_slot));
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    for (int kb = 0; kb < n_kblocks; kb += KB_PER_STAGE) {
+                        const long long t0 = prof ? clock64() : 0;
+                        mbar_wait_sleepy(&ctl->empty[stage], phase ^ 1);
+                        if (prof) t_wait_empty += clock64() - t0;
+                        const int nsub = min(KB_PER_STAGE, n_kblocks - kb);
+                        mbar_arrive_expect_tx(&ctl->full[stage], nsub * SUB_BYTES);
+                        for (int j = 0; j < nsub; ++j) {
+                            unsigned char* sA = stage_base + stage * STAGE_BYTES + j * SUB_BYTES;
+                            tma_load_2d(sA, tmA, (kb + j) * BK, a_row, &ctl->full[stage]);
+                            tma_load_3d(sA + A_BYTES, tmB, (kb + j) * BK, r0 + ch * TN, op.key, &ctl->full[stage]);
+                        }
+                        advance(stage, phase);
+                    }
+                }
+            }
+        }
+        ops_done_base += P.n_ops;
+    }
+    if (prof) {
+        long long* o = P.warp_prof + N_CONSUMER_WARPS * 8;
+        o[0] = clock64() - t_begin; o[1] = t_wait_done; o[2] = t_wait_empty;
+    }
+}
+
+// ================================ leaf-pair gatherers (2 warps) ================================
+// A node whose two children are leaves has the vector L[j] = M_a[j][count_a] * M_b[j][count_b] (cafe_tree.c:204-210 twice, then
+// the product of :266-270): two gathered rows of the transposed matrices.  The gatherers write these vectors for the NEXT pair
+// of tiles into dedicated scratch slots while the DMMA warps work on the current pair - a whole pair of tiles (milliseconds)
+// of slack, no coupling to the ring, one product per element.  The parent's GEMM then streams the slot like any other vector.
+// Gatherer gi owns the tile rows [48 gi, 48 gi + 48); a warp handles two rows at a time, lanes along the sizes.
+__device__ __forceinline__ void gatherer_main(const Params& P, double* scratch, Ctl* ctl, int gi) {
+    const TilePlan plan(P);
+    const int lane = threadIdx.x & 31;
+    if (P.n_cherry == 0 || (P.dbg & 8)) return;
+    double* cta_scratch = scratch + (size_t)blockIdx.x * cta_rows(P) * P.Vp;
+    const int n_pieces = (P.W + 1) / 2;  // 16-byte pieces of a vector that hold a size < W
+    for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        // slot set (pair & 1) was last read by pair - 2: wait until pair - 1 has completed an op (then pair - 2 is over)
+        if (pair >= 2) {
+            const int need = (pair - 1) * P.n_ops + 1;
+            while (ctl->done[0] < N_CONSUMER_WARPS * need) { __nanosleep(500); }
+            __threadfence_block();
+        }
+        for (int oi = 0; oi < P.n_ops; ++oi) {
+            const Op op = P.ops[oi];
+            if (op.a_kind != 1) continue;
+            const double* __restrict__ MTa = P.MT + (size_t)op.key_a1 * P.Sp * P.Sp;
+            const double* __restrict__ MTb = P.MT + (size_t)op.key_a2 * P.Sp * P.Sp;
+            for (int h = 0; h < 2; ++h) {
+                int mb0, m;
+                if (!plan.tile(2 * pair + h, mb0, m)) continue;
+                double* out = cta_scratch + (size_t)cherry_row(P, pair, h, op.in_slot) * P.Vp;
+                for (int r0 = (TILE_M / 2) * gi; r0 < (TILE_M / 2) * (gi + 1); r0 += 2) {
+                    const double2* pa[2]; const double2* pb[2]; double2* po[2]; bool ok[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int f = TilePlan::family_or_neg(mb0, m, r0 + u, P.F);
+                        ok[u] = f >= 0;
+                        const int fc = ok[u] ? f : 0;
+                        pa[u] = reinterpret_cast<const double2*>(MTa + (size_t)__ldg(P.counts + (size_t)op.leaf_a1 * P.F_pad + fc) * P.Sp);
+                        pb[u] = reinterpret_cast<const double2*>(MTb + (size_t)__ldg(P.counts + (size_t)op.leaf_a2 * P.F_pad + fc) * P.Sp);
+                        po[u] = reinterpret_cast<double2*>(out + (size_t)(r0 + u) * P.Vp);
+                    }
+                    for (int p0 = 0; p0 < n_pieces; p0 += 128) {  // 4 pieces per lane and row in flight
+                        double2 x[2][4], y[2][4];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int pc = p0 + k * 32 + lane;
+                                x[u][k] = make_double2(0.0, 0.0); y[u][k] = x[u][k];
+                                if (ok[u] && pc < n_pieces) { x[u][k] = __ldg(pa[u] + pc); y[u][k] = __ldg(pb[u] + pc); }
+                            }
+#pragma unroll
+                        for (int u = 0; u < 2; ++u)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int pc = p0 + k * 32 + lane;
+                                if (ok[u] && pc < n_pieces) {
+                                    // sizes >= W stay exact zeros: the vector has length W although the matrices are wider when S > W
+                                    const double hi = (2 * pc + 1 < P.W) ? __dmul_rn(x[u][k].y, y[u][k].y) : 0.0;
+                                    po[u][pc] = make_double2(__dmul_rn(x[u][k].x, y[u][k].x), hi);
+                                }
+                            }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();  // the vector is read by the producer's TMA loads
+                    atomicAdd(const_cast<int*>(&ctl->cherry_count), 1);
+                }
+            }
+        }
+    }
+}
+
+// ================================ warps 0..7: DMMA consumers ================================
+// Fragments of one k4-step: 4 B fragments and one A fragment per 8-family block.
+template <int MBV>
+__device__ __forceinline__ void load_frags(double (&fa)[MB], double (&fb)[NB], const unsigned char* sA, const unsigned char* sB, int off) {
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) fb[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + off);
+#pragma unroll
+    for (int mb = 0; mb < MBV; ++mb) {
+        fa[mb] = *reinterpret_cast<const double*>(sA + mb * 1024 + off);
+    }
+}
+template <int MBV>
+__device__ __forceinline__ void mma_frags(double (&acc)[MB][NB][2], const double (&fa)[MB], const double (&fb)[NB]) {
+#pragma unroll
+    for (int mb = 0; mb < MBV; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], fa[mb], fb[nb]);
+}
+
+// non-blocking probe of an mbarrier phase: issued a few k4-steps before the result is needed
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok;
+}
+
+// STEPS k4-steps (one or two full K blocks of a ring stage).  The fragments of the next step are fetched before the DMMAs of the
+// current one; after the last step (do_next) the first fragments of whatever follows - the next K block of the stage, or the
+// next stage after its mbarrier wait (~100 cycles even when already full) - so that neither sits between two DMMAs.
+template <int MBV, int STEPS>
+__device__ __forceinline__ void steps_full(double (&acc)[MB][NB][2], double (&fa)[2][MB], double (&fb)[2][NB], const unsigned char* sa,
+                                           const unsigned char* sb, const int (&koff)[4], bool do_next, const unsigned char* next_a,
+                                           const unsigned char* next_b, uint64_t* wait_bar, uint32_t wait_phase,
+                                           bool prof, long long& t_wait_full) {
+    uint32_t ready = 0;
+#pragma unroll
+    for (int kk = 0; kk < STEPS; ++kk) {
+        // probe the next stage's barrier two steps early: its ~100-cycle latency then never sits between two DMMAs
+        if (STEPS >= 4 && kk == STEPS - 3 && do_next && wait_bar) ready = mbar_test(wait_bar, wait_phase);
+        if (kk + 1 < STEPS) {
+            const int j = (kk + 1) >> 2;
+            load_frags<MBV>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sa + j * SUB_BYTES, sb + j * SUB_BYTES, koff[(kk + 1) & 3]);
+        } else if (do_next) {
+            if (wait_bar && !ready) {
+                const long long t0 = prof ? clock64() : 0;
+                mbar_wait(wait_bar, wait_phase);
+                if (prof) t_wait_full += clock64() - t0;
+            }
+            load_frags<MBV>(fa[0], fb[0], next_a, next_b, koff[0]);
+        }
+        mma_frags<MBV>(acc, fa[kk & 1], fb[kk & 1]);
+    }
+}
+
+// K loop of one pass: n_kblocks K blocks of 16 sizes (the last one with tail_steps k4-steps), one per ring stage.
+// MBV == 0: this warp has no work in the tile, it only keeps the ring moving.
+// `released` counts the ring stages this warp has released since the kernel started; group 0 publishes it (Ctl::prog).
+template <int MBV>
+__device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned char* stage_base, Ctl* ctl, uint32_t& stage,
+                                             uint32_t& phase, uint32_t& released, int n_kblocks, int tail_steps, int grp, int nw, int lane,
+                                             int pg, int q, bool prof, long long& t_wait_full, bool nosync) {
+    static_assert(KB_PER_STAGE == 1, "the stage loop below is written for one K block per stage");
+    if (MBV == 0) {
+        for (int st = 0; st < n_kblocks; ++st) {
+            if (!nosync) mbar_wait(&ctl->full[stage], phase);
+            __syncwarp();
+            ++released;
+            if (lane == 0 && !nosync) { mbar_arrive(&ctl->empty[stage]); if (grp == 0) ctl->prog[nw] = released; }
+            advance(stage, phase);
+        }
+        return;
+    }
+    const int off0 = pg * 128 + ((q & 1) << 3), hi = q >> 1;
+    int koff[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) koff[kk] = off0 + (((2 * kk + hi) ^ pg) << 4);
+    const int a_off = grp * (HM * 128), b_off = A_BYTES + nw * WCOLS * 128;
+    const int n_full = (tail_steps == 4) ? n_kblocks : n_kblocks - 1;  // K blocks with all four steps
+
+    double fa[2][MB], fb[2][NB];
+    if (!nosync) {
+        const long long t0 = prof ? clock64() : 0;
+        mbar_wait(&ctl->full[stage], phase);
+        if (prof) t_wait_full += clock64() - t0;
+    }
+    const unsigned char* sbase = stage_base + stage * STAGE_BYTES;
+    load_frags<MBV>(fa[0], fb[0], sbase + a_off, sbase + b_off, koff[0]);
+    for (int st = 0; st < n_kblocks; ++st) {
+        uint32_t nstage = stage, nphase = phase;
+        advance(nstage, nphase);
+        const unsigned char* nbase = stage_base + nstage * STAGE_BYTES;
+        const unsigned char* sa = sbase + a_off;
+        const unsigned char* sb = sbase + b_off;
+        const bool has_next = st + 1 < n_kblocks;
+        uint64_t* nbar = nosync ? nullptr : &ctl->full[nstage];
+        if (st < n_full) {
+            // a full K block; the first fragments of the next stage (if any) are fetched before its last DMMAs
+            steps_full<MBV, 4>(acc, fa, fb, sa, sb, koff, has_next, nbase + a_off, nbase + b_off, nbar, nphase, prof, t_wait_full);
+        } else {
+            // the partial K block that ends the pass (its first fragments are in fa[0] / fb[0])
+            for (int kk = 0; kk < tail_steps; ++kk) {
+                if (kk > 0) load_frags<MBV>(fa[0], fb[0], sa, sb, off0 + (((2 * kk + hi) ^ pg) << 4));
+                mma_frags<MBV>(acc, fa[0], fb[0]);
+            }
+        }
+        __syncwarp();
+        ++released;
+        if (lane == 0 && !nosync) { mbar_arrive(&ctl->empty[stage]); if (grp == 0) ctl->prog[nw] = released; }
+        stage = nstage; phase = nphase; sbase = nbase;
+    }
+}
+
+template <bool PROF>
+__device__ __forceinline__ void consumer_main(const Params& P, unsigned char* stage_base, Ctl* ctl) {
+    const TilePlan plan(P);
+    const int warp = (threadIdx.x >> 5) - N_AUX_WARPS, lane = threadIdx.x & 31;  // consumer warp 0..7
+    const int grp = warp >> 2, nw = warp & 3;
+    const int g = lane >> 2, q = lane & 3;
+    const int pg = mma_row_perm(g);
+    const int pc0 = mma_row_perm(2 * q), pc1 = mma_row_perm(2 * q + 1);
+    const int n_kblocks = (P.W + BK - 1) / BK;
+    const int tail_steps = ((P.W - (n_kblocks - 1) * BK) + 3) >> 2;  // k4-steps of the last K block (1..4)
+
+    // scratch rows of this CTA; a lane's accumulator elements of 8-family block mb are row mb * 8 + pg of its group's 48 rows,
+    // sizes n0 + nb * 8 + {pc0, pc1} (the MMA's n index is the permuted matrix row, see mma_row_perm)
+    const size_t scratch_row0 = (size_t)blockIdx.x * cta_rows(P);
+    // debug profile (CTA 0): cycles waiting for ring stages / in K loops / waiting for the C tile / in epilogues
+    const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
+    long long t_wait_full = 0, t_kloop = 0, t_wait_c = 0, t_epi = 0, t_epi_root = 0, t_kloop_cherry = 0;
+    const long long t_begin = prof ? clock64() : 0;
+
+    uint32_t stage = 0, phase = 0, item = 0, released = 0;
+    for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        // the two tiles of the pair: this group's 8-family blocks (everything else about a tile concerns the helper warps)
+        int mbv_h[2], f0_h[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int mb0 = 0, m = 0;
+            mbv_h[h] = plan.tile(2 * pair + h, mb0, m) ? TilePlan::mbv(m, grp) : -1;
+            f0_h[h] = (mb0 + TilePlan::pre(m, grp)) * 8;
+        }
+        for (int oi = 0; oi < P.n_ops; ++oi) {
+            const int flags = ctl->opflags[oi];
+            const bool is_root = flags & 1;
+            const int other_kind = (flags >> 2) & 3;
+            const int nrows = is_root ? P.R : P.W;
+            const int n_chunks = (nrows + TN - 1) / TN;
+            const bool reduce_now = is_root && other_kind != 0;
+            // what the epilogue needs of the op (uniform loads, consumed only after the K loop)
+            const int op_out_slot = __ldg(&P.ops[oi].out_slot), op_leaf_o = __ldg(&P.ops[oi].leaf_o), op_key_o = __ldg(&P.ops[oi].key_o);
+            const int r0 = is_root ? P.root_min : 0;
+            const double* __restrict__ MTo = P.MT + (size_t)op_key_o * P.Sp * P.Sp + r0;
+            for (int h = 0; h < 2; ++h) {
+                const int mbv_t = h ? mbv_h[1] : mbv_h[0], f0_t = h ? f0_h[1] : f0_h[0];
+                if (mbv_t < 0) continue;
+                // leaf sibling (cafe_tree.c:204-210): the factor of family row (mb, pg) is row `count` of the transposed matrix
+                int rowoff[MB];
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) {
+                    rowoff[mb] = 0;
+                    if (other_kind == 1 && mb < mbv_t)
+                        rowoff[mb] = __ldg(P.counts + (size_t)op_leaf_o * P.F_pad + min(f0_t + mb * 8 + pg, P.F - 1)) * P.Sp;
+                }
+                double* const out_base = P.scratch + (scratch_row0 + (size_t)(h * P.n_slots + op_out_slot) * TILE_M + grp * HM + pg) * P.Vp;
+                // running root reduction of one family row of this group, owned by the group's first HM threads
+                double run_ml = -1.0, run_mp = -INFINITY; int run_am = 0x7fffffff;
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    const int n0 = ch * TN + nw * WCOLS;  // first output size of this warp
+                    const int mbw = (n0 < nrows) ? mbv_t : 0;
+                    double acc[MB][NB][2];
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
+
+                    const long long tk0 = prof ? clock64() : 0;
+                    // Group 1 starts a pass only when group 0 has released `lag` stages of it: the groups then reach their
+                    // epilogues one after the other, and the one in its K loop has the fp64 pipe to itself meanwhile.
+                    if (grp == 1 && P.lag > 0 && !(P.dbg & 8)) {
+                        const uint32_t need = released + (uint32_t)min(P.lag, n_kblocks);
+                        if (lane == 0) { while ((int)(ctl->prog[nw] - need) < 0) { } }
+                        __syncwarp();
+                    }
+#define CAFE_K(MBV_) gemm_kblocks<MBV_>(acc, stage_base, ctl, stage, phase, released, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full, (P.dbg & 8) != 0);
+                    switch (mbw) {
+                        case 6: CAFE_K(6) break;
+                        case 5: CAFE_K(5) break;
+                        case 4: CAFE_K(4) break;
+                        case 3: CAFE_K(3) break;
+                        case 2: CAFE_K(2) break;
+                        case 1: CAFE_K(1) break;
+                        default: CAFE_K(0) break;
+                    }
+#undef CAFE_K
+                    const long long tk1 = prof ? clock64() : 0;
+
+                    // ---------------- epilogue of this pass, in registers: out = acc * sibling factor ----------------
+                    const long long tk2 = tk1;
+                    const int mbs = (n0 < P.Vp) ? mbv_t : 0;  // blocks this warp stores (zeros at sizes in [nrows, Vp), see below)
+                    // sibling factors of one 8-family block: a leaf sibling's gathered matrix row, or the partial product the
+                    // first internal child left in the output slot; loaded one block ahead of their use
+                    auto load_factors = [&](int mb, double (&fac)[NB][2]) {
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const int col = n0 + nb * 8 + (hh ? pc1 : pc0);
+                                fac[nb][hh] = 1.0;
+                                if (col < nrows) {
+                                    if (other_kind == 1) fac[nb][hh] = __ldg(MTo + rowoff[mb] + col);
+                                    else if (other_kind == 2) fac[nb][hh] = __ldcg(out_base + (size_t)mb * 8 * P.Vp + col);
+                                }
+                            }
+                    };
+                    double fac[2][NB][2];
+                    if (mbs > 0) load_factors(0, fac[0]);
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) {
+                        if (mb < mbs) {
+                            if (mb + 1 < mbs) load_factors(mb + 1, fac[(mb + 1) & 1]);
+                            double out[NB][2];
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    const int col = n0 + nb * 8 + (hh ? pc1 : pc0);
+                                    // sizes >= nrows are exact zeros: matrix rows in [W, S) are not zero when S > W, and a slot may
+                                    // still hold the (wider) root partial of the previous pair of tiles there
+                                    out[nb][hh] = (col < nrows) ? __dmul_rn(acc[mb][nb][hh], fac[mb & 1][nb][hh]) : 0.0;
+                                }
+                            if (!reduce_now) {
+#pragma unroll
+                                for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                                    for (int hh = 0; hh < 2; ++hh) {
+                                        const int col = n0 + nb * 8 + (hh ? pc1 : pc0);
+                                        if (col < P.Vp) out_base[(size_t)mb * 8 * P.Vp + col] = out[nb][hh];
+                                    }
+                            } else {
+                                // root: L[i] = acc * other; max / first argmax of L and max of log L + log prior (lambda.cpp:670-686).
+                                // log is monotonic, so among this lane's eight sizes of a family only the one with the largest product
+                                // L * prior can carry the maximum: the products are compared exactly as (exponent sum, mantissa product)
+                                // - no underflow - and ONE log is taken per lane and family instead of eight (two products closer than an
+                                // ulp could swap; their log sums then differ by ~1e-16).  Comparisons on bit patterns: non-negative doubles
+                                // order like integers, and DSETP would queue behind the DMMAs of the other group on the fp64 pipe.
+                                long long ml = -1, best_f = 0; double mp = -INFINITY, best_v = 0.0, best_lp = 0.0; int am = 0x7fffffff, best_e = -0x7fffffff;
+                                const int f = f0_t + mb * 8 + pg;
+#pragma unroll
+                                for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+                                    for (int hh = 0; hh < 2; ++hh) {
+                                        const int i = n0 + nb * 8 + (hh ? pc1 : pc0);
+                                        if (i < nrows) {
+                                            const double v = out[nb][hh];
+                                            if (P.Lroot_out && f < P.F) P.Lroot_out[(size_t)f * P.R + i] = v;  // get_likelihoods, cafe_tree.c:325-329
+                                            const long long vb = __double_as_longlong(v);
+                                            if (vb > ml || (vb == ml && i < am)) { ml = vb; am = i; }
+                                            if (vb > 0) {
+                                                double vs = v;
+                                                int hi32 = __double2hiint(vs), e = (hi32 >> 20) & 0x7ff;
+                                                if (e == 0) { vs = __dmul_rn(vs, 0x1p200); hi32 = __double2hiint(vs); e = ((hi32 >> 20) & 0x7ff) - 200; }
+                                                // mantissa product in [1,4): its own exponent bit joins the exponent sum, its fraction breaks ties
+                                                const long long pb = __double_as_longlong(__dmul_rn(__hiloint2double((hi32 & 0x000fffff) | 0x3ff00000, __double2loint(vs)), __ldg(P.prior_mant + i)));
+                                                e += __ldg(P.prior_exp + i) + (int)(pb >> 52);
+                                                const long long frac = pb & 0x000fffffffffffffLL;
+                                                if (e > best_e || (e == best_e && frac > best_f)) { best_e = e; best_f = frac; best_v = v; best_lp = __ldg(P.logprior + i); }
+                                            }
+                                        }
+                                    }
+                                }
+                                if (best_e != -0x7fffffff) mp = log(best_v) + best_lp;
+                                // the 4 lanes of a quad hold the same family row
+#pragma unroll
+                                for (int off = 1; off <= 2; off <<= 1) {
+                                    const long long oml = __shfl_xor_sync(0xffffffffu, ml, off); const int oam = __shfl_xor_sync(0xffffffffu, am, off);
+                                    const double omp = __shfl_xor_sync(0xffffffffu, mp, off);
+                                    if (oml > ml || (oml == ml && oam < am)) { ml = oml; am = oam; }
+                                    if (omp > mp) mp = omp;
+                                }
+                                const int row = mb * 8 + pg;
+                                if (q == 0) { ctl->red_ml[grp][nw][row] = __longlong_as_double(ml); ctl->red_mp[grp][nw][row] = mp; ctl->red_am[grp][nw][row] = am; }
+                            }
+                        } else if (reduce_now && mb < mbv_t) {
+                            // a warp whose sizes lie beyond the root range still fills its slots of the cross-warp reduction
+                            const int row = mb * 8 + pg;
+                            if (q == 0) { ctl->red_ml[grp][nw][row] = -1.0; ctl->red_mp[grp][nw][row] = -INFINITY; ctl->red_am[grp][nw][row] = 0x7fffffff; }
+                        }
+                    }
+                    const long long tk2b = prof ? clock64() : 0;
+                    __syncwarp();
+                    if (ch == n_chunks - 1 && lane == 0) {
+                        // this warp's part of the op's output is stored: the producer streams the slot (TMA) when all 8 warps are here
+                        __threadfence();
+                        atomicAdd(const_cast<int*>(&ctl->done[h]), 1);
+                    }
+                    ++item;
+                    if (prof && P.timeline && nw == 0 && lane == 0 && item <= 1024) {
+                        long long* tl = P.timeline + ((size_t)grp * 1024 + (item - 1)) * 4;
+                        tl[0] = tk0; tl[1] = tk1; tl[2] = tk2; tl[3] = tk2b;
+                    }
+                    if (prof) { t_kloop += tk1 - tk0; t_wait_c += tk2 - tk1; t_epi += tk2b - tk2; if (flags & 2) t_kloop_cherry += tk1 - tk0; if (reduce_now) t_epi_root += tk2b - tk2; }
+                    if (reduce_now) {
+                        group_bar(grp);
+                        if (nw * 32 + lane < HM) {  // the first HM threads of the group own one family row each
+                            const int row = nw * 32 + lane;
+                            for (int w = 0; w < 4; ++w) {
+                                const double oml = ctl->red_ml[grp][w][row], omp = ctl->red_mp[grp][w][row]; const int oam = ctl->red_am[grp][w][row];
+                                if (oml > run_ml || (oml == run_ml && oam < run_am)) { run_ml = oml; run_am = oam; }
+                                if (omp > run_mp) run_mp = omp;
+                            }
+                            const int f = f0_t + row;
+                            if (ch == n_chunks - 1 && row < mbv_t * 8 && f < P.F) {
+                                // max_j exp(log L + log prior) == exp(max_j(log L + log prior)); its log is the family's term
+                                P.logpost[f] = log(exp(run_mp)); P.maxlik[f] = run_ml; P.argmax[f] = run_am;
+                            }
+                        }
+                        group_bar(grp);
+                    }
+                }
+            }
+        }
+    }
+    if (prof && lane == 0) {
+        long long* o = P.warp_prof + warp * 8;
+        o[0] = clock64() - t_begin; o[1] = t_kloop; o[2] = t_wait_full; o[3] = t_wait_c; o[4] = t_epi; o[5] = t_epi_root; o[6] = 0; o[7] = t_kloop_cherry;
+    }
+}
+
+template <bool PROF>
+__global__ void __launch_bounds__(THREADS, 1)
+k_prune_fused4(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
+    extern __shared__ unsigned char smem_raw[];
+    // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* stage_base = smem;                       // NSTAGE x KB_PER_STAGE x (A | B)
+    Ctl* ctl = reinterpret_cast<Ctl*>(smem + NSTAGE * STAGE_BYTES);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&ctl->full[s], 1); mbar_init(&ctl->empty[s], N_CONSUMER_WARPS); }
+        ctl->done[0] = ctl->done[1] = 0; ctl->cherry_count = 0;
+        for (int w = 0; w < 4; ++w) ctl->prog[w] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < P.n_ops; i += THREADS) {
+        const Op o = P.ops[i];
+        ctl->opflags[i] = (unsigned char)((o.is_root ? 1 : 0) | (o.a_kind << 1) | (o.other_kind << 2));
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5;
+    if (warp < N_AUX_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+        if (warp == 0) { if ((threadIdx.x & 31) == 0) producer_main<PROF>(&tmA, &tmB, P, stage_base, ctl); }
+        else if (warp < 1 + N_GATHER_WARPS) gatherer_main(P, P.scratch, ctl, warp - 1);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
+        long long t_start = 0;
+        if (P.cta_times && threadIdx.x == N_AUX_WARPS * 32) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+        consumer_main<PROF>(P, stage_base, ctl);
+        if (P.cta_times && threadIdx.x == N_AUX_WARPS * 32) {
+            long long t_end; unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const TilePlan plan(P);
+            long long* o = P.cta_times + (size_t)blockIdx.x * 4;
+            o[0] = smid; o[1] = t_start; o[2] = t_end; o[3] = plan.n_mb;
+        }
+    }
+}
+
+// Error-model leaves (cafe_tree.c:196-203): the leaf vector is row `observed` of the error matrix, so the leaf's factor is
+// factor[i] = sum_j M[i][j] * E[observed][j] (birthdeath.c:172-180).  Built once per evaluation as ONE more transposed matrix
+// per such leaf, MTE[observed][i] - same terms, same ascending-j order, one rounding per product and per sum, true sizes above
+// colmax skipped as the matvec's column window does - the fused kernel then gathers a row of it exactly like a row of MT.
+__global__ void __launch_bounds__(256)
+k_err_leaf_matrix(const double* __restrict__ MTsrc, const int* __restrict__ rowptr, const int* __restrict__ col,
+                  const double* __restrict__ val, int dim, int Sp, int colmax, double* __restrict__ out) {
+    const int i = blockIdx.x * 256 + threadIdx.x, o = blockIdx.y;
+    if (i >= Sp) return;
+    double s = 0.0;
+    if (o < dim) {
+        for (int k = rowptr[o]; k < rowptr[o + 1]; ++k) {
+            const int j = col[k];
+            if (j <= colmax) s = __dadd_rn(s, __dmul_rn(MTsrc[(size_t)j * Sp + i], val[k]));
+        }
+    }
+    out[(size_t)o * Sp + i] = s;
+}
+
+}  // namespace fused4
+
+// =================================================================================================
+// host side
+// =================================================================================================
+typedef CUresult (*PFN_encodeTiled4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled4 get_encode_fn4() {
+    static PFN_encodeTiled4 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled4)p;
+    }
+    return fn;
+}
+
+struct Fused4State {
+    fused4::Op* d_ops = nullptr; int ops_cap = 0;
+    double* d_scratch = nullptr; size_t scratch_cap = 0;
+    bool attr_set = false;
+    std::vector<fused4::Op> ops;  // schedule of the current launch
+    int n_slots = 0, n_cherry = 0;
+};
+static Fused4State& fstate4(cafe_gpu_ctx* ctx) {
+    if (!ctx->fused4_state) ctx->fused4_state = new Fused4State();
+    return *static_cast<Fused4State*>(ctx->fused4_state);
+}
+void fused4_release(cafe_gpu_ctx* ctx) {
+    if (!ctx->fused4_state) return;
+    Fused4State* s = static_cast<Fused4State*>(ctx->fused4_state);
+    cudaFree(s->d_ops); cudaFree(s->d_scratch);
+    delete s;
+    ctx->fused4_state = nullptr;
+}
+
+bool fused4_supported(const cafe_gpu_ctx* ctx) {
+    if (get_encode_fn4() == nullptr) return false;
+    if (ctx->n_leaves < 3) return false;                 // the root of a two-leaf tree is itself a leaf pair
+    if (ctx->n_nodes > fused4::OPFLAGS_CAP) return false;
+    if (ctx->max_count >= ctx->W) return false;          // a one-hot leaf outside the matvec columns needs the guarded path
+    return true;
+}
+
+// Post-order schedule of the GEMMs.  A node whose two children are leaves ("cherry") never gets a vector slot; the needier
+// internal child is evaluated first (Sethi–Ullman), its slot is released as soon as its parent's GEMM is issued.
+static void build_schedule4(const cafe_gpu_ctx* ctx, Fused4State& st) {
+    using fused4::Op;
+    const int n = ctx->n_nodes;
+    // matrix index of a leaf's factor rows: its branch's key, or its own error-model matrix behind the keys (launch_prune_fused4)
+    auto leaf_key = [&](int leaf_node) {
+        const int k = leaf_node / 2;
+        const bool err = !ctx->leaf_err.empty() && ctx->leaf_err[k] >= 0;
+        return err ? (int)ctx->mat_cap + k : ctx->node_key[leaf_node];
+    };
+    auto is_leaf = [&](int v) { return ctx->left[v] < 0; };
+    auto is_cherry = [&](int v) { return !is_leaf(v) && is_leaf(ctx->left[v]) && is_leaf(ctx->right[v]); };
+    auto is_virtual = [&](int v) { return is_leaf(v) || is_cherry(v); };
+    std::vector<int> need(n, 0);
+    std::function<int(int)> calc = [&](int v) -> int {
+        if (is_virtual(v)) return need[v] = 0;
+        int a = calc(ctx->left[v]), b = calc(ctx->right[v]);
+        int hi = std::max(a, b), lo = std::min(a, b);
+        int k = std::max(hi, lo + (hi > 0 ? 1 : 0));
+        int live_children = (a > 0) + (b > 0);
+        return need[v] = std::max(k, live_children + 1);
+    };
+    calc(ctx->root);
+
+    st.ops.clear();
+    std::vector<int> free_slots;
+    int n_slots = 0;
+    auto alloc = [&]() {
+        if (!free_slots.empty()) { int s = free_slots.back(); free_slots.pop_back(); return s; }
+        return n_slots++;
+    };
+    int n_cherry = 0;
+    auto gemm_over = [&](Op& op, int child, int slot) {  // the GEMM operand: a stored vector or a leaf pair
+        op.key = ctx->node_key[child];
+        if (is_cherry(child)) {
+            const int a = ctx->left[child], b = ctx->right[child];
+            op.a_kind = 1; op.in_slot = n_cherry++;
+            op.leaf_a1 = a / 2; op.key_a1 = leaf_key(a);
+            op.leaf_a2 = b / 2; op.key_a2 = leaf_key(b);
+        } else {
+            op.a_kind = 0; op.in_slot = slot;
+        }
+    };
+    std::function<int(int)> eval = [&](int v) -> int {  // returns the slot of v's vector (v internal, not a cherry)
+        const int a = ctx->left[v], b = ctx->right[v];
+        Op op{};
+        op.is_root = (v == ctx->root);
+        if (is_leaf(a) != is_leaf(b)) {
+            const int gch = is_leaf(a) ? b : a, l = is_leaf(a) ? a : b;
+            const int sg = is_cherry(gch) ? -1 : eval(gch);
+            op.out_slot = alloc();
+            gemm_over(op, gch, sg);
+            op.other_kind = 1; op.leaf_o = l / 2; op.key_o = leaf_key(l);
+            st.ops.push_back(op);
+            if (sg >= 0) free_slots.push_back(sg);
+            return op.out_slot;
+        }
+        // two internal children
+        const int first = need[a] >= need[b] ? a : b, second = (first == a) ? b : a;
+        const int s1 = is_cherry(first) ? -1 : eval(first);
+        const int s2 = is_cherry(second) ? -1 : eval(second);
+        op.out_slot = alloc();
+        gemm_over(op, first, s1);
+        op.other_kind = 0;
+        st.ops.push_back(op);
+        if (s1 >= 0) free_slots.push_back(s1);
+        Op op2{};
+        op2.is_root = op.is_root; op2.out_slot = op.out_slot;
+        gemm_over(op2, second, s2);
+        op2.other_kind = 2;
+        st.ops.push_back(op2);
+        if (s2 >= 0) free_slots.push_back(s2);
+        return op.out_slot;
+    };
+    eval(ctx->root);
+    st.n_slots = std::max(1, n_slots);
+    st.n_cherry = n_cherry;
+}
+
+int launch_prune_fused4(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
+    using namespace fused4;
+    Fused4State& st = fstate4(ctx);
+    PFN_encodeTiled4 encode = get_encode_fn4();
+    if (!encode) CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available");
+
+    // ---- schedule (a few hundred host instructions; the keys of the branches change with every rate vector) ----
+    build_schedule4(ctx, st);
+    if ((int)st.ops.size() > st.ops_cap) {
+        cudaFree(st.d_ops); st.d_ops = nullptr;
+        st.ops_cap = std::max<int>((int)st.ops.size(), 2 * ctx->n_nodes);
+        CAFE_CK(ctx, cudaMalloc(&st.d_ops, st.ops_cap * sizeof(Op)));
+    }
+    CAFE_CK(ctx, cudaMemcpyAsync(st.d_ops, st.ops.data(), st.ops.size() * sizeof(Op), cudaMemcpyHostToDevice, ctx->stream));
+
+    // ---- error-model leaves: one extra transposed matrix each, behind the keys ----
+    for (int k = 0; k < ctx->n_leaves; ++k) {
+        const int e = ctx->leaf_err.empty() ? -1 : ctx->leaf_err[k];
+        if (e < 0) continue;
+        const ErrModelDev& E = ctx->errs[e];
+        const size_t mat = (size_t)ctx->Sp * ctx->Sp;
+        dim3 g((ctx->Sp + 255) / 256, ctx->Sp);
+        k_err_leaf_matrix<<<g, 256, 0, ctx->stream>>>(ctx->d_MT + (size_t)ctx->node_key[2 * k] * mat, E.d_rowptr, E.d_col, E.d_val, E.dim,
+                                                      ctx->Sp, ctx->W - 1, ctx->d_MT + ((size_t)ctx->mat_cap + k) * mat);
+        ctx->launches++;
+    }
+    CAFE_CK(ctx, cudaGetLastError());
+
+    // ---- geometry: one CTA per SM, every CTA at least two 8-family blocks ----
+    const int n_mblocks = (ctx->F + 7) / 8;
+    const int grid = std::max(1, std::min(ctx->sm_count, (n_mblocks + 1) / 2));
+    const size_t cta_rows = (size_t)(2 * st.n_slots + 4 * st.n_cherry) * TILE_M;
+    const size_t scratch_doubles = (size_t)grid * cta_rows * ctx->Vp;
+    if (scratch_doubles > st.scratch_cap) {
+        cudaFree(st.d_scratch); st.d_scratch = nullptr;
+        CAFE_CK(ctx, cudaMalloc(&st.d_scratch, scratch_doubles * sizeof(double)));
+        CAFE_CK(ctx, cudaMemsetAsync(st.d_scratch, 0, scratch_doubles * sizeof(double), ctx->stream));
+        st.scratch_cap = scratch_doubles;
+    }
+
+    // ---- tensor maps (SWIZZLE_128B, zero OOB fill) ----
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)ctx->Vp, (cuuint64_t)grid * cta_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)ctx->Vp * sizeof(double)};
+        cuuint32_t box[2] = {BK, TILE_M};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, st.d_scratch, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) CAFE_FAIL(ctx, CAFE_GPU_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r));
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)ctx->Sp, (cuuint64_t)ctx->Sp, (cuuint64_t)ctx->mat_cap};
+        cuuint64_t strides[2] = {(cuuint64_t)ctx->Sp * sizeof(double), (cuuint64_t)ctx->Sp * ctx->Sp * sizeof(double)};
+        cuuint32_t box[3] = {BK, TN, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ctx->d_M, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) CAFE_FAIL(ctx, CAFE_GPU_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r));
+    }
+
+    Params P{};
+    P.ops = st.d_ops; P.n_ops = (int)st.ops.size(); P.n_slots = st.n_slots; P.n_cherry = st.n_cherry; P.F = ctx->F; P.F_pad = ctx->F_pad;
+    P.scratch = st.d_scratch;
+    P.W = ctx->W; P.R = ctx->R; P.root_min = ctx->root_min; P.Sp = ctx->Sp; P.Vp = ctx->Vp; P.n_mblocks = n_mblocks;
+    P.MT = ctx->d_MT; P.counts = ctx->d_counts; P.logprior = ctx->d_logprior;
+    P.prior_mant = ctx->d_prior_mant; P.prior_exp = ctx->d_prior_exp;
+    P.logpost = ctx->d_logpost; P.maxlik = ctx->d_maxlik; P.argmax = ctx->d_argmax; P.Lroot_out = d_Lroot_out;
+
+    if (const char* d = std::getenv("CAFE_GPU_DBG")) P.dbg = std::atoi(d);
+    P.lag = 2;   // group 1 two ring stages (= K blocks) behind group 0: the epilogues of the groups do not coincide
+    if (const char* d = std::getenv("CAFE_GPU_LAG")) P.lag = std::max(0, std::min(NSTAGE - 2, std::atoi(d)));
+    const size_t smem_bytes = (size_t)NSTAGE * STAGE_BYTES + sizeof(Ctl) + 1024;
+    if (!st.attr_set) {
+        CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        st.attr_set = true;
+    }
+    const char* trace_path = std::getenv("CAFE_GPU_TRACE");
+    long long* d_trace = nullptr;
+    if (trace_path) {
+        CAFE_CK(ctx, cudaMalloc(&d_trace, ((size_t)grid * 4 + 128 + 8192) * sizeof(long long)));
+        CAFE_CK(ctx, cudaMemsetAsync(d_trace, 0, ((size_t)grid * 4 + 128 + 8192) * sizeof(long long), ctx->stream));
+        P.cta_times = d_trace;
+        P.warp_prof = d_trace + (size_t)grid * 4;
+        P.timeline = P.warp_prof + 128;
+    }
+    if (trace_path) k_prune_fused4<true><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
+    else k_prune_fused4<false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
+    ctx->launches++;
+    CAFE_CK(ctx, cudaGetLastError());
+    if (trace_path) {  // debug only: synchronous dump "cta <i> <smid> <start ns> <end ns> <8-family blocks>"
+        std::vector<long long> h((size_t)grid * 4 + 128 + 8192);
+        CAFE_CK(ctx, cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+        CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_trace);
+        if (FILE* fp = std::fopen(trace_path, "w")) {
+            for (int c = 0; c < grid; ++c) std::fprintf(fp, "cta %d %lld %lld %lld %lld\n", c, h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+            // consumers: total, K loops, wait ring, wait C tile, epilogues, root epilogues, -, K loops of leaf-pair items | producer: total, wait done, wait empty
+            // epilogue manager: total, prep, wait consumers, store, items            (cycles, CTA 0)
+            for (int w = 0; w < 16; ++w) {
+                const long long* o = &h[(size_t)grid * 4 + w * 8];
+                std::fprintf(fp, "warp %d %lld %lld %lld %lld %lld %lld %lld %lld\n", w, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+            }
+            // per pass of warps 0 and 4 (the two DMMA warps of sub-partition 0): K loop start, K loop end, C tile ready, epilogue end
+            for (int g2 = 0; g2 < 2; ++g2)
+                for (int it = 0; it < 1024; ++it) {
+                    const long long* o = &h[(size_t)grid * 4 + 128 + ((size_t)g2 * 1024 + it) * 4];
+                    if (o[0]) std::fprintf(fp, "tl %d %d %lld %lld %lld %lld\n", g2, it, o[0], o[1], o[2], o[3]);
+                }
+            std::fclose(fp);
+        }
+    }
+    return CAFE_GPU_OK;
+}
