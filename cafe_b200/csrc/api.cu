@@ -90,8 +90,6 @@ static void destroy_one(cafe_gpu_ctx* ctx) {
     free_err_models(ctx);
     fused_release(ctx);
     fused2_release(ctx);
-    fused3_release(ctx);
-    fused4_release(ctx);
     for (cudaEvent_t e : ctx->ring) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

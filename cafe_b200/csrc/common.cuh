@@ -142,8 +142,6 @@ struct cafe_gpu_ctx {
 
     void* fused_state = nullptr;   // prune_fused.cu private state (device schedule, scratch)
     void* fused2_state = nullptr;  // prune_fused2.cu private state
-    void* fused3_state = nullptr;  // prune_fused3.cu private state
-    void* fused4_state = nullptr;  // prune_fused4.cu private state
 
     // multi-GPU (comm.cu): a context is one rank of an NCCL communicator.  Either one process per GPU (cafe_gpu_comm_init:
     // world ranks in world processes) or one process with several devices (cafe_gpu_create_multi: the leader context owns
@@ -184,12 +182,6 @@ void fused_release(cafe_gpu_ctx* ctx);
 bool fused2_supported(const cafe_gpu_ctx* ctx);                         // prune_fused2.cu
 int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out);        // prune_fused2.cu (K2, one CTA per SM, default)
 void fused2_release(cafe_gpu_ctx* ctx);
-bool fused3_supported(const cafe_gpu_ctx* ctx);                         // prune_fused3.cu
-int launch_prune_fused3(cafe_gpu_ctx* ctx, double* d_Lroot_out);        // prune_fused3.cu (K2, one CTA per SM, de-phased groups, default)
-void fused3_release(cafe_gpu_ctx* ctx);
-bool fused4_supported(const cafe_gpu_ctx* ctx);                         // prune_fused4.cu
-int launch_prune_fused4(cafe_gpu_ctx* ctx, double* d_Lroot_out);        // prune_fused4.cu (K2, register epilogue, 7-stage ring, default)
-void fused4_release(cafe_gpu_ctx* ctx);
 int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
                                  double* cd_out);                       // conddist.cu    (K4)
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out);  // pvalue.cu (K5)

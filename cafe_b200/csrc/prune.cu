@@ -314,16 +314,8 @@ int launch_prune(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     if (ctx->timing) CAFE_CK(ctx, cudaEventRecord(ctx->evt(ctx->ring_k2, EV_K2_BEGIN), ctx->stream));
     const bool no_fused = std::getenv("CAFE_GPU_NO_FUSED") != nullptr;  // A/B switches for tests and profiling (read per call)
     const bool fused_v1 = std::getenv("CAFE_GPU_FUSED_V1") != nullptr;  // first-generation fused kernel
-    const bool fused_v2 = std::getenv("CAFE_GPU_FUSED_V2") != nullptr;  // second-generation fused kernel (groups in lockstep)
-    const bool fused_v3 = std::getenv("CAFE_GPU_FUSED_V3") != nullptr;  // third generation (per-group C halves in shared memory)
-    if (!no_fused && !fused_v1 && !fused_v2 && !fused_v3 && fused4_supported(ctx)) {
+    if (!no_fused && !fused_v1 && fused2_supported(ctx)) {
         // fused persistent kernel, one CTA per SM: whole tree + root reduction in one launch
-        int rc = launch_prune_fused4(ctx, d_Lroot_out);
-        if (rc) return rc;
-    } else if (!no_fused && !fused_v1 && !fused_v2 && fused3_supported(ctx)) {
-        int rc = launch_prune_fused3(ctx, d_Lroot_out);
-        if (rc) return rc;
-    } else if (!no_fused && !fused_v1 && fused2_supported(ctx)) {
         int rc = launch_prune_fused2(ctx, d_Lroot_out);
         if (rc) return rc;
     } else if (!no_fused && fused_supported(ctx)) {

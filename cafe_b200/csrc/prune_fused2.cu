@@ -7,20 +7,23 @@
 // Why a second kernel: prune_fused.cu runs 3 independent CTAs per SM.  The SM's warp arbiter serves the
 // highest warp slot first, so one of the three CTAs is starved of the DMMA pipe and finishes ~20 % after the
 // other two (profiles/r1_fused_v1_cta_timeline.txt), and every CTA leaves the pipe for its epilogues (global
-// gathers), leaf-pair products and proxy fences.  Here ONE CTA per SM owns the SM:
+// gathers), leaf-pair products and proxy fences.  Here ONE CTA per SM owns the SM, 12 warps:
 //
-//   warps 0..11  DMMA consumers, 3 M-groups x 4 N-warps, CTA tile 96 families x 128 sizes.  All twelve consume the
-//                same shared-memory ring, so they advance in lockstep (a starved warp stalls the ring and thereby
-//                gets the pipe) and the matrix tile (B) is fetched once for all three groups.  Consumers touch shared
-//                memory only: no global loads, no global stores, no membar.
-//   warp 12      TMA producer: child vectors (A, 96 x 16 sizes) and matrix K-blocks (B, 128 rows x 16 sizes).
-//   warp 13      cherry gatherer: when the GEMM child is a node whose two children are leaves, its vector is the
-//                product of two gathered matrix columns (cafe_tree.c:204-210); the rows are copied with cp.async
-//                straight into the ring (A1, A2) and multiplied by the consumers in registers — a leaf-pair
-//                vector never exists in memory.
-//   warp 14      epilogue manager: stages the sibling factor of the next pass in the 96 KB C tile (TMA for a stored
+//   warps 4..11  DMMA consumers, 2 M-groups x 4 N-warps (warp tile 48 families x 32 sizes), CTA tile 96 families x 128
+//                sizes: exactly two DMMA warps per SM sub-partition, one of each group.  All eight consume the same
+//                shared-memory ring (2 stages of 2 K blocks), so the matrix tile (B) is fetched once per CTA.  Consumers
+//                touch shared memory only: no global loads, no global stores, no membar.
+//   warp 0       TMA producer (one lane): child vectors (A, 96 x 16 sizes) and matrix K-blocks (B, 128 rows x 16 sizes).
+//   warps 1..2   leaf-pair gatherers: a node whose two children are leaves has the vector M_a[.][c_a] * M_b[.][c_b]
+//                (cafe_tree.c:204-210); the gatherers write these vectors one pair of tiles ahead into scratch slots of
+//                their own, the parent's GEMM streams them like any other vector.
+//   warp 3       epilogue manager: stages the sibling factor of the next pass in the 96 KB C tile (TMA for a stored
 //                partial product, cp.async row gathers for a leaf sibling), and writes the finished tile back with
-//                a TMA store.  Consumers multiply in place (C = acc * C).  All fences live in this warp.
+//                TMA stores.  Consumers multiply in place (C = acc * C).  All fences live in this warp.
+//
+// Two restructurings of this kernel were measured in round 2 and lost (profiles/r2_k2_experiments.md): per-group C halves
+// with the groups one ring stage apart (4 stages of 1 K block: 3.82 ms), and a register epilogue straight to global memory
+// with a 7-stage ring (5.0 ms), against 3.72 ms here.
 //
 // Bit-for-bit the same arithmetic as prune_fused.cu / prune.cu (same DMMA order over K, one rounding per product).
 #include <cuda.h>
