@@ -30,6 +30,9 @@ def build(ref: bool = True) -> None:
     subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
     if ref and os.path.isdir("/root/reference/cafe"):
         subprocess.run(["make", "-s", "-j8", "-C", HERE, "ref"], check=True)
+        # the reference with integration/gpu_bridge.cpp compiled in (needs ../cafe_b200/libcafe_gpu.so)
+        if os.path.exists(os.path.join(HERE, "..", "cafe_b200", "libcafe_gpu.so")):
+            subprocess.run(["make", "-s", "-j8", "-C", HERE, "bridge"], check=True)
 
 
 def _dptr(a):
@@ -153,6 +156,12 @@ def ref(openmp: bool = False):
     R.refshim_likelihood_ratio_test.argtypes = [C.c_void_p, _dp, C.c_double, C.c_int, _dp]
     R.refshim_fminsearch.argtypes = [MATH_FUNC, C.c_void_p, C.c_int, _dp, C.c_double, C.c_double, _dp, _dp, _ip]
     return R
+
+
+def ref_gpu_binary():
+    """The unmodified reference + integration/gpu_bridge.cpp (oracle/Makefile target `bridge`), or None."""
+    p = os.path.join(HERE, "_ref", "cafe_ref_gpu")
+    return p if os.path.exists(p) else None
 
 
 def ref_binary():
