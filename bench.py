@@ -195,6 +195,27 @@ class ReferenceCpu:
         per_eval = t_mat + n_total / len(cs) * t_fam
         return {"t_matrices": t_mat, "t_sample": t_fam, "value": n_total / per_eval, "score": score, "per_eval_s": per_eval}
 
+    def cond_dist_sample(self, n_rows, n_samples):
+        """The reference's pthreads conditional distribution (cafe_conditional_distribution, conditional_distribution.cpp:86-120:
+        one thread per block of root sizes) on `n_rows` root sizes x `n_samples` draws with all host cores; draws per second."""
+        C = self.C
+        dp = C.POINTER(C.c_double)
+        R = self.R
+        rg = (self.ranges[0], self.ranges[1], self.ranges[2], self.ranges[2] + n_rows - 1)
+        h = R.refshim_session_new(self.newick.encode(), *rg)
+        n = R.refshim_n_nodes(h)
+        la, mu = self.rates(n, self.lam0)
+        R.refshim_set_rates(h, la.ctypes.data_as(dp), mu.ctypes.data_as(dp))
+        self.threads(self.cores)
+        R.refshim_reset_cache(h)
+        out = np.zeros((n_rows, n_samples))
+        R.refshim_srand(10)
+        t0 = time.perf_counter()
+        R.refshim_cond_dist(h, self.cores, n_samples, out.ctypes.data_as(dp))
+        dt = time.perf_counter() - t0
+        R.refshim_session_free(h)
+        return n_rows * n_samples / dt, dt
+
     def calibrate(self, counts_sample, lam):
         """Pick the OpenMP thread count that makes the (serial-over-families) posterior loop fastest on this box."""
         if self.gomp is None or self.kind != "reference":
@@ -365,6 +386,46 @@ def measure(P, args, torch, dist, dev, stream, sampler=None):
     }
 
 
+def measure_pvalue_pass(P, torch, dist, n_samples=1000):
+    """BASELINE configs[4]: the conditional distribution (n_samples Monte-Carlo families per root size, each pruned with its
+    root size fixed: cafe/conditional_distribution.cpp:10-44) and the family-wide p-values of every family of the table
+    (cafe/pvalue.cpp:143-154) through the C-ABI, host arrays out.  With N ranks the root sizes are split over the ranks and
+    the rows all-gathered; every rank then does the p-values of its own families.  Wall clock, max over ranks."""
+    from cafe_b200 import sharding
+    g, world, rank = P.g, P.world, P.rank
+    g.set_rates(*P.rates(0))
+    g.build_matrices()
+    g.synchronize()
+
+    def wall(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, float(t.item())
+
+    g.reset_launch_count()
+    if world > 1:
+        cd, t_cd = wall(lambda: sharding.conditional_distribution_sharded(g, n_samples, 7, rank, world))
+    else:
+        cd, t_cd = wall(lambda: g.conditional_distribution(n_samples, seed=7))
+    pv, t_pv = wall(lambda: g.pvalues(cd))
+    launches = g.launch_count()
+    per_family = g.score_flops() / max(1, P.n_unique)
+    draws = P.R * n_samples
+    return {"workload": f"conditional distribution: {n_samples} draws x {P.R} root sizes, then p-values of the "
+                        f"{P.cfg['families']} families of the headline table (BASELINE configs[4])",
+            "cd_s": t_cd, "pvalues_s": t_pv, "draws_per_s": draws / t_cd, "family_pvalues_per_s": P.cfg["families"] / t_pv,
+            "cd_tflops": draws * per_family / t_cd * 1e-12, "pvalues_tflops_upper": P.cfg["families"] * per_family / t_pv * 1e-12,
+            "flops_note": "internal edges only, full range per simulated family (the per-family range ratchet makes the real work smaller)",
+            "gpu_launches": int(launches), "max_pvalue_mean": float(np.mean(pv)), "cd_checksum": float(cd.sum())}
+
+
 def dgemm_peak(torch, dev):
     """fp64 roofline denominator: cuBLAS DGEMM on this GPU, this run (MEASURED_PEAKS.json carries no fp64 figure)."""
     a = torch.randn(6144, 6144, dtype=torch.float64, device=dev)
@@ -431,6 +492,12 @@ def run_ours(args, rank, local_rank, world):
     P = GpuProblem(HEADLINE, rank, world, local_rank, stream.cuda_stream, comm_id)
     m = measure(P, args, torch, dist, dev, stream, sampler if rank == 0 else None)
     clocks = sampler.stop(max(0, m["marks"][0] - 1), m["marks"][1]) if rank == 0 else None
+    pv_pass = None
+    if not args.no_sub:
+        try:
+            pv_pass = measure_pvalue_pass(P, torch, dist)
+        except Exception as e:  # a secondary measurement must never take the headline down
+            pv_pass = {"error": repr(e)}
     if rank != 0:
         P.g.close()
         if world > 1:
@@ -484,6 +551,19 @@ def run_ours(args, rank, local_rank, world):
             except Exception as e:  # a sub-configuration must never take the headline down
                 subs[name] = {"error": repr(e)}
         line["configs"] = subs
+    if pv_pass is not None:
+        line.setdefault("configs", {})["configs[4]"] = pv_pass
+        if world == 1 and "error" not in pv_pass and not args.no_cpu_baseline:
+            try:
+                ref4 = ReferenceCpu(HEADLINE)
+                dps, dt = ref4.cond_dist_sample(P.R, 4)
+                pv_pass["cpu_baseline"] = {"value": dps, "unit": "draws/s", "cores": ref4.cores, "kind": ref4.kind,
+                                           "sample": f"the reference's pthreads cafe_conditional_distribution (one thread per block of root "
+                                                     f"sizes, conditional_distribution.cpp:86-120) on all {P.R} root sizes x 4 draws instead of "
+                                                     f"1000, {ref4.cores} threads ({dt:.1f}s), same tree, rates and ranges"}
+                pv_pass["cd_speedup_vs_cpu"] = pv_pass["draws_per_s"] / dps
+            except Exception as e:
+                pv_pass["cpu_baseline"] = {"error": repr(e)}
 
     # ---- CPU baseline on this box's host cores (bounded sample of the same table) ----
     if world == 1 and not args.no_cpu_baseline:

@@ -181,6 +181,20 @@ int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out);         // prune
 void fused_release(cafe_gpu_ctx* ctx);
 bool fused2_supported(const cafe_gpu_ctx* ctx);                         // prune_fused2.cu
 int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out);        // prune_fused2.cu (K2, one CTA per SM, default)
+// The same kernel on any table of sizes: the observed families (score), or simulated / windowed ones (conditional distribution,
+// p-values).  counts[k * leaf_stride + f] = size of family f at leaf k; d_colmax (nullable): per-family column window;
+// root rows root_r0 .. root_r0 + root_rows - 1; d_root_pick / d_L0_out (nullable): root SIZE per family whose likelihood is
+// written to d_L0_out[f]; d_Lroot_out (nullable): all root rows, [F][root_rows]; posterior: the root reduction of the score.
+struct Fused2Job {
+    const int* counts = nullptr; size_t leaf_stride = 0; int F = 0, F_pad = 0;
+    const int* d_colmax = nullptr;
+    int root_r0 = 0, root_rows = 0;
+    const int* d_root_pick = nullptr; double* d_L0_out = nullptr;
+    double* d_Lroot_out = nullptr;
+    bool posterior = false;
+};
+bool fused2_windowed_supported(const cafe_gpu_ctx* ctx);
+int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job);
 void fused2_release(cafe_gpu_ctx* ctx);
 int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
                                  double* cd_out);                       // conddist.cu    (K4)

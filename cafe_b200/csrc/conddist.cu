@@ -18,6 +18,7 @@
 #include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -49,10 +50,11 @@ __global__ void k_simulate(const double* __restrict__ CDF, int Sp, const int* __
                            const int* __restrict__ parent, const int* __restrict__ node_key, int n_nonroot, int root,
                            int s_lo, int n_samples, int Fc, int Fc_pad, int range_max,
                            const double* __restrict__ uniforms /* nullable, chunk-local */, uint64_t seed,
-                           int* __restrict__ sizes /* [n_nodes][Fc_pad] */, int* __restrict__ trial_max) {
+                           int* __restrict__ sizes /* [n_nodes][Fc_pad] */, int* __restrict__ trial_max, int* __restrict__ root_size) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= Fc) return;
     const int s = s_lo + f / n_samples, trial = f % n_samples;
+    root_size[f] = s;
     const int max_family_size = max(s, range_max);  // conditional_distribution.cpp:20
     sizes[(size_t)root * Fc_pad + f] = s;
     int mx = 0;
@@ -142,14 +144,17 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
     const size_t mat_bytes = (size_t)D * ctx->Sp * ctx->Sp * sizeof(double);
     double* d_cdf = nullptr;
     int *d_prefix = nullptr, *d_parent = nullptr, *d_node_key = nullptr;
-    int *d_sizes = nullptr, *d_trial_max = nullptr, *d_colmax = nullptr;
+    int *d_sizes = nullptr, *d_trial_max = nullptr, *d_colmax = nullptr, *d_root_size = nullptr;
+    // the fused kernel (prune_fused2.cu, windowed mode) prunes the simulated families whenever it can; the per-node kernels remain
+    // for error-model leaves and as the A/B switch CAFE_GPU_NO_FUSED
+    const bool fused = fused2_windowed_supported(ctx) && std::getenv("CAFE_GPU_NO_FUSED") == nullptr;
     double *d_uniforms = nullptr, *d_L0 = nullptr, *d_sorted = nullptr;
     void* d_tmp = nullptr;
     int* d_offsets = nullptr;
     int rc = CAFE_GPU_OK;
     auto cleanup = [&]() {
         cudaFree(d_cdf); cudaFree(d_prefix); cudaFree(d_parent); cudaFree(d_node_key); cudaFree(d_sizes); cudaFree(d_trial_max);
-        cudaFree(d_colmax); cudaFree(d_uniforms); cudaFree(d_L0); cudaFree(d_sorted); cudaFree(d_tmp); cudaFree(d_offsets);
+        cudaFree(d_colmax); cudaFree(d_root_size); cudaFree(d_uniforms); cudaFree(d_L0); cudaFree(d_sorted); cudaFree(d_tmp); cudaFree(d_offsets);
     };
 #define CD_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
 
@@ -197,11 +202,15 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
     CD_CK(cudaMalloc(&d_trial_max, (size_t)Fc_pad * sizeof(int)));
     CD_CK(cudaMalloc(&d_colmax, (size_t)Fc_pad * sizeof(int)));
     CD_CK(cudaMemsetAsync(d_colmax, 0, (size_t)Fc_pad * sizeof(int), ctx->stream));
+    CD_CK(cudaMalloc(&d_root_size, (size_t)Fc_pad * sizeof(int)));
+    CD_CK(cudaMemsetAsync(d_root_size, 0, (size_t)Fc_pad * sizeof(int), ctx->stream));
     CD_CK(cudaMalloc(&d_L0, (size_t)R * n_samples * sizeof(double)));
     CD_CK(cudaMalloc(&d_sorted, (size_t)R * n_samples * sizeof(double)));
     if (uniforms) CD_CK(cudaMalloc(&d_uniforms, (size_t)Fc_max * n_nonroot * sizeof(double)));
-    rc = ensure_vec_buffers(ctx, Fc_pad);
-    if (rc) { cleanup(); return rc; }
+    if (!fused) {
+        rc = ensure_vec_buffers(ctx, Fc_pad);
+        if (rc) { cleanup(); return rc; }
+    }
     const size_t slot_stride = (size_t)Fc_pad * ctx->Vp;
 
     for (int r_lo = row_lo; r_lo < row_hi; r_lo += rows_per_chunk) {
@@ -210,16 +219,28 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
             CD_CK(cudaMemcpyAsync(d_uniforms, uniforms + (size_t)r_lo * n_samples * n_nonroot, (size_t)Fc * n_nonroot * sizeof(double),
                                   cudaMemcpyHostToDevice, ctx->stream));
         k_simulate<<<(Fc + 127) / 128, 128, 0, ctx->stream>>>(d_cdf, ctx->Sp, d_prefix, d_parent, d_node_key, n_nonroot, ctx->root, s_lo,
-                                                              n_samples, Fc, Fc_pad, ctx->rmax, d_uniforms, seed, d_sizes, d_trial_max);
+                                                              n_samples, Fc, Fc_pad, ctx->rmax, d_uniforms, seed, d_sizes, d_trial_max, d_root_size);
         k_ratchet<<<(rows + 127) / 128, 128, 0, ctx->stream>>>(d_trial_max, rows, n_samples, ctx->rmax, d_colmax);
         ctx->launches += 2;
-        // all non-root nodes with the per-trial column window; leaf k is node 2k of the size table
-        rc = launch_prune_ops(ctx, d_sizes, (size_t)2 * Fc_pad, Fc, Fc_pad, d_colmax, 0, 0, /*skip_root=*/true, nullptr);
-        if (rc) { cleanup(); return rc; }
-        k_root_single_row<<<(Fc + 7) / 8, 256, 0, ctx->stream>>>(rc_child[0], rc_child[1], ctx->d_M, ctx->d_vec, ctx->Sp, ctx->Vp, slot_stride,
-                                                                 d_sizes, Fc, Fc_pad, s_lo, n_samples, d_colmax,
-                                                                 d_L0 + (size_t)r_lo * n_samples);
-        ctx->launches++;
+        if (fused) {
+            // one persistent launch: every node with the per-trial column window, the root over its whole range, and of the
+            // root's likelihoods the one of the family's own root size (the reference prunes with the root range {s})
+            Fused2Job job;
+            job.counts = d_sizes; job.leaf_stride = (size_t)2 * Fc_pad; job.F = Fc; job.F_pad = Fc_pad;  // leaf k is node 2k of the size table
+            job.d_colmax = d_colmax;
+            job.root_r0 = ctx->root_min; job.root_rows = R;
+            job.d_root_pick = d_root_size; job.d_L0_out = d_L0 + (size_t)r_lo * n_samples;
+            rc = launch_prune_fused2_job(ctx, job);
+            if (rc) { cleanup(); return rc; }
+        } else {
+            // all non-root nodes with the per-trial column window; leaf k is node 2k of the size table
+            rc = launch_prune_ops(ctx, d_sizes, (size_t)2 * Fc_pad, Fc, Fc_pad, d_colmax, 0, 0, /*skip_root=*/true, nullptr);
+            if (rc) { cleanup(); return rc; }
+            k_root_single_row<<<(Fc + 7) / 8, 256, 0, ctx->stream>>>(rc_child[0], rc_child[1], ctx->d_M, ctx->d_vec, ctx->Sp, ctx->Vp, slot_stride,
+                                                                     d_sizes, Fc, Fc_pad, s_lo, n_samples, d_colmax,
+                                                                     d_L0 + (size_t)r_lo * n_samples);
+            ctx->launches++;
+        }
         CD_CK(cudaGetLastError());
     }
 

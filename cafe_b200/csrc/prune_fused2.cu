@@ -79,11 +79,18 @@ struct Params {
     int n_mblocks;               // ceil(F / 8)
     double* scratch;             // [grid][cta_rows][Vp]
     const double* MT;            // [D][Sp][Sp] transposed matrices
-    const int* counts;           // [n_leaves][F_pad]
+    const int* counts;           // [n_leaves][leaf_stride]: observed (or simulated) size of family f at leaf k = counts[k * leaf_stride + f]
+    size_t leaf_stride;
+    // Windowed mode (conditional distribution / p-values): per-family column window, cafe_family.c:250-254 and
+    // conditional_distribution.cpp:29.  Sizes above colmax[f] are exact zeros in every node vector of family f (the reference
+    // does not compute them) and a leaf whose size lies above the window has factor 0.  nullptr: the full range for everybody.
+    const int* colmax;           // nullable, [F_pad]
+    const int* root_pick;        // nullable, [F_pad]: root SIZE whose likelihood goes to L0_out[f] (root range {s} of the distribution)
+    double* L0_out;              // [F] with root_pick
     const double* logprior;      // [R]
     const double* prior_mant;    // [R] prior = mant * 2^exp, mant in [1,2)  (host frexp; exp = -2^30 where the prior is 0)
     const int* prior_exp;        // [R]
-    double* logpost;             // [F_pad]
+    double* logpost;             // [F_pad]; nullptr: no posterior reduction at the root (windowed mode)
     double* maxlik;
     int* argmax;
     double* Lroot_out;           // nullable, [F][R]
@@ -175,7 +182,9 @@ struct Ctl {
     uint64_t c_done;             // 8 consumer warps
     volatile int done[2];        // finished (stored, visible) ops per tile of the pair
     volatile int cherry_count;   // leaf-pair vectors: 2 (gatherer warps) per finished vector, in (pair, op, tile) order
-    int rowoff_o[TILE_M];        // epilogue manager: count * Sp of the leaf sibling, per tile row
+    int rowoff_o[TILE_M];        // epilogue manager: count * Sp of the leaf sibling, per tile row (-1: leaf outside the window)
+    int colmax[2][TILE_M];       // windowed mode: column window of the rows of the two tiles of the pair
+    int pick[2][TILE_M];         // windowed mode: root row index to extract (-1 none)
     unsigned char opflags[OPFLAGS_CAP];  // per op: bit0 is_root, bit1 a_kind, bits 2-3 other_kind (what the consumers need)
     double red_ml[GM][4][HM];    // root reduction across the 4 N-warps of a group
     double red_mp[GM][4][HM];
@@ -325,14 +334,22 @@ __device__ __forceinline__ void gatherer_main(const Params& P, double* scratch, 
                 if (!plan.tile(2 * pair + h, mb0, m)) continue;
                 double* out = cta_scratch + (size_t)cherry_row(P, pair, h, op.in_slot) * P.Vp;
                 for (int r0 = (TILE_M / 2) * gi; r0 < (TILE_M / 2) * (gi + 1); r0 += 2) {
-                    const double2* pa[2]; const double2* pb[2]; double2* po[2]; bool ok[2];
+                    const double2* pa[2]; const double2* pb[2]; double2* po[2]; bool ok[2]; int wlim[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         const int f = TilePlan::family_or_neg(mb0, m, r0 + u, P.F);
                         ok[u] = f >= 0;
                         const int fc = ok[u] ? f : 0;
-                        pa[u] = reinterpret_cast<const double2*>(MTa + (size_t)__ldg(P.counts + (size_t)op.leaf_a1 * P.F_pad + fc) * P.Sp);
-                        pb[u] = reinterpret_cast<const double2*>(MTb + (size_t)__ldg(P.counts + (size_t)op.leaf_a2 * P.F_pad + fc) * P.Sp);
+                        const int ca = __ldg(P.counts + (size_t)op.leaf_a1 * P.leaf_stride + fc), cb = __ldg(P.counts + (size_t)op.leaf_a2 * P.leaf_stride + fc);
+                        // sizes >= W stay exact zeros (the vector has length W although the matrices are wider when S > W); with a
+                        // per-family window also the sizes above it, and the whole vector when a leaf lies outside the window
+                        wlim[u] = P.W;
+                        if (P.colmax) {
+                            const int cm = __ldg(P.colmax + fc);
+                            wlim[u] = (ca <= cm && cb <= cm) ? min(P.W, cm + 1) : 0;
+                        }
+                        pa[u] = reinterpret_cast<const double2*>(MTa + (size_t)ca * P.Sp);
+                        pb[u] = reinterpret_cast<const double2*>(MTb + (size_t)cb * P.Sp);
                         po[u] = reinterpret_cast<double2*>(out + (size_t)(r0 + u) * P.Vp);
                     }
                     for (int p0 = 0; p0 < n_pieces; p0 += 128) {  // 4 pieces per lane and row in flight
@@ -351,9 +368,9 @@ __device__ __forceinline__ void gatherer_main(const Params& P, double* scratch, 
                             for (int k = 0; k < 4; ++k) {
                                 const int pc = p0 + k * 32 + lane;
                                 if (ok[u] && pc < n_pieces) {
-                                    // sizes >= W stay exact zeros: the vector has length W although the matrices are wider when S > W
-                                    const double hi = (2 * pc + 1 < P.W) ? __dmul_rn(x[u][k].y, y[u][k].y) : 0.0;
-                                    po[u][pc] = make_double2(__dmul_rn(x[u][k].x, y[u][k].x), hi);
+                                    const double lo = (2 * pc < wlim[u]) ? __dmul_rn(x[u][k].x, y[u][k].x) : 0.0;
+                                    const double hi = (2 * pc + 1 < wlim[u]) ? __dmul_rn(x[u][k].y, y[u][k].y) : 0.0;
+                                    po[u][pc] = make_double2(lo, hi);
                                 }
                             }
                     }
@@ -382,6 +399,21 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
     long long t_prep = 0, t_wait_cdone = 0, t_store = 0;
     const long long t_begin = prof ? clock64() : 0;
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        if (P.colmax || P.root_pick) {
+            // windowed mode: the windows / root picks of the rows of this pair's tiles (every consumer has left the previous pair:
+            // its last pass was handed back through c_done before this point)
+            __syncwarp();
+            for (int h = 0; h < 2; ++h) {
+                int mb0, m;
+                if (!plan.tile(2 * pair + h, mb0, m)) continue;
+                for (int r = lane; r < TILE_M; r += 32) {
+                    const int f = TilePlan::family(mb0, m, r, P.F);
+                    ctl->colmax[h][r] = P.colmax ? __ldg(P.colmax + f) : 0x7fffffff;
+                    ctl->pick[h][r] = P.root_pick ? __ldg(P.root_pick + f) - P.root_min : -1;
+                }
+            }
+            __syncwarp();
+        }
         for (int oi = 0; oi < P.n_ops; ++oi) {
             const Op op = P.ops[oi];
             const int r0 = op.is_root ? P.root_min : 0;
@@ -396,13 +428,18 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                     __syncwarp();
                     for (int r = lane; r < TILE_M; r += 32) {
                         const int f = TilePlan::family(mb0, m, r, P.F);
-                        ctl->rowoff_o[r] = __ldg(P.counts + (size_t)op.leaf_o * P.F_pad + f) * P.Sp;
+                        const int cnt = __ldg(P.counts + (size_t)op.leaf_o * P.leaf_stride + f);
+                        // a leaf outside the family's window has factor 0 (the one-hot entry is not part of the vector)
+                        ctl->rowoff_o[r] = (P.colmax && cnt > __ldg(P.colmax + f)) ? -1 : cnt * P.Sp;
                     }
                     __syncwarp();
                 }
                 const int out_row = scratch_row0 + (h * P.n_slots + op.out_slot) * TILE_M;
                 for (int ch = 0; ch < n_chunks; ++ch) {
                     const int nbx = min(C_BOXES, (P.Vp - ch * TN) / BK);  // boxes of this pass inside the vector
+                    // sizes of the pass the consumers own: whole 8-size blocks up to nrows (consumer_main).  What lies beyond, up to
+                    // the end of the stored boxes, must be zeros in the slot - staged here, never touched by the consumers.
+                    const int ncons = min(TN, ((nrows - ch * TN + 7) >> 3) << 3);
                     const long long tc0 = prof ? clock64() : 0;
                     // ---- stage the sibling factor of this pass in the C tile ----
                     if (op.other_kind == 2) {
@@ -420,30 +457,39 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                             const int cj = lane & 7, rs = lane >> 3;
                             for (int b = 0; b < nbx; ++b) {
                                 const int col = gc0 + b * BK + 2 * cj;
-                                const bool in = col < P.Sp;
+                                const bool in = col < P.Sp && b * BK + 2 * cj < ncons;
                                 const double* src0 = MTo + (in ? col : 0);
 #pragma unroll 4
                                 for (int i = 0; i < TILE_M / 4; ++i) {
                                     const int r = rs + 4 * i;
-                                    cp_async16(sC + b * C_BOX_BYTES + r * 128 + ((cj ^ (r & 7)) << 4), src0 + ctl->rowoff_o[r], in ? 16 : 0);
+                                    const int ro = ctl->rowoff_o[r];
+                                    cp_async16(sC + b * C_BOX_BYTES + r * 128 + ((cj ^ (r & 7)) << 4), src0 + max(ro, 0), (in && ro >= 0) ? 16 : 0);
                                 }
                             }
                         } else {  // odd first size (the root range starts at 1): rows are only 8-byte aligned
                             const int cl = lane & 15, rs = lane >> 4;
                             for (int b = 0; b < nbx; ++b) {
                                 const int col = gc0 + b * BK + cl;
-                                const bool in = col < P.Sp;
+                                const bool in = col < P.Sp && b * BK + cl < ncons;
                                 const double* src0 = MTo + (in ? col : 0);
 #pragma unroll 4
                                 for (int i = 0; i < TILE_M / 2; ++i) {
                                     const int r = rs + 2 * i;
+                                    const int ro = ctl->rowoff_o[r];
                                     cp_async8(sC + b * C_BOX_BYTES + r * 128 + (((cl >> 1) ^ (r & 7)) << 4) + ((cl & 1) << 3),
-                                              src0 + ctl->rowoff_o[r], in ? 8 : 0);
+                                              src0 + max(ro, 0), (in && ro >= 0) ? 8 : 0);
                                 }
                             }
                         }
                         cp_async_arrive_noinc(&ctl->c_ready);
                     } else {
+                        if (ncons < nbx * BK) {  // no sibling factor to stage: only the zeros beyond the consumers' blocks
+                            const int nz = nbx * BK - ncons;
+                            for (int idx = lane; idx < TILE_M * nz; idx += 32) {
+                                const int r = idx / nz, c = ncons + idx % nz;
+                                *reinterpret_cast<double*>(Cbuf + (c >> 4) * C_BOX_BYTES + r * 128 + ((((c & 15) >> 1) ^ (r & 7)) << 4) + ((c & 1) << 3)) = 0.0;
+                            }
+                        }
                         mbar_arrive(&ctl->c_ready);
                     }
                     // ---- the consumers multiply in place ----
@@ -461,6 +507,14 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                     } else {
                         // ... or, at the root (reduced by the consumers), is only copied out on request
                         const int ncols = min(TN, nrows - ch * TN);
+                        if (P.root_pick) {  // the distribution's root range {s}: one likelihood per simulated family
+                            for (int r = lane; r < TILE_M; r += 32) {
+                                const int f = TilePlan::family_or_neg(mb0, m, r, P.F);
+                                const int c = ctl->pick[h][r] - ch * TN;
+                                if (f >= 0 && c >= 0 && c < ncols)
+                                    P.L0_out[f] = *reinterpret_cast<const double*>(Cbuf + (c >> 4) * C_BOX_BYTES + r * 128 + ((((c & 15) >> 1) ^ (r & 7)) << 4) + ((c & 1) << 3));
+                            }
+                        }
                         if (P.Lroot_out) {  // get_likelihoods (cafe_tree.c:325-329): rows copied out, lanes along the sizes
                             for (int r = 0; r < TILE_M; ++r) {
                                 const int f = TilePlan::family_or_neg(mb0, m, r, P.F);
@@ -491,21 +545,22 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
 
 // ================================ warps 0..7: DMMA consumers ================================
 // Fragments of one k4-step: 4 B fragments and one A fragment per 8-family block.
-template <int MBV>
+// NBV: 8-size blocks of this warp in the pass (4, or 3 in a pass whose blocks do not divide by 4, see consumer_main)
+template <int MBV, int NBV>
 __device__ __forceinline__ void load_frags(double (&fa)[MB], double (&fb)[NB], const unsigned char* sA, const unsigned char* sB, int off) {
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) fb[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + off);
+    for (int nb = 0; nb < NBV; ++nb) fb[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + off);
 #pragma unroll
     for (int mb = 0; mb < MBV; ++mb) {
         fa[mb] = *reinterpret_cast<const double*>(sA + mb * 1024 + off);
     }
 }
-template <int MBV>
+template <int MBV, int NBV>
 __device__ __forceinline__ void mma_frags(double (&acc)[MB][NB][2], const double (&fa)[MB], const double (&fb)[NB]) {
 #pragma unroll
     for (int mb = 0; mb < MBV; ++mb)
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], fa[mb], fb[nb]);
+        for (int nb = 0; nb < NBV; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], fa[mb], fb[nb]);
 }
 
 // non-blocking probe of an mbarrier phase: issued a few k4-steps before the result is needed
@@ -523,7 +578,7 @@ __device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
 // STEPS k4-steps (one or two full K blocks of a ring stage).  The fragments of the next step are fetched before the DMMAs of the
 // current one; after the last step (do_next) the first fragments of whatever follows - the next K block of the stage, or the
 // next stage after its mbarrier wait (~100 cycles even when already full) - so that neither sits between two DMMAs.
-template <int MBV, int STEPS>
+template <int MBV, int NBV, int STEPS>
 __device__ __forceinline__ void steps_full(double (&acc)[MB][NB][2], double (&fa)[2][MB], double (&fb)[2][NB], const unsigned char* sa,
                                            const unsigned char* sb, const int (&koff)[4], bool do_next, const unsigned char* next_a,
                                            const unsigned char* next_b, uint64_t* wait_bar, uint32_t wait_phase,
@@ -535,24 +590,25 @@ __device__ __forceinline__ void steps_full(double (&acc)[MB][NB][2], double (&fa
         if (STEPS >= 4 && kk == STEPS - 3 && do_next && wait_bar) ready = mbar_test(wait_bar, wait_phase);
         if (kk + 1 < STEPS) {
             const int j = (kk + 1) >> 2;
-            load_frags<MBV>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sa + j * SUB_BYTES, sb + j * SUB_BYTES, koff[(kk + 1) & 3]);
+            load_frags<MBV, NBV>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sa + j * SUB_BYTES, sb + j * SUB_BYTES, koff[(kk + 1) & 3]);
         } else if (do_next) {
             if (wait_bar && !ready) {
                 const long long t0 = prof ? clock64() : 0;
                 mbar_wait(wait_bar, wait_phase);
                 if (prof) t_wait_full += clock64() - t0;
             }
-            load_frags<MBV>(fa[0], fb[0], next_a, next_b, koff[0]);
+            load_frags<MBV, NBV>(fa[0], fb[0], next_a, next_b, koff[0]);
         }
-        mma_frags<MBV>(acc, fa[kk & 1], fb[kk & 1]);
+        mma_frags<MBV, NBV>(acc, fa[kk & 1], fb[kk & 1]);
     }
 }
 
 // K loop of one pass: n_kblocks K blocks of 16 sizes (the last one with tail_steps k4-steps), KB_PER_STAGE per ring stage.
 // MBV == 0: this warp has no work in the tile, it only keeps the ring moving.
-template <int MBV>
+// blk0: first 8-size block of this warp inside the pass's 128 sizes.
+template <int MBV, int NBV>
 __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned char* stage_base, Ctl* ctl, uint32_t& stage,
-                                             uint32_t& phase, int n_kblocks, int tail_steps, int grp, int nw, int lane, int pg, int q,
+                                             uint32_t& phase, int n_kblocks, int tail_steps, int grp, int blk0, int lane, int pg, int q,
                                              bool prof, long long& t_wait_full, bool nosync) {
     static_assert(KB_PER_STAGE == 2, "the stage loop below is written for two K blocks per stage");
     const int n_stages = (n_kblocks + KB_PER_STAGE - 1) / KB_PER_STAGE;
@@ -569,7 +625,7 @@ __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned 
     int koff[4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) koff[kk] = off0 + (((2 * kk + hi) ^ pg) << 4);
-    const int a_off = grp * (HM * 128), b_off = A_BYTES + nw * WCOLS * 128;
+    const int a_off = grp * (HM * 128), b_off = A_BYTES + blk0 * 8 * 128;
     const int n_full = (tail_steps == 4) ? n_kblocks : n_kblocks - 1;  // K blocks with all four steps
 
     double fa[2][MB], fb[2][NB];
@@ -579,7 +635,7 @@ __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned 
         if (prof) t_wait_full += clock64() - t0;
     }
     const unsigned char* sbase = stage_base + stage * STAGE_BYTES;
-    load_frags<MBV>(fa[0], fb[0], sbase + a_off, sbase + b_off, koff[0]);
+    load_frags<MBV, NBV>(fa[0], fb[0], sbase + a_off, sbase + b_off, koff[0]);
     for (int st = 0; st < n_stages; ++st) {
         uint32_t nstage = stage, nphase = phase;
         advance(nstage, nphase);
@@ -591,20 +647,20 @@ __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned 
         uint64_t* nbar = nosync ? nullptr : &ctl->full[nstage];
         if (kb0 + 2 <= n_full) {
             // two full K blocks; then the next stage (if any)
-            steps_full<MBV, 8>(acc, fa, fb, sa, sb, koff, has_next, nbase + a_off, nbase + b_off, nbar, nphase, prof, t_wait_full);
+            steps_full<MBV, NBV, 8>(acc, fa, fb, sa, sb, koff, has_next, nbase + a_off, nbase + b_off, nbar, nphase, prof, t_wait_full);
         } else {
             // the last stage of the pass: [full block] [partial block], either may be missing
             int kb = kb0;
             if (kb < n_full) {
                 const bool more = kb + 1 < n_kblocks;  // a partial block follows in this stage
-                steps_full<MBV, 4>(acc, fa, fb, sa, sb, koff, more, sa + SUB_BYTES, sb + SUB_BYTES, nullptr, 0, prof, t_wait_full);
+                steps_full<MBV, NBV, 4>(acc, fa, fb, sa, sb, koff, more, sa + SUB_BYTES, sb + SUB_BYTES, nullptr, 0, prof, t_wait_full);
                 ++kb;
             }
             if (kb < n_kblocks && kb >= n_full) {
                 const int j = kb - kb0;
                 for (int kk = 0; kk < tail_steps; ++kk) {
-                    if (kk > 0) load_frags<MBV>(fa[0], fb[0], sa + j * SUB_BYTES, sb + j * SUB_BYTES, off0 + (((2 * kk + hi) ^ pg) << 4));
-                    mma_frags<MBV>(acc, fa[0], fb[0]);
+                    if (kk > 0) load_frags<MBV, NBV>(fa[0], fb[0], sa + j * SUB_BYTES, sb + j * SUB_BYTES, off0 + (((2 * kk + hi) ^ pg) << 4));
+                    mma_frags<MBV, NBV>(acc, fa[0], fb[0]);
                 }
             }
         }
@@ -636,7 +692,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
         coff[0][par] = pg * 128 + ((pcA & 1) << 3) + ((((par << 2) | (pcA >> 1)) ^ pg) << 4);
         coff[1][par] = pg * 128 + ((pcB & 1) << 3) + ((((par << 2) | (pcB >> 1)) ^ pg) << 4);
     }
-    unsigned char* cwarp = Cbuf + (nw * 2) * C_BOX_BYTES + (grp * HM) * 128;
+    unsigned char* cgrp = Cbuf + (grp * HM) * 128;  // a lane's element of block b (of the pass) and 8-family block mb: box b >> 1, parity b & 1
 
     // debug profile (CTA 0): cycles waiting for ring stages / in K loops / waiting for the C tile / in epilogues
     const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
@@ -666,8 +722,20 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                 // running root reduction of one family row of this group, owned by the group's first HM threads
                 double run_ml = -1.0, run_mp = -INFINITY; int run_am = 0x7fffffff;
                 for (int ch = 0; ch < n_chunks; ++ch) {
-                    const int n0 = ch * TN + nw * WCOLS;  // first output size of this warp
-                    const int mbw = (n0 < nrows) ? mbv_t : 0;
+                    // The 8-size blocks of the pass that hold a size < nrows go to the four N-warps of the group: four each in a
+                    // full pass.  A pass with fewer blocks (the last one: 13 at W = 481) is split evenly instead, and group 1
+                    // takes them in an order rotated by two warps - warp nw of both groups runs on SM sub-partition nw, so the
+                    // larger shares of the two groups land on different sub-partitions (4+3, 3+3, 3+4, 3+3 blocks instead of 4+4 x 4).
+                    const int nbl = min(TN / 8, (nrows - ch * TN + 7) >> 3);
+                    int blk0 = 4 * nw, cnt = 4;
+                    if (nbl < TN / 8) {
+                        const int wr = (grp == 0) ? nw : ((nw + 2) & 3);
+                        const int base = nbl >> 2, rem = nbl & 3;
+                        cnt = base + (wr < rem ? 1 : 0);
+                        blk0 = wr * base + min(wr, rem);
+                    }
+                    const int n0 = ch * TN + blk0 * 8;  // first output size of this warp
+                    const int mbw = (cnt > 0) ? mbv_t : 0;
                     double acc[MB][NB][2];
 #pragma unroll
                     for (int mb = 0; mb < MB; ++mb)
@@ -677,15 +745,27 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     const long long tk0 = prof ? clock64() : 0;
                     // experiment knob (CAFE_GPU_SKEW): start group 1 of the very first pass some cycles after group 0
                     if (grp == 1 && P.skew > 0 && item == 0) { const long long t0 = clock64(); while (clock64() - t0 < P.skew) { } }
-#define CAFE_K(MBV_) gemm_kblocks<MBV_>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, nw, lane, pg, q, prof, t_wait_full, (P.dbg & 8) != 0);
-                    switch (mbw) {
-                        case 6: CAFE_K(6) break;
-                        case 5: CAFE_K(5) break;
-                        case 4: CAFE_K(4) break;
-                        case 3: CAFE_K(3) break;
-                        case 2: CAFE_K(2) break;
-                        case 1: CAFE_K(1) break;
-                        default: CAFE_K(0) break;
+#define CAFE_K(MBV_, NBV_) gemm_kblocks<MBV_, NBV_>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, blk0, lane, pg, q, prof, t_wait_full, (P.dbg & 8) != 0);
+                    if (cnt <= 3) {
+                        switch (mbw) {
+                            case 6: CAFE_K(6, 3) break;
+                            case 5: CAFE_K(5, 3) break;
+                            case 4: CAFE_K(4, 3) break;
+                            case 3: CAFE_K(3, 3) break;
+                            case 2: CAFE_K(2, 3) break;
+                            case 1: CAFE_K(1, 3) break;
+                            default: CAFE_K(0, 4) break;
+                        }
+                    } else {
+                        switch (mbw) {
+                            case 6: CAFE_K(6, 4) break;
+                            case 5: CAFE_K(5, 4) break;
+                            case 4: CAFE_K(4, 4) break;
+                            case 3: CAFE_K(3, 4) break;
+                            case 2: CAFE_K(2, 4) break;
+                            case 1: CAFE_K(1, 4) break;
+                            default: CAFE_K(0, 4) break;
+                        }
                     }
 #undef CAFE_K
                     const long long tk1 = prof ? clock64() : 0;
@@ -708,32 +788,41 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                             // all eight factors of this 8-family block first, then the products, then the stores
                             // (shared-memory pointers may alias for the compiler: written out explicitly)
                             double fac[NB][2];
+                            unsigned char* cel[NB][2];  // this lane's two elements of every block
 #pragma unroll
                             for (int nb = 0; nb < NB; ++nb) {
+                                const int b = blk0 + nb;
+                                unsigned char* box = cgrp + (b >> 1) * C_BOX_BYTES + mb * 1024;
+                                cel[nb][0] = box + ((b & 1) ? coff[0][1] : coff[0][0]);
+                                cel[nb][1] = box + ((b & 1) ? coff[1][1] : coff[1][0]);
                                 fac[nb][0] = 1.0; fac[nb][1] = 1.0;
-                                if (other_kind != 0) {
-                                    fac[nb][0] = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[0][nb & 1]);
-                                    fac[nb][1] = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[1][nb & 1]);
+                                if (other_kind != 0 && nb < cnt) {
+                                    fac[nb][0] = *reinterpret_cast<const volatile double*>(cel[nb][0]);
+                                    fac[nb][1] = *reinterpret_cast<const volatile double*>(cel[nb][1]);
                                 }
                             }
                             double out[NB][2];
+                            // sizes >= nrows stay exact zeros: matrix rows in [W, S) are not zero when S > W.  Windowed mode: below
+                            // the root also the sizes above the family's own window (the reference never computes them)
+                            const int lim = (P.colmax && !is_root) ? min(nrows, ctl->colmax[h][grp * HM + mb * 8 + pg] + 1) : nrows;
 #pragma unroll
                             for (int nb = 0; nb < NB; ++nb) {
                                 const double v0 = swp ? acc[mb][nb][1] : acc[mb][nb][0], v1 = swp ? acc[mb][nb][0] : acc[mb][nb][1];
-                                // sizes >= nrows stay exact zeros: matrix rows in [W, S) are not zero when S > W
-                                out[nb][0] = (n0 + nb * 8 + pcA < nrows) ? __dmul_rn(v0, fac[nb][0]) : 0.0;
-                                out[nb][1] = (n0 + nb * 8 + pcB < nrows) ? __dmul_rn(v1, fac[nb][1]) : 0.0;
+                                out[nb][0] = (n0 + nb * 8 + pcA < lim) ? __dmul_rn(v0, fac[nb][0]) : 0.0;
+                                out[nb][1] = (n0 + nb * 8 + pcB < lim) ? __dmul_rn(v1, fac[nb][1]) : 0.0;
                             }
 #pragma unroll
                             for (int nb = 0; nb < NB; ++nb) {
-                                *reinterpret_cast<volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[0][nb & 1]) = out[nb][0];
-                                *reinterpret_cast<volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[1][nb & 1]) = out[nb][1];
+                                if (nb < cnt) {
+                                    *reinterpret_cast<volatile double*>(cel[nb][0]) = out[nb][0];
+                                    *reinterpret_cast<volatile double*>(cel[nb][1]) = out[nb][1];
+                                }
                             }
                         }
                     }
                     // no proxy fence here (MEMBAR.ALL.CTA would drain every store of the warp with the DMMA pipe idle): the arrive
                     // below releases the writes, the epilogue manager acquires them and fences before its TMA store
-                    if (reduce_now && !(P.dbg & 3)) {
+                    if (reduce_now && P.logpost && !(P.dbg & 3)) {
                         // root: L[i] = acc * other; max / first argmax of L and max of log L + log prior (lambda.cpp:670-686).
                         // log is monotonic, so among this lane's eight sizes of a family only the one with the largest product
                         // L * prior can carry the maximum: the products are compared exactly as (exponent sum, mantissa product)
@@ -760,8 +849,9 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
 #pragma unroll
                                     for (int hh = 0; hh < 2; ++hh) {
                                         const int i = n0 + nb * 8 + (hh ? pcB : pcA);
-                                        if (i < nrows) {
-                                            const double v = *reinterpret_cast<const volatile double*>(cwarp + (nb >> 1) * C_BOX_BYTES + mb * 1024 + coff[hh][nb & 1]);
+                                        if (i < nrows && nb < cnt) {
+                                            const int b = blk0 + nb;
+                                            const double v = *reinterpret_cast<const volatile double*>(cgrp + (b >> 1) * C_BOX_BYTES + mb * 1024 + ((b & 1) ? coff[hh][1] : coff[hh][0]));
                                             const long long vb = __double_as_longlong(v);
                                             if (vb > ml || (vb == ml && i < am)) { ml = vb; am = i; }
                                             if (vb > 0) {
@@ -800,7 +890,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         tl[0] = tk0; tl[1] = tk1; tl[2] = tk2; tl[3] = tk2b;
                     }
                     if (prof) { t_kloop += tk1 - tk0; t_wait_c += tk2 - tk1; t_epi += tk2b - tk2; if (flags & 2) t_kloop_cherry += tk1 - tk0; if (reduce_now) t_epi_root += tk2b - tk2; }
-                    if (reduce_now && !(P.dbg & 3)) {
+                    if (reduce_now && P.logpost && !(P.dbg & 3)) {
                         group_bar(grp);
                         if (nw * 32 + lane < HM) {  // the first HM threads of the group own one family row each
                             const int row = nw * 32 + lane;
@@ -1019,6 +1109,14 @@ static void build_schedule2(const cafe_gpu_ctx* ctx, Fused2State& st) {
 }
 
 int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
+    Fused2Job job;
+    job.counts = ctx->d_counts; job.leaf_stride = (size_t)ctx->F_pad; job.F = ctx->F; job.F_pad = ctx->F_pad;
+    job.root_r0 = ctx->root_min; job.root_rows = ctx->R;
+    job.posterior = true; job.d_Lroot_out = d_Lroot_out;
+    return launch_prune_fused2_job(ctx, job);
+}
+
+int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
     using namespace fused2;
     Fused2State& st = fstate2(ctx);
     PFN_encodeTiled2 encode = get_encode_fn2();
@@ -1047,7 +1145,7 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     CAFE_CK(ctx, cudaGetLastError());
 
     // ---- geometry: one CTA per SM, every CTA at least two 8-family blocks ----
-    const int n_mblocks = (ctx->F + 7) / 8;
+    const int n_mblocks = (job.F + 7) / 8;
     const int grid = std::max(1, std::min(ctx->sm_count, (n_mblocks + 1) / 2));
     const size_t cta_rows = (size_t)(2 * st.n_slots + 4 * st.n_cherry) * TILE_M;
     const size_t scratch_doubles = (size_t)grid * cta_rows * ctx->Vp;
@@ -1080,12 +1178,18 @@ int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out) {
     }
 
     Params P{};
-    P.ops = st.d_ops; P.n_ops = (int)st.ops.size(); P.n_slots = st.n_slots; P.n_cherry = st.n_cherry; P.F = ctx->F; P.F_pad = ctx->F_pad;
+    P.ops = st.d_ops; P.n_ops = (int)st.ops.size(); P.n_slots = st.n_slots; P.n_cherry = st.n_cherry; P.F = job.F; P.F_pad = job.F_pad;
     P.scratch = st.d_scratch;
-    P.W = ctx->W; P.R = ctx->R; P.root_min = ctx->root_min; P.Sp = ctx->Sp; P.Vp = ctx->Vp; P.n_mblocks = n_mblocks;
-    P.MT = ctx->d_MT; P.counts = ctx->d_counts; P.logprior = ctx->d_logprior;
-    P.prior_mant = ctx->d_prior_mant; P.prior_exp = ctx->d_prior_exp;
-    P.logpost = ctx->d_logpost; P.maxlik = ctx->d_maxlik; P.argmax = ctx->d_argmax; P.Lroot_out = d_Lroot_out;
+    P.W = ctx->W; P.R = job.root_rows; P.root_min = job.root_r0; P.Sp = ctx->Sp; P.Vp = ctx->Vp; P.n_mblocks = n_mblocks;
+    P.MT = ctx->d_MT; P.counts = job.counts; P.leaf_stride = job.leaf_stride;
+    P.colmax = job.d_colmax; P.root_pick = job.d_root_pick; P.L0_out = job.d_L0_out;
+    if (job.posterior) {
+        P.logprior = ctx->d_logprior; P.prior_mant = ctx->d_prior_mant; P.prior_exp = ctx->d_prior_exp;
+        P.logpost = ctx->d_logpost; P.maxlik = ctx->d_maxlik; P.argmax = ctx->d_argmax;
+    }
+    P.Lroot_out = job.d_Lroot_out;
+    if (job.root_rows > ctx->Vp || job.root_r0 + job.root_rows > ctx->Sp)
+        CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "fused pruning: root rows exceed the vector / matrix");
 
     if (const char* d = std::getenv("CAFE_GPU_DBG")) P.dbg = std::atoi(d);
     P.skew = 0;  // measured: no effect for 0..9000 cycles (profiles/r1_k2_experiments.md)

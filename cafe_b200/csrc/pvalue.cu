@@ -8,6 +8,7 @@
 //   viterbi_set_max_pvalue (cafe/viterbi.cpp:32-39): max over s, 0 for an empty root range
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -39,7 +40,7 @@ __device__ __forceinline__ double pvalue_dev(double v, const double* __restrict_
 
 // one warp per family: lanes take root sizes s, warp-max of the p-values
 __global__ void __launch_bounds__(256)
-k_family_pvalue(const double* __restrict__ Lroot, int Vp, int F, const int* __restrict__ rfsize, const double* __restrict__ cd,
+k_family_pvalue(const double* __restrict__ Lroot, size_t Vp, int F, const int* __restrict__ rfsize, const double* __restrict__ cd,
                 int cd_rows, int n_samples, double* __restrict__ out) {
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (f >= F) return;
@@ -69,8 +70,8 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
     if (rf_max > ctx->Vp || 1 + rf_max > ctx->S)
         CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "pvalues: a family's root range rint(1.25*max) exceeds the matrices (set_ranges from the table's max first)");
     int *d_colmax = nullptr, *d_rf = nullptr;
-    double *d_cd = nullptr, *d_out = nullptr;
-    auto cleanup = [&]() { cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_cd); cudaFree(d_out); };
+    double *d_cd = nullptr, *d_out = nullptr, *d_Lroot = nullptr;
+    auto cleanup = [&]() { cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_cd); cudaFree(d_out); cudaFree(d_Lroot); };
 #define PV_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
     PV_CK(cudaMalloc(&d_colmax, ctx->F_pad * sizeof(int)));
     PV_CK(cudaMalloc(&d_rf, ctx->F_pad * sizeof(int)));
@@ -79,14 +80,31 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
     PV_CK(cudaMemcpyAsync(d_colmax, colmax.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PV_CK(cudaMemcpyAsync(d_rf, rfsize.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PV_CK(cudaMemcpyAsync(d_cd, cd, (size_t)cd_rows * n_samples * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    int rc = ensure_vec_buffers(ctx, ctx->F_pad);
-    if (rc) { cleanup(); return rc; }
-    int root_slot = -1;
     // root rows 1..rf_max for everybody (rows beyond a family's own range are ignored by k_family_pvalue)
-    rc = launch_prune_ops(ctx, ctx->d_counts, ctx->F_pad, F, ctx->F_pad, d_colmax, 1, std::min(rf_max, ctx->S - 1), false, &root_slot);
-    if (rc) { cleanup(); return rc; }
-    const double* Lroot = ctx->d_vec + (size_t)root_slot * ctx->F_pad * ctx->Vp;
-    k_family_pvalue<<<(F + 7) / 8, 256, 0, ctx->stream>>>(Lroot, ctx->Vp, F, d_rf, d_cd, cd_rows, n_samples, d_out);
+    const int root_rows = std::min(rf_max, ctx->S - 1);
+    const double* Lroot = nullptr;
+    size_t Lstride = 0;
+    int rc = CAFE_GPU_OK;
+    if (root_rows >= 1 && fused2_windowed_supported(ctx) && std::getenv("CAFE_GPU_NO_FUSED") == nullptr) {
+        // the fused kernel in windowed mode: every family with its own forced range, all root rows copied out
+        PV_CK(cudaMalloc(&d_Lroot, (size_t)F * root_rows * sizeof(double)));
+        Fused2Job job;
+        job.counts = ctx->d_counts; job.leaf_stride = (size_t)ctx->F_pad; job.F = F; job.F_pad = ctx->F_pad;
+        job.d_colmax = d_colmax;
+        job.root_r0 = 1; job.root_rows = root_rows;
+        job.d_Lroot_out = d_Lroot;
+        rc = launch_prune_fused2_job(ctx, job);
+        if (rc) { cleanup(); return rc; }
+        Lroot = d_Lroot; Lstride = (size_t)root_rows;
+    } else {
+        rc = ensure_vec_buffers(ctx, ctx->F_pad);
+        if (rc) { cleanup(); return rc; }
+        int root_slot = -1;
+        rc = launch_prune_ops(ctx, ctx->d_counts, ctx->F_pad, F, ctx->F_pad, d_colmax, 1, root_rows, false, &root_slot);
+        if (rc) { cleanup(); return rc; }
+        Lroot = ctx->d_vec + (size_t)root_slot * ctx->F_pad * ctx->Vp; Lstride = (size_t)ctx->Vp;
+    }
+    k_family_pvalue<<<(F + 7) / 8, 256, 0, ctx->stream>>>(Lroot, Lstride, F, d_rf, d_cd, cd_rows, n_samples, d_out);
     ctx->launches++;
     PV_CK(cudaGetLastError());
     PV_CK(cudaMemcpyAsync(out, d_out, F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -170,3 +170,35 @@ def test_k4_k5_config5_full_size_properties():
     g2 = Problem(nw, counts[perm], lam0, prior_lambda=60.0, ranges=(0, 480, 1, 500)).make_gpu()
     assert np.array_equal(g2.pvalues(cd), pv[perm])
     g2.close()
+
+
+def test_k4_k5_fused_windowed_path_equals_per_node_kernels(monkeypatch):
+    # K4 / K5 prune with per-family column windows.  The fused kernel (prune_fused2.cu, windowed mode) and the per-node
+    # kernels (prune.cu) must agree: same simulated sizes (same device generator), likelihoods to summation order, and the
+    # p-values they give identical up to ties.
+    nw = oracle.random_tree(11, 4)
+    rng = np.random.RandomState(9)
+    base = rng.randint(1, 40, size=(700, 1))
+    counts = np.maximum(0, base + rng.randint(-4, 5, size=(700, 11))).astype(np.int32)
+    counts[5] = 0                      # an all-zero family: empty root range in the forced range of K5
+    counts[6, 3] = 140                 # one leaf far above the others: wide window, most leaves deep in the tails
+    p = Problem(nw, counts, 0.006, mu=0.005)
+    g = p.make_gpu()
+    n = 300
+    cd_fused = g.conditional_distribution(n, seed=3)
+    pv_fused = g.pvalues(cd_fused)
+    monkeypatch.setenv("CAFE_GPU_NO_FUSED", "1")
+    cd_node = g.conditional_distribution(n, seed=3)
+    pv_node = g.pvalues(cd_fused)
+    monkeypatch.delenv("CAFE_GPU_NO_FUSED")
+    big = cd_node > 1e-290
+    assert big.mean() > 0.5
+    assert rel_err(cd_fused[big], cd_node[big]).max() < 1e-12
+    assert np.abs(pv_fused - pv_node).max() <= 1.0 / n + 1e-12 and (pv_fused == pv_node).mean() > 0.99
+    assert pv_fused[5] == 0.0
+    # and against the oracle on a sample (its distribution argument is the GPU's own: the draws differ from glibc's)
+    mats = [None if v == p.otree.root else g.get_matrix(v) for v in range(p.otree.n_nodes)]
+    idx = [0, 1, 5, 6, 17, 123, 699]
+    ref = np.array([oracle.family_pvalue(p.otree, mats, counts[f], cd_fused)[0] for f in idx])
+    assert np.abs(pv_fused[idx] - ref).max() <= 1.0 / n + 1e-12
+    g.close()
