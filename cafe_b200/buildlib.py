@@ -8,7 +8,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-GPU_LIB = os.path.join(HERE, "libcafe_gpu.so")
+GPU_LIB = os.environ.get("CAFE_GPU_LIB") or os.path.join(HERE, "libcafe_gpu.so")  # CAFE_GPU_LIB: an A/B build (tools/k2_variants.sh)
 HOST_LIB = os.path.join(HERE, "libcafe_host.so")
 SHELL_BIN = os.path.join(HERE, "cafe_gpu_shell")
 STAMP = os.path.join(HERE, "build", ".sources.sha1")
@@ -31,6 +31,7 @@ def build(verbose: bool = False) -> None:
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
         fcntl.flock(lock, fcntl.LOCK_EX)  # one builder at a time (torchrun starts one process per GPU)
+        # -z defs: an undefined symbol fails the link of the library here, not the load on the GPU box
         subprocess.run(["make", "-j8", "-C", os.path.join(HERE, "csrc")], check=True, stdout=out)
         subprocess.run(["make", "-j8", "-C", os.path.join(HERE, "host")], check=True, stdout=out)
         with open(STAMP, "w") as fp:

@@ -82,7 +82,7 @@ static void destroy_one(cafe_gpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     comm_release(ctx);
-    cudaFree(ctx->d_score_all); cudaFree(ctx->d_score_final);
+    cudaFree(ctx->d_score_all); cudaFree(ctx->d_score_final); cudaFree(ctx->d_Lroot_cache);
     cudaFree(ctx->d_lnc); cudaFree(ctx->d_lncT); cudaFree(ctx->d_counts); cudaFree(ctx->d_mult); cudaFree(ctx->d_first);
     cudaFree(ctx->d_logprior); cudaFree(ctx->d_prior_mant); cudaFree(ctx->d_prior_exp); cudaFree(ctx->d_keyparams); cudaFree(ctx->d_M); cudaFree(ctx->d_MT); cudaFree(ctx->d_vec);
     cudaFree(ctx->d_logpost); cudaFree(ctx->d_maxlik); cudaFree(ctx->d_argmax); cudaFree(ctx->d_score);

@@ -140,6 +140,8 @@ struct cafe_gpu_ctx {
     double* h_score = nullptr;    // pinned [2]
     bool results_valid = false;
 
+    double* d_Lroot_cache = nullptr;  // root likelihood rows of all families, grown on demand (p-values)
+    size_t Lroot_cache_cap = 0;
     void* fused_state = nullptr;   // prune_fused.cu private state (device schedule, scratch)
     void* fused2_state = nullptr;  // prune_fused2.cu private state
 

@@ -31,6 +31,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -311,6 +312,7 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
 // of tiles into dedicated scratch slots while the DMMA warps work on the current pair - a whole pair of tiles (milliseconds)
 // of slack, no coupling to the ring, one product per element.  The parent's GEMM then streams the slot like any other vector.
 // Gatherer gi owns the tile rows [48 gi, 48 gi + 48); a warp handles two rows at a time, lanes along the sizes.
+template <bool WIN>
 __device__ __forceinline__ void gatherer_main(const Params& P, double* scratch, Ctl* ctl, int gi) {
     const TilePlan plan(P);
     const int lane = threadIdx.x & 31;
@@ -344,7 +346,7 @@ __device__ __forceinline__ void gatherer_main(const Params& P, double* scratch, 
                         // sizes >= W stay exact zeros (the vector has length W although the matrices are wider when S > W); with a
                         // per-family window also the sizes above it, and the whole vector when a leaf lies outside the window
                         wlim[u] = P.W;
-                        if (P.colmax) {
+                        if (WIN) {
                             const int cm = __ldg(P.colmax + fc);
                             wlim[u] = (ca <= cm && cb <= cm) ? min(P.W, cm + 1) : 0;
                         }
@@ -386,7 +388,7 @@ __device__ __forceinline__ void gatherer_main(const Params& P, double* scratch, 
 }
 
 // ================================ epilogue manager (1 warp) ================================ ================================
-template <bool PROF>
+template <bool PROF, bool WIN>
 __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Params& P, unsigned char* Cbuf, Ctl* ctl) {
     const TilePlan plan(P);
     const int lane = threadIdx.x & 31;
@@ -399,7 +401,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
     long long t_prep = 0, t_wait_cdone = 0, t_store = 0;
     const long long t_begin = prof ? clock64() : 0;
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
-        if (P.colmax || P.root_pick) {
+        if (WIN) {
             // windowed mode: the windows / root picks of the rows of this pair's tiles (every consumer has left the previous pair:
             // its last pass was handed back through c_done before this point)
             __syncwarp();
@@ -408,7 +410,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                 if (!plan.tile(2 * pair + h, mb0, m)) continue;
                 for (int r = lane; r < TILE_M; r += 32) {
                     const int f = TilePlan::family(mb0, m, r, P.F);
-                    ctl->colmax[h][r] = P.colmax ? __ldg(P.colmax + f) : 0x7fffffff;
+                    ctl->colmax[h][r] = __ldg(P.colmax + f);
                     ctl->pick[h][r] = P.root_pick ? __ldg(P.root_pick + f) - P.root_min : -1;
                 }
             }
@@ -430,7 +432,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                         const int f = TilePlan::family(mb0, m, r, P.F);
                         const int cnt = __ldg(P.counts + (size_t)op.leaf_o * P.leaf_stride + f);
                         // a leaf outside the family's window has factor 0 (the one-hot entry is not part of the vector)
-                        ctl->rowoff_o[r] = (P.colmax && cnt > __ldg(P.colmax + f)) ? -1 : cnt * P.Sp;
+                        ctl->rowoff_o[r] = (WIN && cnt > __ldg(P.colmax + f)) ? -1 : cnt * P.Sp;
                     }
                     __syncwarp();
                 }
@@ -507,7 +509,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                     } else {
                         // ... or, at the root (reduced by the consumers), is only copied out on request
                         const int ncols = min(TN, nrows - ch * TN);
-                        if (P.root_pick) {  // the distribution's root range {s}: one likelihood per simulated family
+                        if (WIN && P.root_pick) {  // the distribution's root range {s}: one likelihood per simulated family
                             for (int r = lane; r < TILE_M; r += 32) {
                                 const int f = TilePlan::family_or_neg(mb0, m, r, P.F);
                                 const int c = ctl->pick[h][r] - ch * TN;
@@ -670,7 +672,7 @@ __device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned 
     }
 }
 
-template <bool PROF>
+template <bool PROF, bool WIN>
 __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* stage_base, unsigned char* Cbuf, Ctl* ctl) {
     const TilePlan plan(P);
     const int warp = (threadIdx.x >> 5) - N_AUX_WARPS, lane = threadIdx.x & 31;  // consumer warp 0..7
@@ -781,44 +783,53 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                             for (int nb = 0; nb < NB; ++nb) sum += acc[mb][nb][0] + acc[mb][nb][1];
                         if (sum == 1.2345e-300) P.logpost[0] = sum;
                     }
-                    if (!(P.dbg & 3))
+                    // FULL: the warp owns the four blocks 4 nw .. 4 nw + 3 of the pass (every pass but a partial last one): block
+                    // indices and guards are compile-time constants, the code of the common case is what it was before partial passes
+                    auto multiply_in_place = [&](auto full_c) {
+                        constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
-                    for (int mb = 0; mb < MB; ++mb) {
-                        if (mb < mbw) {
-                            // all eight factors of this 8-family block first, then the products, then the stores
-                            // (shared-memory pointers may alias for the compiler: written out explicitly)
-                            double fac[NB][2];
-                            unsigned char* cel[NB][2];  // this lane's two elements of every block
+                        for (int mb = 0; mb < MB; ++mb) {
+                            if (mb < mbw) {
+                                // all eight factors of this 8-family block first, then the products, then the stores
+                                // (shared-memory pointers may alias for the compiler: written out explicitly)
+                                double fac[NB][2];
+                                unsigned char* cel[NB][2];  // this lane's two elements of every block
 #pragma unroll
-                            for (int nb = 0; nb < NB; ++nb) {
-                                const int b = blk0 + nb;
-                                unsigned char* box = cgrp + (b >> 1) * C_BOX_BYTES + mb * 1024;
-                                cel[nb][0] = box + ((b & 1) ? coff[0][1] : coff[0][0]);
-                                cel[nb][1] = box + ((b & 1) ? coff[1][1] : coff[1][0]);
-                                fac[nb][0] = 1.0; fac[nb][1] = 1.0;
-                                if (other_kind != 0 && nb < cnt) {
-                                    fac[nb][0] = *reinterpret_cast<const volatile double*>(cel[nb][0]);
-                                    fac[nb][1] = *reinterpret_cast<const volatile double*>(cel[nb][1]);
+                                for (int nb = 0; nb < NB; ++nb) {
+                                    const int boxi = FULL ? (2 * nw + (nb >> 1)) : ((blk0 + nb) >> 1);
+                                    const int par = FULL ? (nb & 1) : ((blk0 + nb) & 1);
+                                    unsigned char* box = cgrp + boxi * C_BOX_BYTES + mb * 1024;
+                                    cel[nb][0] = box + (par ? coff[0][1] : coff[0][0]);
+                                    cel[nb][1] = box + (par ? coff[1][1] : coff[1][0]);
+                                    fac[nb][0] = 1.0; fac[nb][1] = 1.0;
+                                    if (other_kind != 0 && (FULL || nb < cnt)) {
+                                        fac[nb][0] = *reinterpret_cast<const volatile double*>(cel[nb][0]);
+                                        fac[nb][1] = *reinterpret_cast<const volatile double*>(cel[nb][1]);
+                                    }
                                 }
-                            }
-                            double out[NB][2];
-                            // sizes >= nrows stay exact zeros: matrix rows in [W, S) are not zero when S > W.  Windowed mode: below
-                            // the root also the sizes above the family's own window (the reference never computes them)
-                            const int lim = (P.colmax && !is_root) ? min(nrows, ctl->colmax[h][grp * HM + mb * 8 + pg] + 1) : nrows;
+                                double out[NB][2];
+                                // sizes >= nrows stay exact zeros: matrix rows in [W, S) are not zero when S > W.  Windowed mode: below
+                                // the root also the sizes above the family's own window (the reference never computes them)
+                                const int lim = (WIN && !is_root) ? min(nrows, ctl->colmax[h][grp * HM + mb * 8 + pg] + 1) : nrows;
 #pragma unroll
-                            for (int nb = 0; nb < NB; ++nb) {
-                                const double v0 = swp ? acc[mb][nb][1] : acc[mb][nb][0], v1 = swp ? acc[mb][nb][0] : acc[mb][nb][1];
-                                out[nb][0] = (n0 + nb * 8 + pcA < lim) ? __dmul_rn(v0, fac[nb][0]) : 0.0;
-                                out[nb][1] = (n0 + nb * 8 + pcB < lim) ? __dmul_rn(v1, fac[nb][1]) : 0.0;
-                            }
+                                for (int nb = 0; nb < NB; ++nb) {
+                                    const double v0 = swp ? acc[mb][nb][1] : acc[mb][nb][0], v1 = swp ? acc[mb][nb][0] : acc[mb][nb][1];
+                                    out[nb][0] = (n0 + nb * 8 + pcA < lim) ? __dmul_rn(v0, fac[nb][0]) : 0.0;
+                                    out[nb][1] = (n0 + nb * 8 + pcB < lim) ? __dmul_rn(v1, fac[nb][1]) : 0.0;
+                                }
 #pragma unroll
-                            for (int nb = 0; nb < NB; ++nb) {
-                                if (nb < cnt) {
-                                    *reinterpret_cast<volatile double*>(cel[nb][0]) = out[nb][0];
-                                    *reinterpret_cast<volatile double*>(cel[nb][1]) = out[nb][1];
+                                for (int nb = 0; nb < NB; ++nb) {
+                                    if (FULL || nb < cnt) {
+                                        *reinterpret_cast<volatile double*>(cel[nb][0]) = out[nb][0];
+                                        *reinterpret_cast<volatile double*>(cel[nb][1]) = out[nb][1];
+                                    }
                                 }
                             }
                         }
+                    };
+                    if (!(P.dbg & 3)) {
+                        if (cnt == 4 && blk0 == 4 * nw) multiply_in_place(std::true_type{});
+                        else multiply_in_place(std::false_type{});
                     }
                     // no proxy fence here (MEMBAR.ALL.CTA would drain every store of the warp with the DMMA pipe idle): the arrive
                     // below releases the writes, the epilogue manager acquires them and fences before its TMA store
@@ -917,7 +928,9 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
     }
 }
 
-template <bool PROF>
+// WIN: windowed mode (Params::colmax set): per-family column windows and root picks, for the conditional distribution and the
+// p-values.  A separate instantiation, so that the score path carries none of it (measured: 0.8 % of a launch otherwise).
+template <bool PROF, bool WIN>
 __global__ void __launch_bounds__(THREADS, 1)
 k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
     extern __shared__ unsigned char smem_raw[];
@@ -944,13 +957,13 @@ k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp < N_AUX_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
         if (warp == 0) { if ((threadIdx.x & 31) == 0) producer_main<PROF>(&tmA, &tmB, P, stage_base, ctl); }
-        else if (warp == 3) cmanager_main<PROF>(&tmA, P, Cbuf, ctl);
-        else gatherer_main(P, P.scratch, ctl, warp - 1);
+        else if (warp == 3) cmanager_main<PROF, WIN>(&tmA, P, Cbuf, ctl);
+        else gatherer_main<WIN>(P, P.scratch, ctl, warp - 1);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_CONSUMER));
         long long t_start = 0;
         if (P.cta_times && threadIdx.x == N_AUX_WARPS * 32) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-        consumer_main<PROF>(P, stage_base, Cbuf, ctl);
+        consumer_main<PROF, WIN>(P, stage_base, Cbuf, ctl);
         if (P.cta_times && threadIdx.x == N_AUX_WARPS * 32) {
             long long t_end; unsigned smid;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -1020,11 +1033,23 @@ void fused2_release(cafe_gpu_ctx* ctx) {
     ctx->fused2_state = nullptr;
 }
 
-bool fused2_supported(const cafe_gpu_ctx* ctx) {
+static bool fused2_tree_supported(const cafe_gpu_ctx* ctx) {
     if (get_encode_fn2() == nullptr) return false;
     if (ctx->n_leaves < 3) return false;                 // the root of a two-leaf tree is itself a leaf pair
     if (ctx->n_nodes > fused2::OPFLAGS_CAP) return false;
+    return true;
+}
+bool fused2_supported(const cafe_gpu_ctx* ctx) {
+    if (!fused2_tree_supported(ctx)) return false;
     if (ctx->max_count >= ctx->W) return false;          // a one-hot leaf outside the matvec columns needs the guarded path
+    return true;
+}
+// windowed jobs (conditional distribution, p-values): leaves outside a family's window are handled by the window itself, but
+// an error-model leaf would need one matrix per window (k_err_leaf_matrix sums over the columns up to the window)
+bool fused2_windowed_supported(const cafe_gpu_ctx* ctx) {
+    if (!fused2_tree_supported(ctx)) return false;
+    for (int e : ctx->leaf_err)
+        if (e >= 0) return false;
     return true;
 }
 
@@ -1196,8 +1221,9 @@ int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
     if (const char* d = std::getenv("CAFE_GPU_SKEW")) P.skew = std::atoi(d);
     const size_t smem_bytes = (size_t)NSTAGE * STAGE_BYTES + C_BYTES + sizeof(Ctl) + 1024;
     if (!st.attr_set) {
-        CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         st.attr_set = true;
     }
     const char* trace_path = std::getenv("CAFE_GPU_TRACE");
@@ -1209,8 +1235,11 @@ int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
         P.warp_prof = d_trace + (size_t)grid * 4;
         P.timeline = P.warp_prof + 128;
     }
-    if (trace_path) k_prune_fused2<true><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
-    else k_prune_fused2<false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
+    const bool windowed = job.d_colmax != nullptr;
+    if (job.d_root_pick && !windowed) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "fused pruning: a root pick needs the per-family windows");
+    if (windowed) k_prune_fused2<false, true><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
+    else if (trace_path) k_prune_fused2<true, false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
+    else k_prune_fused2<false, false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
     ctx->launches++;
     CAFE_CK(ctx, cudaGetLastError());
     if (trace_path) {  // debug only: synchronous dump "cta <i> <smid> <start ns> <end ns> <8-family blocks>"

@@ -70,8 +70,8 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
     if (rf_max > ctx->Vp || 1 + rf_max > ctx->S)
         CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "pvalues: a family's root range rint(1.25*max) exceeds the matrices (set_ranges from the table's max first)");
     int *d_colmax = nullptr, *d_rf = nullptr;
-    double *d_cd = nullptr, *d_out = nullptr, *d_Lroot = nullptr;
-    auto cleanup = [&]() { cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_cd); cudaFree(d_out); cudaFree(d_Lroot); };
+    double *d_cd = nullptr, *d_out = nullptr;
+    auto cleanup = [&]() { cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_cd); cudaFree(d_out); };
 #define PV_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
     PV_CK(cudaMalloc(&d_colmax, ctx->F_pad * sizeof(int)));
     PV_CK(cudaMalloc(&d_rf, ctx->F_pad * sizeof(int)));
@@ -87,7 +87,13 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
     int rc = CAFE_GPU_OK;
     if (root_rows >= 1 && fused2_windowed_supported(ctx) && std::getenv("CAFE_GPU_NO_FUSED") == nullptr) {
         // the fused kernel in windowed mode: every family with its own forced range, all root rows copied out
-        PV_CK(cudaMalloc(&d_Lroot, (size_t)F * root_rows * sizeof(double)));
+        const size_t need = (size_t)F * root_rows;
+        if (need > ctx->Lroot_cache_cap) {  // kept across calls: a malloc / free pair of this size costs more than the pass itself
+            cudaFree(ctx->d_Lroot_cache); ctx->d_Lroot_cache = nullptr; ctx->Lroot_cache_cap = 0;
+            PV_CK(cudaMalloc(&ctx->d_Lroot_cache, need * sizeof(double)));
+            ctx->Lroot_cache_cap = need;
+        }
+        double* d_Lroot = ctx->d_Lroot_cache;
         Fused2Job job;
         job.counts = ctx->d_counts; job.leaf_stride = (size_t)ctx->F_pad; job.F = F; job.F_pad = ctx->F_pad;
         job.d_colmax = d_colmax;
