@@ -35,6 +35,20 @@
 
 #include "common.cuh"
 
+// Timing ablations (results are garbage), compiled in only for A/B builds (tools/k2_variants.sh "-DCAFE_K2_ABLATE"): the hot loops
+// of the product build carry no test of Params::dbg.  CAFE_GPU_DBG bits: 1 no epilogue work, 2 no epilogue at all, 4 no store.
+// -DCAFE_K2_NOSYNC: no ring at all (K loops on whatever is in shared memory, no producer).
+#ifdef CAFE_K2_ABLATE
+#define K2_DBG(bits) ((P.dbg & (bits)) != 0)
+#else
+#define K2_DBG(bits) false
+#endif
+#ifdef CAFE_K2_NOSYNC
+#define K2_DBG_NOSYNC true
+#else
+#define K2_DBG_NOSYNC false
+#endif
+
 namespace fused2 {
 
 constexpr int GM = 2;                  // M-groups (consumer warpgroups): exactly two DMMA warps per SM sub-partition
@@ -96,7 +110,7 @@ struct Params {
     int* argmax;
     double* Lroot_out;           // nullable, [F][R]
     int skew;                    // cycles group 1 starts every K loop after group 0 (see consumer_main)
-    int dbg;                     // debug ablations (CAFE_GPU_DBG, results are garbage): 1 no epilogue work, 2 no epilogue at all, 4 no store, 8 no ring (K loops on whatever is in shared memory)
+    int dbg;                     // timing ablations, honoured by -DCAFE_K2_ABLATE builds only (see K2_DBG above)
     long long* cta_times;        // nullable debug: [grid][4] = smid, start ns, end ns, 8-family blocks
     long long* warp_prof;        // nullable debug: CTA 0, [16 warps][8] cycle sums (see consumer_main / producer_main)
     long long* timeline;         // nullable debug: CTA 0, warps 0 and 4 (one sub-partition): [2][1024 items][4] clock stamps
@@ -251,7 +265,7 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
     const TilePlan plan(P);
     const int scratch_row0 = blockIdx.x * cta_rows(P);
     const int n_kblocks = (P.W + BK - 1) / BK;
-    if (P.dbg & 8) return;
+    if (K2_DBG_NOSYNC) return;
     uint32_t stage = 0, phase = 0;
     int ops_done_base = 0;
     const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
@@ -269,7 +283,7 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
                 if (op.a_kind == 0) {
                     // the vector to stream was stored by an earlier op of this tile: wait until it is visible
                     const long long t0 = prof ? clock64() : 0;
-                    while (!(P.dbg & 2) && ctl->done[h] < ops_done_base + oi) { __nanosleep(20); }
+                    while (!K2_DBG(2) && ctl->done[h] < ops_done_base + oi) { __nanosleep(20); }
                     __threadfence_block();
                     fence_proxy_async();
                     if (prof) t_wait_done += clock64() - t0;
@@ -316,14 +330,14 @@ template <bool WIN>
 __device__ __forceinline__ void gatherer_main(const Params& P, double* scratch, Ctl* ctl, int gi) {
     const TilePlan plan(P);
     const int lane = threadIdx.x & 31;
-    if (P.n_cherry == 0 || (P.dbg & 8)) return;
+    if (P.n_cherry == 0 || K2_DBG_NOSYNC) return;
     double* cta_scratch = scratch + (size_t)blockIdx.x * cta_rows(P) * P.Vp;
     const int n_pieces = (P.W + 1) / 2;  // 16-byte pieces of a vector that hold a size < W
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
         // slot set (pair & 1) was last read by pair - 2: wait until pair - 1 has completed an op (then pair - 2 is over)
         if (pair >= 2) {
             const int need = (pair - 1) * P.n_ops + 1;
-            while (!(P.dbg & 2) && ctl->done[0] < need) { __nanosleep(500); }
+            while (!K2_DBG(2) && ctl->done[0] < need) { __nanosleep(500); }
             __threadfence_block();
         }
         for (int oi = 0; oi < P.n_ops; ++oi) {
@@ -394,7 +408,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
     const int lane = threadIdx.x & 31;
     const int scratch_row0 = blockIdx.x * cta_rows(P);
     const uint32_t sC = smem_u32(Cbuf);
-    if (P.dbg & 2) return;
+    if (K2_DBG(2)) return;
     uint32_t item = 0;
     int ops_done_base = 0;
     const bool prof = PROF && P.warp_prof != nullptr && blockIdx.x == 0;
@@ -500,7 +514,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                     const long long tc2 = prof ? clock64() : 0;
                     if (!reduce_now) {
                         // ... then the tile goes back to the scratch slot
-                        if (lane == 0 && !(P.dbg & 4)) {
+                        if (lane == 0 && !K2_DBG(4)) {
                             fence_proxy_async_smem();  // consumer writes (generic proxy, acquired above) -> TMA store (async proxy)
                             for (int b = 0; b < nbx; ++b) tma_store_2d(tmA, ch * TN + b * BK, out_row, Cbuf + b * C_BOX_BYTES);
                             bulk_commit();
@@ -545,17 +559,70 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
     }
 }
 
-// ================================ warps 0..7: DMMA consumers ================================
-// Fragments of one k4-step: 4 B fragments and one A fragment per 8-family block.
+// ================================ warps 4..11: DMMA consumers ================================
+// Shared-memory accesses of the K loops go through 32-bit shared addresses with compile-time offsets (LDS [R + imm]): a lane keeps
+// eight address registers per ring stage (A and B, one per k4-step of a K block: the swizzle term differs per step) and nothing
+// else is recomputed at a stage boundary.  Written with generic pointers the compiler rematerialised the whole address chain
+// (thread id, shared window base, alignment, swizzle) at every stage to stay inside the register budget: ~70 instructions with
+// special-register and constant-bank latencies between the last DMMA of a stage and the first of the next, for both DMMA warps
+// of a sub-partition at once (profiles/r2_k2_experiments.md).
+template <int IMM>
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// non-blocking probe of an mbarrier phase: issued a few k4-steps before the result is needed
+__device__ __forceinline__ uint32_t mbar_test_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// one arrival per warp, by an elected lane (no thread-id read, no predicate register to keep alive across the K loop)
+__device__ __forceinline__ void mbar_arrive_elect_u32(uint32_t bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(bar) : "memory");
+}
+// a value the compiler must keep in a register instead of recomputing it from special registers at every use
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+// Fragments of one k4-step: NBV B fragments and one A fragment per 8-family block, OFF = byte offset of the K block in the stage.
 // NBV: 8-size blocks of this warp in the pass (4, or 3 in a pass whose blocks do not divide by 4, see consumer_main)
-template <int MBV, int NBV>
-__device__ __forceinline__ void load_frags(double (&fa)[MB], double (&fb)[NB], const unsigned char* sA, const unsigned char* sB, int off) {
-#pragma unroll
-    for (int nb = 0; nb < NBV; ++nb) fb[nb] = *reinterpret_cast<const double*>(sB + nb * 1024 + off);
-#pragma unroll
-    for (int mb = 0; mb < MBV; ++mb) {
-        fa[mb] = *reinterpret_cast<const double*>(sA + mb * 1024 + off);
-    }
+template <int MBV, int NBV, int OFF>
+__device__ __forceinline__ void load_frags(double (&fa)[MB], double (&fb)[NB], uint32_t pa, uint32_t pb) {
+#define CAFE_LDB(nb_) if (nb_ < NBV) fb[nb_] = lds_f64<OFF + nb_ * 1024>(pb);
+    CAFE_LDB(0) CAFE_LDB(1) CAFE_LDB(2) CAFE_LDB(3)
+#undef CAFE_LDB
+#define CAFE_LDA(mb_) if (mb_ < MBV) fa[mb_] = lds_f64<OFF + mb_ * 1024>(pa);
+    CAFE_LDA(0) CAFE_LDA(1) CAFE_LDA(2) CAFE_LDA(3) CAFE_LDA(4) CAFE_LDA(5)
+#undef CAFE_LDA
 }
 template <int MBV, int NBV>
 __device__ __forceinline__ void mma_frags(double (&acc)[MB][NB][2], const double (&fa)[MB], const double (&fb)[NB]) {
@@ -565,110 +632,102 @@ __device__ __forceinline__ void mma_frags(double (&acc)[MB][NB][2], const double
         for (int nb = 0; nb < NBV; ++nb) dmma_884(acc[mb][nb][0], acc[mb][nb][1], fa[mb], fb[nb]);
 }
 
-// non-blocking probe of an mbarrier phase: issued a few k4-steps before the result is needed
-__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok;
-}
-
-// STEPS k4-steps (one or two full K blocks of a ring stage).  The fragments of the next step are fetched before the DMMAs of the
-// current one; after the last step (do_next) the first fragments of whatever follows - the next K block of the stage, or the
-// next stage after its mbarrier wait (~100 cycles even when already full) - so that neither sits between two DMMAs.
-template <int MBV, int NBV, int STEPS>
-__device__ __forceinline__ void steps_full(double (&acc)[MB][NB][2], double (&fa)[2][MB], double (&fb)[2][NB], const unsigned char* sa,
-                                           const unsigned char* sb, const int (&koff)[4], bool do_next, const unsigned char* next_a,
-                                           const unsigned char* next_b, uint64_t* wait_bar, uint32_t wait_phase,
-                                           bool prof, long long& t_wait_full) {
-    uint32_t ready = 0;
-#pragma unroll
-    for (int kk = 0; kk < STEPS; ++kk) {
-        // probe the next stage's barrier two steps early: its ~100-cycle latency then never sits between two DMMAs
-        if (STEPS >= 4 && kk == STEPS - 3 && do_next && wait_bar) ready = mbar_test(wait_bar, wait_phase);
-        if (kk + 1 < STEPS) {
-            const int j = (kk + 1) >> 2;
-            load_frags<MBV, NBV>(fa[(kk + 1) & 1], fb[(kk + 1) & 1], sa + j * SUB_BYTES, sb + j * SUB_BYTES, koff[(kk + 1) & 3]);
-        } else if (do_next) {
-            if (wait_bar && !ready) {
-                const long long t0 = prof ? clock64() : 0;
-                mbar_wait(wait_bar, wait_phase);
-                if (prof) t_wait_full += clock64() - t0;
-            }
-            load_frags<MBV, NBV>(fa[0], fb[0], next_a, next_b, koff[0]);
-        }
-        mma_frags<MBV, NBV>(acc, fa[kk & 1], fb[kk & 1]);
-    }
-}
-
 // K loop of one pass: n_kblocks K blocks of 16 sizes (the last one with tail_steps k4-steps), KB_PER_STAGE per ring stage.
 // MBV == 0: this warp has no work in the tile, it only keeps the ring moving.
 // blk0: first 8-size block of this warp inside the pass's 128 sizes.
+// The fragments of the next step are fetched before the DMMAs of the current one; during the last step of a stage the first
+// fragments of the next stage (its barrier is probed two steps earlier: the ~100-cycle latency of the probe then never sits
+// between two DMMAs), so that a stage boundary costs the arrive on the empty barrier and eight address updates.
 template <int MBV, int NBV>
-__device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], unsigned char* stage_base, Ctl* ctl, uint32_t& stage,
-                                             uint32_t& phase, int n_kblocks, int tail_steps, int grp, int blk0, int lane, int pg, int q,
-                                             bool prof, long long& t_wait_full, bool nosync) {
-    static_assert(KB_PER_STAGE == 2, "the stage loop below is written for two K blocks per stage");
+__device__ __forceinline__ void gemm_kblocks(double (&acc)[MB][NB][2], uint32_t ring, uint32_t bars, uint32_t& stage,
+                                             uint32_t& phase, int n_kblocks, int tail_steps, int grp, int blk0, int pg, int q,
+                                             bool prof, long long& t_wait_full) {
+    static_assert(KB_PER_STAGE == 2 && NSTAGE == 2, "the stage loop below is written for two stages of two K blocks");
+    // bars: shared address of Ctl::full[0]; full[s] at +8 s, empty[s] at +16 + 8 s
     const int n_stages = (n_kblocks + KB_PER_STAGE - 1) / KB_PER_STAGE;
     if (MBV == 0) {
         for (int st = 0; st < n_stages; ++st) {
-            if (!nosync) mbar_wait(&ctl->full[stage], phase);
+            if (!K2_DBG_NOSYNC) mbar_wait_u32(bars + 8 * stage, phase);
             __syncwarp();
-            if (lane == 0 && !nosync) mbar_arrive(&ctl->empty[stage]);
-            advance(stage, phase);
+            if (!K2_DBG_NOSYNC) mbar_arrive_elect_u32(bars + 16 + 8 * stage);
+            stage ^= 1; phase ^= (stage == 0);
         }
         return;
     }
-    const int off0 = pg * 128 + ((q & 1) << 3), hi = q >> 1;
-    int koff[4];
+    const int hi = q >> 1;
+    const uint32_t lane_off = ring + stage * STAGE_BYTES + pg * 128 + ((q & 1) << 3);
+    uint32_t pa[4], pb[4];  // this lane's A / B fragment addresses in the current stage, per k4-step of a K block
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) koff[kk] = off0 + (((2 * kk + hi) ^ pg) << 4);
-    const int a_off = grp * (HM * 128), b_off = A_BYTES + blk0 * 8 * 128;
+    for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t o = lane_off + (((2 * kk + hi) ^ pg) << 4);
+        pa[kk] = o + grp * (HM * 128);
+        pb[kk] = o + A_BYTES + blk0 * 8 * 128;
+    }
+    int delta = stage ? -STAGE_BYTES : STAGE_BYTES;   // to the other stage
+    uint32_t fbar_next = bars + 8 * (stage ^ 1), ebar = bars + 16 + 8 * stage;  // Ctl is 1024-byte aligned: ^ 8 switches the stage
     const int n_full = (tail_steps == 4) ? n_kblocks : n_kblocks - 1;  // K blocks with all four steps
 
     double fa[2][MB], fb[2][NB];
-    if (!nosync) {
+    if (!K2_DBG_NOSYNC) {
         const long long t0 = prof ? clock64() : 0;
-        mbar_wait(&ctl->full[stage], phase);
+        mbar_wait_u32(bars + 8 * stage, phase);
         if (prof) t_wait_full += clock64() - t0;
     }
-    const unsigned char* sbase = stage_base + stage * STAGE_BYTES;
-    load_frags<MBV, NBV>(fa[0], fb[0], sbase + a_off, sbase + b_off, koff[0]);
+    load_frags<MBV, NBV, 0>(fa[0], fb[0], pa[0], pb[0]);
     for (int st = 0; st < n_stages; ++st) {
-        uint32_t nstage = stage, nphase = phase;
-        advance(nstage, nphase);
-        const unsigned char* nbase = stage_base + nstage * STAGE_BYTES;
-        const unsigned char* sa = sbase + a_off;
-        const unsigned char* sb = sbase + b_off;
         const int kb0 = st * KB_PER_STAGE;
-        const bool has_next = st + 1 < n_stages;
-        uint64_t* nbar = nosync ? nullptr : &ctl->full[nstage];
         if (kb0 + 2 <= n_full) {
-            // two full K blocks; then the next stage (if any)
-            steps_full<MBV, NBV, 8>(acc, fa, fb, sa, sb, koff, has_next, nbase + a_off, nbase + b_off, nbar, nphase, prof, t_wait_full);
+            // two full K blocks; then the first fragments of the next stage (if any)
+            const bool has_next = st + 1 < n_stages;
+            load_frags<MBV, NBV, 0>(fa[1], fb[1], pa[1], pb[1]);          mma_frags<MBV, NBV>(acc, fa[0], fb[0]);
+            load_frags<MBV, NBV, 0>(fa[0], fb[0], pa[2], pb[2]);          mma_frags<MBV, NBV>(acc, fa[1], fb[1]);
+            load_frags<MBV, NBV, 0>(fa[1], fb[1], pa[3], pb[3]);          mma_frags<MBV, NBV>(acc, fa[0], fb[0]);
+            load_frags<MBV, NBV, SUB_BYTES>(fa[0], fb[0], pa[0], pb[0]);  mma_frags<MBV, NBV>(acc, fa[1], fb[1]);
+            load_frags<MBV, NBV, SUB_BYTES>(fa[1], fb[1], pa[1], pb[1]);  mma_frags<MBV, NBV>(acc, fa[0], fb[0]);
+            uint32_t ready = 1;
+            if (has_next && !K2_DBG_NOSYNC) ready = mbar_test_u32(fbar_next, phase ^ stage);
+            load_frags<MBV, NBV, SUB_BYTES>(fa[0], fb[0], pa[2], pb[2]);  mma_frags<MBV, NBV>(acc, fa[1], fb[1]);
+            load_frags<MBV, NBV, SUB_BYTES>(fa[1], fb[1], pa[3], pb[3]);  mma_frags<MBV, NBV>(acc, fa[0], fb[0]);
+            if (has_next) {
+                if (!ready) {
+                    const long long t0 = prof ? clock64() : 0;
+                    mbar_wait_u32(fbar_next, phase ^ stage);
+                    if (prof) t_wait_full += clock64() - t0;
+                }
+                load_frags<MBV, NBV, 0>(fa[0], fb[0], pa[0] + delta, pb[0] + delta);
+            }
+            mma_frags<MBV, NBV>(acc, fa[1], fb[1]);
         } else {
             // the last stage of the pass: [full block] [partial block], either may be missing
             int kb = kb0;
             if (kb < n_full) {
                 const bool more = kb + 1 < n_kblocks;  // a partial block follows in this stage
-                steps_full<MBV, NBV, 4>(acc, fa, fb, sa, sb, koff, more, sa + SUB_BYTES, sb + SUB_BYTES, nullptr, 0, prof, t_wait_full);
+                load_frags<MBV, NBV, 0>(fa[1], fb[1], pa[1], pb[1]);  mma_frags<MBV, NBV>(acc, fa[0], fb[0]);
+                load_frags<MBV, NBV, 0>(fa[0], fb[0], pa[2], pb[2]);  mma_frags<MBV, NBV>(acc, fa[1], fb[1]);
+                load_frags<MBV, NBV, 0>(fa[1], fb[1], pa[3], pb[3]);  mma_frags<MBV, NBV>(acc, fa[0], fb[0]);
+                if (more) load_frags<MBV, NBV, SUB_BYTES>(fa[0], fb[0], pa[0], pb[0]);
+                mma_frags<MBV, NBV>(acc, fa[1], fb[1]);
                 ++kb;
             }
             if (kb < n_kblocks && kb >= n_full) {
-                const int j = kb - kb0;
-                for (int kk = 0; kk < tail_steps; ++kk) {
-                    if (kk > 0) load_frags<MBV, NBV>(fa[0], fb[0], sa + j * SUB_BYTES, sb + j * SUB_BYTES, off0 + (((2 * kk + hi) ^ pg) << 4));
+                // the partial block sits at offset 0 of the stage when it is alone, after the full block otherwise
+                if (kb == kb0) {
                     mma_frags<MBV, NBV>(acc, fa[0], fb[0]);
+                    if (tail_steps > 1) { load_frags<MBV, NBV, 0>(fa[0], fb[0], pa[1], pb[1]); mma_frags<MBV, NBV>(acc, fa[0], fb[0]); }
+                    if (tail_steps > 2) { load_frags<MBV, NBV, 0>(fa[0], fb[0], pa[2], pb[2]); mma_frags<MBV, NBV>(acc, fa[0], fb[0]); }
+                } else {
+                    mma_frags<MBV, NBV>(acc, fa[0], fb[0]);
+                    if (tail_steps > 1) { load_frags<MBV, NBV, SUB_BYTES>(fa[0], fb[0], pa[1], pb[1]); mma_frags<MBV, NBV>(acc, fa[0], fb[0]); }
+                    if (tail_steps > 2) { load_frags<MBV, NBV, SUB_BYTES>(fa[0], fb[0], pa[2], pb[2]); mma_frags<MBV, NBV>(acc, fa[0], fb[0]); }
                 }
             }
         }
-        __syncwarp();
-        if (lane == 0 && !nosync) mbar_arrive(&ctl->empty[stage]);
-        stage = nstage; phase = nphase; sbase = nbase;
+        // every lane's fragment loads of this stage have completed: the warp-wide DMMAs that consume them have been issued
+        if (!K2_DBG_NOSYNC) mbar_arrive_elect_u32(ebar);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) { pa[kk] += delta; pb[kk] += delta; }
+        delta = -delta; fbar_next ^= 8; ebar ^= 8;
+        phase ^= stage; stage ^= 1;
     }
 }
 
@@ -702,6 +761,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
     const long long t_begin = prof ? clock64() : 0;
 
     uint32_t stage = 0, phase = 0, item = 0;
+    const uint32_t ring_u32 = opaque_u32(smem_u32(stage_base)), bars_u32 = opaque_u32(smem_u32(&ctl->full[0]));
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
         // the two tiles of the pair: this group's 8-family blocks (everything else about a tile concerns the helper warps)
         int mbv_h[2], f0_h[2];
@@ -747,7 +807,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     const long long tk0 = prof ? clock64() : 0;
                     // experiment knob (CAFE_GPU_SKEW): start group 1 of the very first pass some cycles after group 0
                     if (grp == 1 && P.skew > 0 && item == 0) { const long long t0 = clock64(); while (clock64() - t0 < P.skew) { } }
-#define CAFE_K(MBV_, NBV_) gemm_kblocks<MBV_, NBV_>(acc, stage_base, ctl, stage, phase, n_kblocks, tail_steps, grp, blk0, lane, pg, q, prof, t_wait_full, (P.dbg & 8) != 0);
+#define CAFE_K(MBV_, NBV_) gemm_kblocks<MBV_, NBV_>(acc, ring_u32, bars_u32, stage, phase, n_kblocks, tail_steps, grp, blk0, pg, q, prof, t_wait_full);
                     if (cnt <= 3) {
                         switch (mbw) {
                             case 6: CAFE_K(6, 3) break;
@@ -773,9 +833,9 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     const long long tk1 = prof ? clock64() : 0;
 
                     // ---------------- epilogue of this pass: C = acc * C in shared memory ----------------
-                    if (!(P.dbg & 2)) mbar_wait(&ctl->c_ready, item & 1);
+                    if (!K2_DBG(2)) mbar_wait(&ctl->c_ready, item & 1);
                     const long long tk2 = prof ? clock64() : 0;
-                    if (P.dbg & 3) {  // keep the accumulators alive
+                    if (K2_DBG(3)) {  // keep the accumulators alive
                         double sum = 0.0;
 #pragma unroll
                         for (int mb = 0; mb < MB; ++mb)
@@ -827,13 +887,13 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                             }
                         }
                     };
-                    if (!(P.dbg & 3)) {
+                    if (!K2_DBG(3)) {
                         if (cnt == 4 && blk0 == 4 * nw) multiply_in_place(std::true_type{});
                         else multiply_in_place(std::false_type{});
                     }
                     // no proxy fence here (MEMBAR.ALL.CTA would drain every store of the warp with the DMMA pipe idle): the arrive
                     // below releases the writes, the epilogue manager acquires them and fences before its TMA store
-                    if (reduce_now && P.logpost && !(P.dbg & 3)) {
+                    if (reduce_now && P.logpost && !K2_DBG(3)) {
                         // root: L[i] = acc * other; max / first argmax of L and max of log L + log prior (lambda.cpp:670-686).
                         // log is monotonic, so among this lane's eight sizes of a family only the one with the largest product
                         // L * prior can carry the maximum: the products are compared exactly as (exponent sum, mantissa product)
@@ -894,14 +954,14 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     }
                     const long long tk2b = prof ? clock64() : 0;
                     __syncwarp();
-                    if (lane == 0 && !(P.dbg & 2)) mbar_arrive(&ctl->c_done);
+                    if (lane == 0 && !K2_DBG(2)) mbar_arrive(&ctl->c_done);
                     ++item;
                     if (prof && P.timeline && nw == 0 && lane == 0 && item <= 1024) {
                         long long* tl = P.timeline + ((size_t)grp * 1024 + (item - 1)) * 4;
                         tl[0] = tk0; tl[1] = tk1; tl[2] = tk2; tl[3] = tk2b;
                     }
                     if (prof) { t_kloop += tk1 - tk0; t_wait_c += tk2 - tk1; t_epi += tk2b - tk2; if (flags & 2) t_kloop_cherry += tk1 - tk0; if (reduce_now) t_epi_root += tk2b - tk2; }
-                    if (reduce_now && P.logpost && !(P.dbg & 3)) {
+                    if (reduce_now && P.logpost && !K2_DBG(3)) {
                         group_bar(grp);
                         if (nw * 32 + lane < HM) {  // the first HM threads of the group own one family row each
                             const int row = nw * 32 + lane;
