@@ -337,6 +337,19 @@ def test_k2_config2_full_size_properties():
     assert rel_err(ml[idx], o["maxlik"], 1e-290).max() <= TOL_L
 
 
+@pytest.mark.gpu
+def test_k2_cold_contexts_are_bit_stable():
+    """A fresh context (cold scratch, TLB and L2) puts the producer warp right behind the leaf-pair gatherers at the first tile
+    pair - the place where a shared completion counter once let one gatherer's lead hide the other's lag (stale rows at the
+    end of a gatherer's half, rarely, and only on the first launch of a context).  Twelve cold launches, every family bit for bit."""
+    nw, counts, lam0 = _config2_problem()
+    _, _, _, lp0, ml0, am0 = _family_terms(nw, counts, lam0, env={"CAFE_GPU_FUSED_V1": "1"})
+    for _ in range(12):
+        _, _, fz, lp, ml, am = _family_terms(nw, counts, lam0)
+        assert fz == -1 and np.array_equal(ml, ml0) and np.array_equal(am, am0)
+        assert np.abs(lp - lp0).max() <= 1e-12
+
+
 def _terms_of(make_problem, counts, env=None, want_mats=False):
     """(problem, score, first zero, log-posterior terms, max likelihoods, argmax[, GPU-built matrix per node]) of one evaluation,
     optionally under A/B environment switches."""
