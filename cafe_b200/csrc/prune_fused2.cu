@@ -110,7 +110,6 @@ struct Params {
     double* maxlik;
     int* argmax;
     double* Lroot_out;           // nullable, [F][R]
-    int skew;                    // cycles group 1 starts every K loop after group 0 (see consumer_main)
     int dbg;                     // timing ablations, honoured by -DCAFE_K2_ABLATE builds only (see K2_DBG above)
     long long* cta_times;        // nullable debug: [grid][4] = smid, start ns, end ns, 8-family blocks
     long long* warp_prof;        // nullable debug: CTA 0, [16 warps][8] cycle sums (see consumer_main / producer_main)
@@ -263,7 +262,7 @@ __device__ __forceinline__ void advance(uint32_t& stage, uint32_t& phase) {
 
 // ================================ TMA producer (one lane) ================================ ================================
 template <bool PROF>
-__device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUtensorMap* tmB, const Params& P,
+__device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmBroot, const Params& P,
                                               unsigned char* stage_base, Ctl* ctl) {
     const TilePlan plan(P);
     const int scratch_row0 = blockIdx.x * cta_rows(P);
@@ -308,7 +307,7 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
                         for (int j = 0; j < nsub; ++j) {
                             unsigned char* sA = stage_base + stage * STAGE_BYTES + j * SUB_BYTES;
                             tma_load_2d(sA, tmA, (kb + j) * BK, a_row, &ctl->full[stage]);
-                            tma_load_3d(sA + A_BYTES, tmB, (kb + j) * BK, r0 + ch * TN, op.key, &ctl->full[stage]);
+                            tma_load_3d(sA + A_BYTES, op.is_root ? tmBroot : tmB, (kb + j) * BK, r0 + ch * TN, op.key, &ctl->full[stage]);
                         }
                         advance(stage, phase);
                     }
@@ -811,8 +810,6 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         for (int nb = 0; nb < NB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
 
                     const long long tk0 = prof ? clock64() : 0;
-                    // experiment knob (CAFE_GPU_SKEW): start group 1 of the very first pass some cycles after group 0
-                    if (grp == 1 && P.skew > 0 && item == 0) { const long long t0 = clock64(); while (clock64() - t0 < P.skew) { } }
 #define CAFE_K(MBV_, NBV_) gemm_kblocks<MBV_, NBV_>(acc, ring_u32, bars_u32, stage, phase, n_kblocks, tail_steps, grp, blk0, pg, sg, q, prof, t_wait_full);
                     if (cnt <= 3) {
                         switch (mbw) {
@@ -875,17 +872,21 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                                     }
                                 }
                                 double out[NB][2];
-                                // sizes >= nrows stay exact zeros: matrix rows in [W, S) are not zero when S > W.  Windowed mode: below
-                                // the root also the sizes above the family's own window (the reference never computes them)
+                                // sizes >= nrows are exact zeros already (the matrix tile's rows end at nrows: zero fill, see the tensor
+                                // maps).  Windowed mode: below the root also the sizes above the family's own window must be zeros
+                                // (the reference never computes them)
                                 const int lim = (WIN && !is_root) ? min(nrows, ctl->colmax[h][grp * HM + mb * 8 + pg] + 1) : nrows;
 #pragma unroll
                                 for (int nb = 0; nb < NB; ++nb) {
                                     if (FAST) {  // a product with 1.0 is the value itself
                                         out[nb][0] = FAC ? __dmul_rn(acc[mb][nb][0], fac[nb][0]) : acc[mb][nb][0];
                                         out[nb][1] = FAC ? __dmul_rn(acc[mb][nb][1], fac[nb][1]) : acc[mb][nb][1];
-                                    } else {
+                                    } else if (WIN) {
                                         out[nb][0] = (n0 + nb * 8 + pcA < lim) ? __dmul_rn(acc[mb][nb][0], fac[nb][0]) : 0.0;
                                         out[nb][1] = (n0 + nb * 8 + pcB < lim) ? __dmul_rn(acc[mb][nb][1], fac[nb][1]) : 0.0;
+                                    } else {
+                                        out[nb][0] = __dmul_rn(acc[mb][nb][0], fac[nb][0]);
+                                        out[nb][1] = __dmul_rn(acc[mb][nb][1], fac[nb][1]);
                                     }
                                 }
 #pragma unroll
@@ -902,7 +903,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                         #ifdef K2_NO_FAST
                         const bool fast = false;
 #else
-                        const bool fast = cnt == 4 && blk0 == 4 * nw && n0 + WCOLS <= nrows && !(WIN && !is_root);
+                        const bool fast = cnt == 4 && blk0 == 4 * nw && !(WIN && !is_root);
 #endif
                         if (fast && other_kind != 0) multiply_in_place(std::true_type{}, std::true_type{});
                         else if (fast) multiply_in_place(std::true_type{}, std::false_type{});
@@ -1009,7 +1010,8 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
 // p-values.  A separate instantiation, so that the score path carries none of it (measured: 0.8 % of a launch otherwise).
 template <bool PROF, bool WIN>
 __global__ void __launch_bounds__(THREADS, 1)
-k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params P) {
+k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmBroot, const Params P) {
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B tiles must start on a 1024-byte boundary of the shared window
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1033,7 +1035,7 @@ k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5;
     if (warp < N_AUX_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
-        if (warp == 0) { if ((threadIdx.x & 31) == 0) producer_main<PROF>(&tmA, &tmB, P, stage_base, ctl); }
+        if (warp == 0) { if ((threadIdx.x & 31) == 0) producer_main<PROF>(&tmA, &tmB, &tmBroot, P, stage_base, ctl); }
         else if (warp == 3) cmanager_main<PROF, WIN>(&tmA, P, Cbuf, ctl);
         else gatherer_main<WIN>(P, P.scratch, ctl, warp - 1);
     } else {
@@ -1269,13 +1271,21 @@ int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) CAFE_FAIL(ctx, CAFE_GPU_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r));
     }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)ctx->Sp, (cuuint64_t)ctx->Sp, (cuuint64_t)ctx->mat_cap};
+    // The matrix tile: rows = output sizes.  The row extent of the map is the number of sizes the op produces (W below the root,
+    // root_min + R at the root), not the padded matrix: TMA fills the rows beyond it with zeros, so the accumulators of sizes that
+    // do not exist are exact zeros (matrix rows in [W, S) are not zero when S > W) and the epilogue needs no per-element limit.
+    auto encode_B = [&](CUtensorMap* tm, int rows) -> CUresult {
+        cuuint64_t dims[3] = {(cuuint64_t)ctx->Sp, (cuuint64_t)std::min(rows, ctx->Sp), (cuuint64_t)ctx->mat_cap};
         cuuint64_t strides[2] = {(cuuint64_t)ctx->Sp * sizeof(double), (cuuint64_t)ctx->Sp * ctx->Sp * sizeof(double)};
         cuuint32_t box[3] = {BK, TN, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ctx->d_M, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ctx->d_M, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUtensorMap tmBroot;
+    {
+        CUresult r = encode_B(&tmB, ctx->W);
+        if (r == CUDA_SUCCESS) r = encode_B(&tmBroot, job.root_r0 + job.root_rows);
         if (r != CUDA_SUCCESS) CAFE_FAIL(ctx, CAFE_GPU_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r));
     }
 
@@ -1294,8 +1304,6 @@ int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
         CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "fused pruning: root rows exceed the vector / matrix");
 
     if (const char* d = std::getenv("CAFE_GPU_DBG")) P.dbg = std::atoi(d);
-    P.skew = 0;  // measured: no effect for 0..9000 cycles (profiles/r1_k2_experiments.md)
-    if (const char* d = std::getenv("CAFE_GPU_SKEW")) P.skew = std::atoi(d);
     const size_t smem_bytes = (size_t)NSTAGE * STAGE_BYTES + C_BYTES + sizeof(Ctl) + 1024;
     if (!st.attr_set) {
         CAFE_CK(ctx, cudaFuncSetAttribute(k_prune_fused2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -1314,9 +1322,9 @@ int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
     }
     const bool windowed = job.d_colmax != nullptr;
     if (job.d_root_pick && !windowed) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "fused pruning: a root pick needs the per-family windows");
-    if (windowed) k_prune_fused2<false, true><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
-    else if (trace_path) k_prune_fused2<true, false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
-    else k_prune_fused2<false, false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, P);
+    if (windowed) k_prune_fused2<false, true><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, tmBroot, P);
+    else if (trace_path) k_prune_fused2<true, false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, tmBroot, P);
+    else k_prune_fused2<false, false><<<grid, THREADS, smem_bytes, ctx->stream>>>(tmA, tmB, tmBroot, P);
     ctx->launches++;
     CAFE_CK(ctx, cudaGetLastError());
     if (trace_path) {  // debug only: synchronous dump "cta <i> <smid> <start ns> <end ns> <8-family blocks>"
