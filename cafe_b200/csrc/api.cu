@@ -883,6 +883,15 @@ int cafe_gpu_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_sam
     });
 }
 
+int cafe_gpu_cut_pvalues(cafe_gpu_ctx* ctx, const double* L_rest, const double* L_sub, int n_families, int rfsize,
+                         const double* cd_rest, const double* cd_sub, int cdlen, double* cut_pvalue_out) {
+    CAFE_NEED_LEADER(ctx);
+    if (!L_rest || !cd_rest || !cut_pvalue_out || n_families < 0 || rfsize < 1 || cdlen < 1 || ((L_sub == nullptr) != (cd_sub == nullptr)))
+        CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "cut_pvalues: bad arguments");
+    cudaSetDevice(ctx->device);
+    return run_cut_pvalues(ctx, L_rest, L_sub, n_families, rfsize, cd_rest, cd_sub, cdlen, cut_pvalue_out);
+}
+
 // The branch-stretch test shards by families like the score.  Only the table's first tested family starts from the parsed
 // branch lengths (cafe/cafe_main.c:350,390), so the slices after the one that holds it mark their families 2.
 int cafe_gpu_likelihood_ratio_test(cafe_gpu_ctx* ctx, const uint8_t* tested, const double* lengthened_mu_per_node,

@@ -201,6 +201,8 @@ void fused2_release(cafe_gpu_ctx* ctx);
 int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,
                                  double* cd_out);                       // conddist.cu    (K4)
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out);  // pvalue.cu (K5)
+int run_cut_pvalues(cafe_gpu_ctx* ctx, const double* L1, const double* L2, int F, int rf, const double* cd1, const double* cd2,
+                    int cdlen, double* out);  // pvalue.cu (branch cutting)
 int run_lrt_branch_stretch(cafe_gpu_ctx* ctx, const uint8_t* tested, const double* lengthened_mu, double* base_out, double* best_out,
                            int32_t* steps_out);                     // lrt.cu
 int build_one_matrix(cafe_gpu_ctx* ctx, int key);                       // api.cu (K1 for one key)

@@ -52,6 +52,50 @@ k_family_pvalue(const double* __restrict__ Lroot, size_t Vp, int F, const int* _
     if (lane == 0) out[f] = (rf > 0) ? best : 0.0;
 }
 
+// ---------------------------------------------------------------- branch cutting (cafe/branch_cutting.cpp:20-44, :101-150)
+// One side of the cut is a single leaf: cutPvalue = max_s pvalue(L[s], cd[s]) over the whole root range (cafe_tree_p_values on
+// the other tree, :125-131).  One warp per family.
+__global__ void __launch_bounds__(256)
+k_cut_pvalue_one(const double* __restrict__ L, int F, int rf, const double* __restrict__ cd, int cdlen, double* __restrict__ out) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= F) return;
+    double best = -INFINITY;
+    for (int s = lane; s < rf; s += 32) best = fmax(best, pvalue_dev(L[(size_t)f * rf + s], cd + (size_t)s * cdlen, cdlen));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if (lane == 0) out[f] = best;
+}
+
+// Both sides are trees (p_values_of_two_trees, :20-44): p2[s1][s2] = (1/cdlen) sum_t pvalue(L1[s1] L2[s2] / cd2[s2][t], cd1[s1]),
+// cutPvalue = max over (s1, s2), never below 0 (:136-147).  One thread per (s1, s2) pair, the sum over t in the reference's order
+// (one rounding per product, quotient and addition), block maximum, one atomic maximum per block: p >= 0, so the bit patterns
+// order like the values.  grid = (pair chunks, families).
+__global__ void __launch_bounds__(256)
+k_cut_pvalue_two(const double* __restrict__ L1, const double* __restrict__ L2, int rf, const double* __restrict__ cd1,
+                 const double* __restrict__ cd2, int cdlen, unsigned long long* __restrict__ out_bits) {
+    const int f = blockIdx.y;
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    double p = 0.0;
+    if (pair < rf * rf) {
+        const int s2 = pair / rf, s1 = pair - s2 * rf;
+        const double prod = __dmul_rn(L1[(size_t)f * rf + s1], L2[(size_t)f * rf + s2]);
+        const double* row1 = cd1 + (size_t)s1 * cdlen;
+        const double* row2 = cd2 + (size_t)s2 * cdlen;
+        for (int t = 0; t < cdlen; ++t) p = __dadd_rn(p, pvalue_dev(__ddiv_rn(prod, row2[t]), row1, cdlen));
+        p = __ddiv_rn(p, (double)cdlen);
+    }
+    if (!(p > 0.0)) p = 0.0;  // the running maximum starts at 0 (:136); a NaN never replaces it (:142)
+    __shared__ double red[8];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) p = fmax(p, __shfl_xor_sync(0xffffffffu, p, off));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) p = fmax(p, red[w]);
+        atomicMax(out_bits + f, (unsigned long long)__double_as_longlong(p));
+    }
+}
+
 }  // namespace
 
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out) {
@@ -118,5 +162,41 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
     cleanup();
     ctx->results_valid = false;
 #undef PV_CK
+    return CAFE_GPU_OK;
+}
+
+// cafe_gpu_cut_pvalues: see include/cafe_gpu.h.  Host arrays in, host array out; the arithmetic of one family does not depend on
+// the others.
+int run_cut_pvalues(cafe_gpu_ctx* ctx, const double* L1, const double* L2, int F, int rf, const double* cd1, const double* cd2,
+                    int cdlen, double* out) {
+    if (F <= 0) return CAFE_GPU_OK;
+    double *dL1 = nullptr, *dL2 = nullptr, *dcd1 = nullptr, *dcd2 = nullptr, *dout = nullptr;
+    auto cleanup = [&]() { cudaFree(dL1); cudaFree(dL2); cudaFree(dcd1); cudaFree(dcd2); cudaFree(dout); };
+#define CUT_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
+    const size_t lb = (size_t)F * rf * sizeof(double), cb = (size_t)rf * cdlen * sizeof(double);
+    CUT_CK(cudaMalloc(&dL1, lb)); CUT_CK(cudaMalloc(&dcd1, cb)); CUT_CK(cudaMalloc(&dout, F * sizeof(double)));
+    CUT_CK(cudaMemcpyAsync(dL1, L1, lb, cudaMemcpyHostToDevice, ctx->stream));
+    CUT_CK(cudaMemcpyAsync(dcd1, cd1, cb, cudaMemcpyHostToDevice, ctx->stream));
+    if (L2) {
+        CUT_CK(cudaMalloc(&dL2, lb)); CUT_CK(cudaMalloc(&dcd2, cb));
+        CUT_CK(cudaMemcpyAsync(dL2, L2, lb, cudaMemcpyHostToDevice, ctx->stream));
+        CUT_CK(cudaMemcpyAsync(dcd2, cd2, cb, cudaMemcpyHostToDevice, ctx->stream));
+        CUT_CK(cudaMemsetAsync(dout, 0, F * sizeof(double), ctx->stream));  // +0.0: the maximum starts at 0
+        const int pairs = rf * rf;
+        for (int f0 = 0; f0 < F; f0 += 32768) {  // gridDim.y limit
+            const int nf = std::min(32768, F - f0);
+            k_cut_pvalue_two<<<dim3((pairs + 255) / 256, nf), 256, 0, ctx->stream>>>(dL1 + (size_t)f0 * rf, dL2 + (size_t)f0 * rf, rf, dcd1, dcd2, cdlen,
+                                                                                    reinterpret_cast<unsigned long long*>(dout) + f0);
+            ctx->launches++;
+        }
+    } else {
+        k_cut_pvalue_one<<<(F + 7) / 8, 256, 0, ctx->stream>>>(dL1, F, rf, dcd1, cdlen, dout);
+        ctx->launches++;
+    }
+    CUT_CK(cudaGetLastError());
+    CUT_CK(cudaMemcpyAsync(out, dout, F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUT_CK(cudaStreamSynchronize(ctx->stream));
+    cleanup();
+#undef CUT_CK
     return CAFE_GPU_OK;
 }

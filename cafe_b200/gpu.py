@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "cafe_gpu_set_families", "cafe_gpu_set_prior", "cafe_gpu_set_error_model", "cafe_gpu_set_rates",
     "cafe_gpu_build_matrices", "cafe_gpu_num_keys", "cafe_gpu_get_matrix", "cafe_gpu_score", "cafe_gpu_objective",
     "cafe_gpu_objective_device", "cafe_gpu_family_results", "cafe_gpu_family_likelihoods",
-    "cafe_gpu_conditional_distribution", "cafe_gpu_pvalues", "cafe_gpu_launch_count",
+    "cafe_gpu_conditional_distribution", "cafe_gpu_pvalues", "cafe_gpu_cut_pvalues", "cafe_gpu_launch_count",
     "cafe_gpu_reset_launch_count", "cafe_gpu_enable_timing", "cafe_gpu_timing_collect", "cafe_gpu_score_flops",
     "cafe_gpu_score_device", "cafe_gpu_set_key_shard", "cafe_gpu_matrix_storage", "cafe_gpu_matrices_exchanged",
     "cafe_gpu_viterbi", "cafe_gpu_viterbi_report", "cafe_gpu_conditional_distribution_rows",
@@ -77,6 +77,7 @@ def load_library():
     L.cafe_gpu_conditional_distribution.argtypes = [vp, C.c_int, _dp, C.c_uint64, _dp]
     L.cafe_gpu_conditional_distribution_rows.argtypes = [vp, C.c_int, _dp, C.c_uint64, C.c_int, C.c_int, _dp]
     L.cafe_gpu_pvalues.argtypes = [vp, _dp, C.c_int, C.c_int, _dp]
+    L.cafe_gpu_cut_pvalues.argtypes = [vp, _dp, _dp, C.c_int, C.c_int, _dp, _dp, C.c_int, _dp]
     L.cafe_gpu_launch_count.restype = C.c_int64
     L.cafe_gpu_launch_count.argtypes = [vp]
     L.cafe_gpu_reset_launch_count.argtypes = [vp]
@@ -320,6 +321,18 @@ class CafeGpu:
         cd = np.ascontiguousarray(cd, dtype=np.float64)
         out = np.zeros(self.F)
         self._ck(self.L.cafe_gpu_pvalues(self.h, _d(cd), cd.shape[0], cd.shape[1], _d(out)), "pvalues")
+        return out
+
+    def cut_pvalues(self, L_rest, cd_rest, L_sub=None, cd_sub=None):
+        """Branch cutting, the p-value part: rows [F][rfsize] of one or both sides of the cut with their distributions."""
+        L_rest = np.ascontiguousarray(L_rest, dtype=np.float64); cd_rest = np.ascontiguousarray(cd_rest, dtype=np.float64)
+        F, rf = L_rest.shape
+        out = np.zeros(F)
+        l2 = c2 = None
+        if L_sub is not None:
+            L_sub = np.ascontiguousarray(L_sub, dtype=np.float64); cd_sub = np.ascontiguousarray(cd_sub, dtype=np.float64)
+            l2, c2 = _d(L_sub), _d(cd_sub)
+        self._ck(self.L.cafe_gpu_cut_pvalues(self.h, _d(L_rest), l2, F, rf, _d(cd_rest), c2, cd_rest.shape[1], _d(out)), "cut_pvalues")
         return out
 
     def launch_count(self):

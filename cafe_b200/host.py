@@ -63,6 +63,7 @@ def load_library():
     H.cafe_host_chi2cdf.restype = C.c_double
     H.cafe_host_chi2cdf.argtypes = [C.c_double, C.c_int]
     H.cafe_host_likelihood_ratio_test.argtypes = [vp, C.c_int, _dp, C.c_long, _ip, _ip]
+    H.cafe_host_branch_cutting.argtypes = [vp, C.c_int, C.c_int, _dp, C.c_long, _ip, _ip]
     return H
 
 
@@ -279,6 +280,18 @@ class Session:
         nodes = C.c_int()
         fams = C.c_int()
         if self.H.cafe_host_likelihood_ratio_test(self.h, int(tree_level_mu), _d(buf), buf.size, C.byref(nodes), C.byref(fams)) < 0:
+            raise CafeHostError(self.H.cafe_host_last_error().decode())
+        return buf[: nodes.value * fams.value].reshape(nodes.value, fams.value).copy()
+
+    def branch_cutting(self, num_random_samples, tree_level_mu=False):
+        """cafe_branch_cutting (cafe/branch_cutting.cpp:101-272): cutPvalues [nodes][families] for the family p-values given with
+        set_max_pvalues (or the last report).  The conditional distributions replay glibc rand() (after `seed`) when the session
+        has one thread, as the reference's single-threaded run would draw them."""
+        F = self.num_families()
+        buf = np.zeros(F * 4096)
+        nodes = C.c_int()
+        fams = C.c_int()
+        if self.H.cafe_host_branch_cutting(self.h, int(num_random_samples), int(tree_level_mu), _d(buf), buf.size, C.byref(nodes), C.byref(fams)) < 0:
             raise CafeHostError(self.H.cafe_host_last_error().decode())
         return buf[: nodes.value * fams.value].reshape(nodes.value, fams.value).copy()
 

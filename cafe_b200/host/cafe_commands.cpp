@@ -327,18 +327,21 @@ int cafe_cmd_pvalue(Globals& globals, std::vector<std::string> tokens) {
 // p-values, Viterbi reconstruction, branch p-values), optionally the likelihood-ratio test, and the text report "<name>.cafe" in
 // the reference's format (cafe_report_text).  "<name>.pvalues" (one "ID<TAB>p" line per family) is kept as a convenience.
 // Options: `likelihood` = the test with the nodes' own mu; `likelihood-stock` = keyed like the stock binary (cafe_param.h);
-// `branchcutting` / `lh2` fail inside the reference itself and are rejected; html/json formats are not built.
+// `branchcutting` = the branch-cutting p-values (the nodes' own mu; `branchcutting-stock` keys the copies like the stock binary would);
+// `lh2` fails inside the reference itself and is rejected; html/json formats are not built.
 int cafe_cmd_report(Globals& globals, std::vector<std::string> tokens) {
     pCafeParam param = &globals.param;
     prereqs(param, true, true, true);
     if (tokens.size() < 2) throw std::runtime_error("Usage(report): report <name>\n");
-    bool likelihood = false;
+    bool likelihood = false, branchcutting = false;
     for (size_t i = 2; i < tokens.size(); ++i) {  // report_parameters, reports.cpp:604-616
         std::string o = tokens[i];
         for (char& c : o) c = (char)std::tolower((unsigned char)c);
         if (o == "likelihood") { likelihood = true; param->lrt_tree_level_mu = 0; }
         if (o == "likelihood-stock") { likelihood = true; param->lrt_tree_level_mu = 1; }
-        if (o == "branchcutting" || o == "lh2" || o == "html" || o == "json") throw std::runtime_error("report: " + o + " is not built (SURVEY.md 8f)");
+        if (o == "branchcutting") { branchcutting = true; param->lrt_tree_level_mu = 0; }
+        if (o == "branchcutting-stock") { branchcutting = true; param->lrt_tree_level_mu = 1; }
+        if (o == "lh2" || o == "html" || o == "json") throw std::runtime_error("report: " + o + " is not built (SURVEY.md 8f)");
     }
     cafe_shell_set_lambdas(param, param->input.parameters);
     reset_birthdeath_cache(param->pcafe, param->parameterized_k_value, &param->family_size);
@@ -354,6 +357,8 @@ int cafe_cmd_report(Globals& globals, std::vector<std::string> tokens) {
     for (size_t i = 0; i < param->pfamily->flist.size(); ++i) ofst << param->pfamily->flist[i].id << "\t" << param->max_pvalues[i] << "\n";
     viterbi_parameters viterbi;
     cafe_viterbi(param, viterbi);
+    param->cutPvalues.clear();
+    if (branchcutting) cafe_branch_cutting(param, globals.num_random_samples);  // cafe_do_report, reports.cpp:679-682
     if (likelihood) cafe_likelihood_ratio_test(param, param->max_pvalues.data());
     cafe_log(param, "Building Text report: %s\n", tokens[1].c_str());
     std::ofstream report((tokens[1] + ".cafe").c_str());

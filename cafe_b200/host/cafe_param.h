@@ -54,6 +54,7 @@ struct CafeParam {  // libtree/family.h:115-172 (fields used by the lambda / lam
     std::vector<std::vector<double>> cond_dist;  // ConditionalDistribution::matrix
     std::vector<double> max_pvalues;             // viterbi.maximumPvalues
     std::vector<std::vector<double>> likelihoodRatios;  // [node][family], libtree/family.h:169
+    std::vector<std::vector<double>> cutPvalues;        // [node][family], viterbi_parameters::cutPvalues (cafe/viterbi.h:52)
     // 1: key the lengthened branches of the likelihood-ratio test with the tree-level mu (0 after cafe_tree_new), as the stock
     // reference does because cafe_tree_node_copy drops the nodes' mu (cafe/cafe_tree.c:485-494); 0: the nodes' own mu
     int lrt_tree_level_mu = 0;
@@ -112,6 +113,10 @@ void cafe_family_pvalues(pCafeParam param, std::vector<double>& max_pvalues);
 // fills param->likelihoodRatios[b][i]; -1 for the root's row and for families whose maximumPvalues[i] > param->pvalue;
 // duplicates copy their first occurrence.  All families at once through cafe_gpu_likelihood_ratio_test.
 void cafe_likelihood_ratio_test(pCafeParam param, double* maximumPvalues);
+// cafe/branch_cutting.cpp:101-272 — `report ... branchcutting`: param->cutPvalues[b][i] = p-value of cutting the branch above node b
+// for family i; -1 for the root's row and for families whose family-wide p-value exceeds param->pvalue; needs param->max_pvalues.
+// param->lrt_tree_level_mu selects the stock keying of the copies' nodes, as for the likelihood-ratio test (branch_cutting.cpp).
+void cafe_branch_cutting(pCafeParam param, int num_random_samples);
 // Viterbi pass + text report of `report` (cafe/viterbi.h, cafe/viterbi.cpp:88-173,570-595, cafe/reports.cpp:157-194,230-500)
 struct change { int expand = 0, remain = 0, decrease = 0; };  // cafe/viterbi.h
 struct viterbi_parameters {

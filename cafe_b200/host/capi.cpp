@@ -276,4 +276,22 @@ int cafe_host_likelihood_ratio_test(void* h, int tree_level_mu, double* out, lon
     HOST_CATCH(-1)
 }
 
+// cafe_branch_cutting with the family p-values set by cafe_host_set_max_pvalues / the last report; out row-major [nodes][families]
+int cafe_host_branch_cutting(void* h, int num_random_samples, int tree_level_mu, double* out, long cap, int* nodes, int* families) {
+    HOST_TRY
+    CafeParam& p = static_cast<Globals*>(h)->param;
+    if (!p.pcafe || !p.pfamily) { g_host_err = "load and tree first"; return -1; }
+    if (p.max_pvalues.size() != p.pfamily->flist.size()) p.max_pvalues.assign(p.pfamily->flist.size(), 0.0);
+    const int saved = p.lrt_tree_level_mu;
+    p.lrt_tree_level_mu = tree_level_mu;
+    try { cafe_branch_cutting(&p, num_random_samples); } catch (...) { p.lrt_tree_level_mu = saved; throw; }
+    p.lrt_tree_level_mu = saved;
+    *nodes = (int)p.cutPvalues.size();
+    *families = (int)p.pfamily->flist.size();
+    if ((long)*nodes * *families > cap) { g_host_err = "cap too small"; return -1; }
+    for (int b = 0; b < *nodes; ++b) std::copy(p.cutPvalues[b].begin(), p.cutPvalues[b].end(), out + (size_t)b * *families);
+    return 0;
+    HOST_CATCH(-1)
+}
+
 }  // extern "C"

@@ -120,9 +120,10 @@ void cafe_report_text(std::ostream& ost, pCafeParam param, const viterbi_paramet
     ost << "\nnDecrease :";
     for (size_t b = 0; b < npairs; ++b) ost << "\t(" << viterbi.expandRemainDecrease[2 * b].decrease << "," << viterbi.expandRemainDecrease[2 * b + 1].decrease << ")";
     ost << "\n";
-    const bool have_lr = !param->likelihoodRatios.empty();
-    // write_families_header with the inverted flags of reports.cpp:445-446 (no branch cutting here: that column is always absent)
-    ost << "'ID'\t'Newick'\t'Family-wide P-value'\t'Viterbi P-values'\t'cut P-value'";
+    const bool have_lr = !param->likelihoodRatios.empty(), have_cut = !param->cutPvalues.empty();
+    // write_families_header with the inverted flags of reports.cpp:456-457: a column's title appears when the column is ABSENT
+    ost << "'ID'\t'Newick'\t'Family-wide P-value'\t'Viterbi P-values'";
+    if (!have_cut) ost << "\t'cut P-value'";
     if (!have_lr) ost << "\t'Likelihood Ratio'";
     ost << "\n";
     CafeTree ft = t;
@@ -138,6 +139,12 @@ void cafe_report_text(std::ostream& ost, pCafeParam param, const viterbi_paramet
             if (b + 1 < npairs) ost << ",";
         }
         ost << ")\t";
+        if (have_cut) {  // reports.cpp:340-344
+            std::vector<double> cp(nnodes);
+            for (int b = 0; b < nnodes; ++b) cp[b] = param->cutPvalues[b][i];
+            write_doubles(ost, cp);
+            ost << "\t";
+        }
         if (have_lr) {
             std::vector<double> lr(nnodes);
             for (int b = 0; b < nnodes; ++b) lr[b] = param->likelihoodRatios[b][i];

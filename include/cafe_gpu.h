@@ -230,6 +230,16 @@ int cafe_gpu_conditional_distribution_rows(cafe_gpu_ctx* ctx, int n_samples, con
 int cafe_gpu_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
                      double* max_pvalue_out);
 
+/* Branch cutting, the p-value part (cafe/branch_cutting.cpp:20-44 p_values_of_two_trees, :101-150 compute_cutpvalues).  The caller
+ * cuts a branch (phylogeny_split_tree, libtree/phylogeny.c:571-614), gives each side its own context (tree, rates, the families'
+ * counts at that side's leaves), and passes the root likelihood rows of the two sides (cafe_gpu_family_likelihoods, row-major
+ * [n_families][rfsize]) with their conditional distributions ([rfsize][cdlen] ascending rows, cafe_gpu_conditional_distribution):
+ *   L_sub == cd_sub == NULL (one side is a single leaf):  out[f] = max_s pvalue(L_rest[f][s], cd_rest[s])
+ *   otherwise:  out[f] = max(0, max_{s1,s2} (1/cdlen) sum_t pvalue(L_rest[f][s1] * L_sub[f][s2] / cd_sub[s2][t], cd_rest[s1]))
+ * with the sum over t in ascending order, one rounding per operation as on the CPU.  `ctx` only names the device and stream. */
+int cafe_gpu_cut_pvalues(cafe_gpu_ctx* ctx, const double* L_rest, const double* L_sub, int n_families, int rfsize,
+                         const double* cd_rest, const double* cd_sub, int cdlen, double* cut_pvalue_out);
+
 /* Bookkeeping for measurement: kernels launched by this context since creation / last reset; and,
  * when timing is enabled, one CUDA-event quad per objective evaluation recorded on the context's
  * stream around K1 (matrix build) and K2 (pruning + root reduction).  cafe_gpu_timing_collect

@@ -512,5 +512,114 @@ def conditional_distribution(tree: FlatTree, mats, ranges, n_samples, uniforms=N
     return np.array(rows)
 
 
+# --------------------------------------------------------------------------- branch cutting
+
+def split_tree(tree: FlatTree, b: int):
+    """phylogeny_split_tree (libtree/phylogeny.c:571-614) as cafe_tree_split uses it (cafe/cafe_tree.c:517-527): cut the branch
+    above node b.  Returns (rest, sub, rest_orig, sub_orig): the remaining tree and the cut-off subtree as FlatTrees in their own
+    infix numbering (tree_build_node_list), and for each the original node id of every new node.  In the remaining tree b's
+    parent disappears: its other child takes its place and inherits its branch length on top of its own (:594), or becomes the
+    root when the parent was the root (:586-591).  Both roots get branch length -1 (:611-612)."""
+    assert b != tree.root
+    left, right, parent = tree.left.tolist(), tree.right.tolist(), tree.parent.tolist()
+    bl = tree.branchlength.tolist()
+    par = parent[b]
+    sib = right[par] if left[par] == b else left[par]
+    if par == tree.root:
+        rest_root = sib
+    else:
+        bl[sib] += bl[par]
+        grand = parent[par]
+        if left[grand] == par:
+            left[grand] = sib
+        else:
+            right[grand] = sib
+        rest_root = tree.root
+
+    def flatten(root):
+        order = []
+
+        def infix(v):
+            if left[v] >= 0:
+                infix(left[v]); order.append(v); infix(right[v])
+            else:
+                order.append(v)
+
+        infix(root)
+        new = {v: i for i, v in enumerate(order)}
+        L = [new[left[v]] if left[v] >= 0 else -1 for v in order]
+        R = [new[right[v]] if right[v] >= 0 else -1 for v in order]
+        P = [-1] * len(order)
+        for i, v in enumerate(order):
+            if L[i] >= 0:
+                P[L[i]] = i; P[R[i]] = i
+        B = [bl[v] for v in order]
+        B[new[root]] = -1.0
+        return FlatTree(L, R, P, B, [tree.names[v] for v in order]), order
+
+    rest, rest_orig = flatten(rest_root)
+    sub, sub_orig = flatten(b)
+    return rest, sub, rest_orig, sub_orig
+
+
+def branch_cut(tree: FlatTree, lam_per_node, mu_per_node, counts, ranges, n_samples, b, max_pvalues, cutoff, uniforms=None):
+    """cut_branch + compute_cutpvalues (cafe/branch_cutting.cpp:185-219, :101-150) for branch b and the families `counts`
+    (F x n_leaves, leaf order of `tree`).  The conditional distributions draw from glibc rand() (after the caller's srand) or
+    from `uniforms`; the remaining tree's distribution first, then the subtree's.  Returns {"pvalues": F values (-1 where
+    max_pvalues > cutoff), "cd1", "cd2" (None when one side is a single leaf), "rest", "sub"}."""
+    counts = np.asarray(counts)
+    lam_per_node = np.asarray(lam_per_node, dtype=np.float64); mu_per_node = np.asarray(mu_per_node, dtype=np.float64)
+    if b == tree.root:
+        return {"pvalues": np.zeros(len(counts)), "cd1": None, "cd2": None}
+    rest, sub, ro, so = split_tree(tree, b)
+    maxfs = max(ranges[1], ranges[3])
+    m_rest = node_matrices(rest, lam_per_node[ro], mu_per_node[ro], maxfs) if rest.n_nodes > 1 else None
+    m_sub = node_matrices(sub, lam_per_node[so], mu_per_node[so], maxfs) if sub.n_nodes > 1 else None
+    leaf_col = {v: v // 2 for v in range(0, tree.n_nodes, 2)}            # original leaf id -> column of counts
+    cols_rest = [leaf_col[ro[i]] for i in range(0, rest.n_nodes, 2)]
+    cols_sub = [leaf_col[so[i]] for i in range(0, sub.n_nodes, 2)]
+    off = [0]
+
+    def cd(t, mats, n):
+        per = (ranges[3] - ranges[2] + 1) * n * (t.n_nodes - 1)
+        u = None if uniforms is None else uniforms[off[0]:off[0] + per]
+        off[0] += per
+        return conditional_distribution(t, mats, ranges, n, u)
+
+    rf = ranges[3] - ranges[2] + 1
+    out = np.zeros(len(counts))
+    if sub.n_nodes == 1 or rest.n_nodes == 1:
+        t, mats, cols = (rest, m_rest, cols_rest) if sub.n_nodes == 1 else (sub, m_sub, cols_sub)
+        cd1, cd2 = cd(t, mats, n_samples), None
+        for f in range(len(counts)):
+            if max_pvalues[f] > cutoff:
+                out[f] = -1.0
+                continue
+            L = prune(t, mats, counts[f, cols], ranges)
+            out[f] = max(pvalue(L[s], cd1[s][:n_samples]) for s in range(rf))
+    else:
+        n10 = n_samples // 10
+        cd1 = cd(rest, m_rest, n10)
+        cd2 = cd(sub, m_sub, n10)
+        for f in range(len(counts)):
+            if max_pvalues[f] > cutoff:
+                out[f] = -1.0
+                continue
+            l1 = prune(rest, m_rest, counts[f, cols_rest], ranges)
+            l2 = prune(sub, m_sub, counts[f, cols_sub], ranges)
+            best = 0.0
+            with np.errstate(divide="ignore", invalid="ignore"):
+                for s2 in range(rf):          # p_values_of_two_trees, branch_cutting.cpp:20-44
+                    for s1 in range(rf):
+                        p = 0.0
+                        for t in range(n10):
+                            p += pvalue(float(np.float64(l1[s1]) * np.float64(l2[s2]) / np.float64(cd2[s2][t])), cd1[s1][:n10])
+                        p = p / n10
+                        if p > best:
+                            best = p
+            out[f] = best
+    return {"pvalues": out, "cd1": cd1, "cd2": cd2, "rest": rest, "sub": sub, "rest_orig": ro, "sub_orig": so}
+
+
 def srand(seed: int):
     C.CDLL(None).srand(C.c_uint(seed))

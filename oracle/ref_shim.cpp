@@ -30,6 +30,7 @@ void __cafe_famliy_check_the_pattern(pCafeFamily pcf);
 #include "pvalue.h"
 #include "viterbi.h"
 #include "error_model.h"
+#include "branch_cutting.h"
 
 namespace {
 struct Session {
@@ -407,4 +408,42 @@ void refshim_session_free(void* h) {
     delete s;
 }
 
+
+// Branch cutting for ONE branch b (nlist index) and every family of the session: cut_branch (cafe/branch_cutting.cpp:185-219:
+// copy + split of the tree, conditional distributions of the remaining tree and of the cut-off subtree from the rand() stream,
+// n_samples draws, or n_samples / 10 each when neither side is a single leaf) followed by compute_cutpvalues (:101-150).
+// The stock driver cafe_branch_cutting (:221-272) cannot run - it never fills pfamily / viterbi / num_random_samples / pvalue of
+// its thread parameters - so the two functions are called the way its thread function would have called them.
+// keep_node_mu: as in refshim_likelihood_ratio_test - cafe_tree_copy gives the copies' nodes the TREE-level mu (cafe_tree.c:39,
+// :485-494), which cafe_tree_new leaves at 0; 1 sets it to the nodes' common mu first, 0 is the stock behaviour.
+// out[F]: cutPvalues[b][f] (-1 where max_pvalues[f] > cutoff; 0 for a root b: compute_cutpvalues returns before writing).
+// dims = {rows of the first distribution, its draws, rows of the second, its draws}; cd1 / cd2 (nullable) receive them row-major.
+int refshim_branch_cut(void* h, int b, int n_samples, int keep_node_mu, const double* max_pvalues, double cutoff, double* out,
+                       double* cd1, double* cd2, int* dims, char* log, int log_len) {
+    Session* s = (Session*)h;
+    const int n = refshim_n_nodes(h), F = s->family->flist->size;
+    s->tree->mu = keep_node_mu ? node_at(s, 0)->birth_death_probabilities.mu : 0;
+    CutBranch cb(n);
+    std::ostringstream ost;
+    cut_branch(cb, (pTree)s->tree, s->tree, s->range, 1, n_samples, b, ost);
+    if (log) { strncpy(log, ost.str().c_str(), log_len - 1); log[log_len - 1] = 0; }
+    matrix& m1 = cb.pCDSs[b].first; matrix& m2 = cb.pCDSs[b].second;
+    dims[0] = (int)m1.size(); dims[1] = m1.empty() ? 0 : (int)m1[0].size();
+    dims[2] = (int)m2.size(); dims[3] = m2.empty() ? 0 : (int)m2[0].size();
+    if (cd1) for (size_t i = 0; i < m1.size(); i++) memcpy(cd1 + i * m1[i].size(), m1[i].data(), sizeof(double) * m1[i].size());
+    if (cd2) for (size_t i = 0; i < m2.size(); i++) memcpy(cd2 + i * m2[i].size(), m2[i].data(), sizeof(double) * m2[i].size());
+    viterbi_parameters v;
+    viterbi_parameters_init(&v, n, F);
+    std::vector<double> mp(max_pvalues, max_pvalues + F);
+    v.maximumPvalues = mp.data();
+    v.cutPvalues = (double**)memory_new_2dim(n, F, sizeof(double));
+    std::vector<double> p1(s->tree->rfsize);
+    double** p2 = (double**)memory_new_2dim(s->tree->rfsize, s->tree->rfsize, sizeof(double));
+    compute_cutpvalues(s->tree, s->family, n_samples, b, 0, F, v, cutoff, p1, p2, cb);
+    for (int f = 0; f < F; f++) out[f] = v.cutPvalues[b][f];
+    memory_free_2dim((void**)p2, s->tree->rfsize, s->tree->rfsize, NULL);
+    memory_free_2dim((void**)v.cutPvalues, n, F, NULL);
+    v.maximumPvalues = nullptr; v.cutPvalues = nullptr;
+    return F;
+}
 }  // extern "C"
