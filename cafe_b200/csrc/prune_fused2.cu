@@ -12,18 +12,22 @@
 //   warps 4..11  DMMA consumers, 2 M-groups x 4 N-warps (warp tile 48 families x 32 sizes), CTA tile 96 families x 128
 //                sizes: exactly two DMMA warps per SM sub-partition, one of each group.  All eight consume the same
 //                shared-memory ring (2 stages of 2 K blocks), so the matrix tile (B) is fetched once per CTA.  Consumers
-//                touch shared memory only: no global loads, no global stores, no membar.
-//   warp 0       TMA producer (one lane): child vectors (A, 96 x 16 sizes) and matrix K-blocks (B, 128 rows x 16 sizes).
+//                touch shared memory only: no global loads, no global stores, no membar.  Fragment loads go through
+//                32-bit shared addresses with immediate offsets (a ring-stage boundary is ~30 integer instructions).
+//   warp 0       TMA producer (one lane): child vectors (A, 96 x 16 sizes) and matrix K-blocks (B, 128 rows x 16 sizes;
+//                the B maps end at the op's last size, so TMA zero-fills the rows of sizes that do not exist).
 //   warps 1..2   leaf-pair gatherers: a node whose two children are leaves has the vector M_a[.][c_a] * M_b[.][c_b]
 //                (cafe_tree.c:204-210); the gatherers write these vectors one pair of tiles ahead into scratch slots of
-//                their own, the parent's GEMM streams them like any other vector.
+//                their own, the parent's GEMM streams them like any other vector.  One progress counter per gatherer.
 //   warp 3       epilogue manager: stages the sibling factor of the next pass in the 96 KB C tile (TMA for a stored
 //                partial product, cp.async row gathers for a leaf sibling), and writes the finished tile back with
 //                TMA stores.  Consumers multiply in place (C = acc * C).  All fences live in this warp.
 //
-// Two restructurings of this kernel were measured in round 2 and lost (profiles/r2_k2_experiments.md): per-group C halves
-// with the groups one ring stage apart (4 stages of 1 K block: 3.82 ms), and a register epilogue straight to global memory
-// with a 7-stage ring (5.0 ms), against 3.72 ms here.
+// Round-2 history (profiles/r2_k2_experiments.md): per-group C halves with the groups one ring stage apart (3.82 ms) and a
+// register epilogue straight to global memory (5.0 ms) lost against 3.72 ms for this structure; the lean stage boundary, the
+// sigma permutation of the matrix-tile rows (no lane-dependent access order in the C tile), compile-time epilogue
+// instantiations and the clipped B maps then took it to 3.58 ms at configs[1] and 132.8 ms (0.93 of cuBLAS DGEMM) at
+// configs[2].  k_prune_fused2<.., WIN = true> is the windowed instantiation for the conditional distribution and the p-values.
 //
 // Bit-for-bit the same arithmetic as prune_fused.cu / prune.cu (same DMMA order over K, one rounding per product).
 #include <cuda.h>
