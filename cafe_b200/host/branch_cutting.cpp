@@ -20,6 +20,7 @@
 #include <functional>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 
 #include "cafe_math.h"
 #include "cafe_param.h"
@@ -92,7 +93,7 @@ struct Side {
         ck(ctx, cafe_gpu_set_prior(ctx, unit.data(), (int)unit.size()), "set_prior");
     }
     // cafe_conditional_distribution on this side (cafe/conditional_distribution.cpp:86-120), rows flattened
-    std::vector<double> distribution(const SideTree& s, const family_size_range& rg, int n_samples, bool replay) {
+    std::vector<double> distribution(const SideTree& s, const family_size_range& rg, int n_samples, bool replay, uint64_t seed) {
         const int R = rg.root_max - rg.root_min + 1;
         std::vector<double> flat((size_t)R * n_samples);
         if (replay) {  // the draws the single-threaded reference would make, in its order
@@ -100,7 +101,6 @@ struct Side {
             for (double& x : u) x = cafe::unifrnd();
             ck(ctx, cafe_gpu_conditional_distribution(ctx, n_samples, u.data(), 0, flat.data()), "conditional_distribution");
         } else {
-            const uint64_t seed = ((uint64_t)std::rand() << 32) ^ (uint64_t)std::rand();
             ck(ctx, cafe_gpu_conditional_distribution(ctx, n_samples, nullptr, seed, flat.data()), "conditional_distribution");
         }
         return flat;
@@ -153,8 +153,6 @@ void cafe_branch_cutting(pCafeParam param, int num_random_samples) {
     const int R = rg.root_max - rg.root_min + 1;
     const char* mode = std::getenv("CAFE_GPU_CD_RNG");
     const bool replay = mode ? std::strcmp(mode, "replay") == 0 : param->num_threads <= 1;
-    int device = 0;
-    if (const char* d = std::getenv("CAFE_GPU_DEVICE")) device = std::atoi(d);
 
     std::vector<int> node_species(nnodes, -1);  // leaf node id -> column of the family table (set_size_for_split, :61-87)
     for (int i = 0; i < fam->num_species; ++i)
@@ -171,20 +169,28 @@ void cafe_branch_cutting(pCafeParam param, int num_random_samples) {
     }
 
     param->cutPvalues.assign(nnodes, std::vector<double>(nrows, 0.0));
-    for (int b = 0; b < nnodes; ++b) {
-        if (b == t.root) { std::fill(param->cutPvalues[b].begin(), param->cutPvalues[b].end(), -1.0); continue; }  // :236-240
+    std::vector<std::string> logs(nnodes);
+    const bool tree_level_mu = param->lrt_tree_level_mu != 0;
+    // device-generator seeds of the two distributions of every branch, drawn here in branch order: the result does not depend
+    // on how the branches are spread over devices (unused with the rand() replay)
+    std::vector<uint64_t> seeds(2 * (size_t)nnodes, 0);
+    if (!replay)
+        for (uint64_t& x : seeds) x = ((uint64_t)std::rand() << 32) ^ (uint64_t)std::rand();
+    // one branch: both sides of the cut on `device`, the row of cutPvalues and the log text of cut_branch
+    auto do_branch = [&](int b, int device) {
+        if (b == t.root) { std::fill(param->cutPvalues[b].begin(), param->cutPvalues[b].end(), -1.0); return; }  // :236-240
         SideTree rest, sub;
         split_tree(t, b, rest, sub);
         std::ostringstream ost;
         ost << ">> " << b << "  --------------------\n" << side_string(t, rest) << "\n" << side_string(t, sub) << "\n";
-        cafe_log(param, "%s", ost.str().c_str());
+        logs[b] = ost.str();
         std::vector<double> cut(tested.size(), 0.0);
         const bool one = sub.n() == 1 || rest.n() == 1;
         if (one) {
             const SideTree& s = (sub.n() == 1) ? rest : sub;  // :192-201
             Side side;
-            side.setup(t, s, rg, param->lrt_tree_level_mu != 0, device);
-            std::vector<double> cd = side.distribution(s, rg, num_random_samples, replay);
+            side.setup(t, s, rg, tree_level_mu, device);
+            std::vector<double> cd = side.distribution(s, rg, num_random_samples, replay, seeds[2 * b]);
             if (!tested.empty()) {
                 std::vector<double> L = side.likelihood_rows(t, s, fam, tested, node_species, R);
                 ck(side.ctx, cafe_gpu_cut_pvalues(side.ctx, L.data(), nullptr, (int)tested.size(), R, cd.data(), nullptr, num_random_samples, cut.data()), "cut_pvalues");
@@ -193,10 +199,10 @@ void cafe_branch_cutting(pCafeParam param, int num_random_samples) {
             const int n10 = num_random_samples / 10;  // :204
             if (n10 < 1) throw std::runtime_error("branch cutting: fewer than 10 random samples");
             Side a, c;
-            a.setup(t, rest, rg, param->lrt_tree_level_mu != 0, device);
-            c.setup(t, sub, rg, param->lrt_tree_level_mu != 0, device);
-            std::vector<double> cd1 = a.distribution(rest, rg, n10, replay);
-            std::vector<double> cd2 = c.distribution(sub, rg, n10, replay);
+            a.setup(t, rest, rg, tree_level_mu, device);
+            c.setup(t, sub, rg, tree_level_mu, device);
+            std::vector<double> cd1 = a.distribution(rest, rg, n10, replay, seeds[2 * b]);
+            std::vector<double> cd2 = c.distribution(sub, rg, n10, replay, seeds[2 * b + 1]);
             if (!tested.empty()) {
                 std::vector<double> L1 = a.likelihood_rows(t, rest, fam, tested, node_species, R);
                 std::vector<double> L2 = c.likelihood_rows(t, sub, fam, tested, node_species, R);
@@ -210,7 +216,26 @@ void cafe_branch_cutting(pCafeParam param, int num_random_samples) {
             if (param->max_pvalues[i] > param->pvalue) row[i] = -1.0;
         }
         for (size_t j = 0; j < tested.size(); ++j) row[tested[j]] = cut[j];
+    };
+    // The branches are independent.  With the rand() replay they must run in order (the stream is shared); with the device
+    // generator and several devices (CAFE_GPUS) every device takes every n-th branch on a host thread of its own - the reference
+    // spreads the FAMILIES of a branch over its pthreads instead (:242-258), the result is the same.
+    const std::vector<int> devices = cafe_gpu_engine_devices();
+    if (replay || devices.size() < 2) {
+        for (int b = 0; b < nnodes; ++b) do_branch(b, devices[0]);
+    } else {
+        std::vector<std::string> errors(devices.size());
+        std::vector<std::thread> workers;
+        for (size_t d = 0; d < devices.size(); ++d)
+            workers.emplace_back([&, d]() {
+                try {
+                    for (int b = (int)d; b < nnodes; b += (int)devices.size()) do_branch(b, devices[d]);
+                } catch (std::exception& e) { errors[d] = e.what(); }
+            });
+        for (std::thread& w : workers) w.join();
+        for (const std::string& e : errors) if (!e.empty()) throw std::runtime_error(e);
     }
+    for (int b = 0; b < nnodes; ++b) if (!logs[b].empty()) cafe_log(param, "%s", logs[b].c_str());
     for (size_t i = 0; i < nrows; ++i) {  // duplicates take their first occurrence's values, :259-267
         const int ref = fam->flist[i].ref;
         if (ref < 0 || ref == (int)i) continue;

@@ -191,6 +191,12 @@ static std::vector<int> engine_devices() {
     return dev;
 }
 
+std::vector<int> cafe_gpu_engine_devices() {
+    std::vector<int> dev = engine_devices();
+    if (dev.empty()) dev.push_back(-1);  // the current device
+    return dev;
+}
+
 cafe_gpu_ctx* cafe_gpu_engine() {
     if (!g_eng.ctx) {
         const std::vector<int> dev = engine_devices();

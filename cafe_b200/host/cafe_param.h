@@ -68,6 +68,7 @@ void cafe_log(pCafeParam param, const char* msg, ...);
 // --- the GPU engine behind the reference's entry points (replaces the global probability_cache) ---
 cafe_gpu_ctx* cafe_gpu_engine();   // lazily created; throws std::runtime_error when no device
 void cafe_gpu_engine_release();
+std::vector<int> cafe_gpu_engine_devices();  // CAFE_GPUS as a device list; {-1} (the current device) when unset
 // push tree / ranges / families / error models / prior to the device when they changed
 void cafe_gpu_sync_state(pCafeFamily pfamily, pCafeTree pcafe, const double* prior_rfsize);
 

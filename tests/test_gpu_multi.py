@@ -159,3 +159,32 @@ def test_host_shell_lambda_search_on_two_gpus(tmp_path):
     last = [float(ln.split("Score:")[1].split()[0]) for ln in (lam[0][-1], lam[1][-1])]
     assert abs(last[0] - last[1]) <= 1e-9 * abs(last[0])
     assert lam[0][-1].split("&")[0] == lam[1][-1].split("&")[0]  # lambda-hat printed identically
+
+
+@needs2
+def test_branch_cutting_spreads_branches_over_two_gpus(tmp_path):
+    """`report ... branchcutting` with the device generator (more than one thread): with CAFE_GPUS=2 the branches alternate between
+    the devices on two host threads; the seeds are drawn in branch order beforehand, so the report is the same file."""
+    from cafe_b200 import buildlib
+    rs = np.random.RandomState(4)
+    counts = rs.poisson(6, size=(40, 5))
+    tab = tmp_path / "fam.tab"
+    with open(tab, "w") as f:
+        f.write("\t".join(["Desc", "Family ID", "chimp", "human", "mouse", "rat", "dog"]) + "\n")
+        for i, r in enumerate(counts):
+            f.write("\t".join(["d", "F%d" % i] + [str(int(x)) for x in r]) + "\n")
+    outs = []
+    for gpus in (None, "2"):
+        script = tmp_path / ("run%s.sh" % (gpus or "1"))
+        rep = tmp_path / ("rep%s" % (gpus or "1"))
+        script.write_text("seed 10\nload -i %s -t 4 -r 60 -p 0.9\ntree (((chimp:6,human:6):81,(mouse:17,rat:17):70):6,dog:93)\n"
+                          "lambda -l 0.006\nreport %s branchcutting\n" % (tab, rep))
+        env = dict(os.environ)
+        env.pop("CAFE_GPUS", None)
+        if gpus:
+            env["CAFE_GPUS"] = gpus
+        r = subprocess.run([buildlib.SHELL_BIN, str(script)], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(open(str(rep) + ".cafe").read())
+    cut = [[ln.split("\t")[4] for ln in o.split("\n") if ln.startswith("F")] for o in outs]
+    assert len(cut[0]) == 40 and cut[0] == cut[1]
