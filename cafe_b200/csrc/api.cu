@@ -210,10 +210,14 @@ static int one_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, con
     const int F = n_families, F_pad = round_up(F, 128);
     std::vector<int> T((size_t)n_leaves * F_pad, 0), mult(F_pad, 0), first(F_pad, 0);
     int mx = 0;
+    bool missing = false;
     for (int f = 0; f < F; ++f) {
         for (int k = 0; k < n_leaves; ++k) {
             int c = counts[(size_t)f * n_leaves + k];
-            if (c < 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_families: negative count");
+            // -1: the species has no column in the family table (familysize < 0, cafe_family.c:214-216).  Only the Viterbi
+            // reconstruction defines a meaning for it (viterbi.cpp:236-250); the likelihood paths refuse such a table (check_ready).
+            if (c < -1) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_families: negative count");
+            if (c < 0) missing = true;
             mx = std::max(mx, c);
             T[(size_t)k * F_pad + f] = c;
         }
@@ -241,7 +245,7 @@ static int one_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, con
     CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_mult, mult.data(), F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CAFE_CK(ctx, cudaMemcpyAsync(ctx->d_first, first.data(), F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->F = F; ctx->F_pad = F_pad; ctx->max_count = mx;
+    ctx->F = F; ctx->F_pad = F_pad; ctx->max_count = mx; ctx->has_missing = missing;
     ctx->h_counts.assign(counts, counts + (size_t)F * n_leaves);
     ctx->results_valid = false;
     return CAFE_GPU_OK;
@@ -495,7 +499,9 @@ int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad) {
 
 extern "C" {
 
-static int check_ready(cafe_gpu_ctx* ctx, const char* who) {
+static int check_ready(cafe_gpu_ctx* ctx, const char* who, bool missing_ok = false) {
+    if (ctx->has_missing && !missing_ok)
+        CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, std::string(who) + ": a leaf without data (count -1) - only cafe_gpu_viterbi reconstructs such families; the reference's pruning asserts (cafe_tree.c:207)");
     if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + (ctx->matrices_need_exchange ? ": all-gather the matrices and call cafe_gpu_matrices_exchanged first" : ": build_matrices first"));
     if (ctx->F == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + ": set_families first");
     if (!ctx->d_logprior) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, std::string(who) + ": set_prior first");
@@ -538,7 +544,7 @@ static int one_family_results(cafe_gpu_ctx* ctx, double* log_max_posterior, doub
 
 static int one_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_likelihood_out) {
     if (!ctx || !node_sizes_out) return CAFE_GPU_ERR_ARG;
-    int rc = check_ready(ctx, "viterbi");
+    int rc = check_ready(ctx, "viterbi", true);
     if (rc) return rc;
     return run_viterbi(ctx, node_sizes_out, max_likelihood_out, false, nullptr);
 }
@@ -593,6 +599,7 @@ static int one_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_s
     if (!ctx || !cd || !max_pvalue_out || cd_rows < 1 || n_samples < 1) return CAFE_GPU_ERR_ARG;
     if (!ctx->matrices_valid) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "pvalues: build_matrices first");
     if (ctx->F == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "pvalues: set_families first");
+    if (ctx->has_missing) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "pvalues: a leaf without data (count -1): the reference's pruning asserts (cafe_tree.c:207)");
     return run_pvalues(ctx, cd, cd_rows, n_samples, max_pvalue_out);
 }
 

@@ -99,6 +99,7 @@ struct cafe_gpu_ctx {
     int* d_first = nullptr;   // [F_pad]
     std::vector<int> h_counts;  // [F][n_leaves] as given
     int max_count = 0;
+    bool has_missing = false;   // some leaf count is -1 (a species without data): Viterbi only
 
     // prior
     double* d_logprior = nullptr;  // [R] log(prior[i])

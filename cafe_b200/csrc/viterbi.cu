@@ -8,7 +8,9 @@
 // A (max, x) semiring product has no tensor-core form; the kernel keeps the K2 layout instead (transposed matrices, so that the
 // threads of a block - consecutive output sizes - read consecutive addresses, 8 families per block to reuse every matrix element
 // from registers) and is bound by the fp64 pipe (one DMUL + one compare per matrix element and family).
-// Every leaf must carry an observed size (the reference's "familysize < 0" branch for missing data is not implemented).
+// A leaf with count -1 carries no data (the reference's "familysize < 0" branch, viterbi.cpp:236-250): its vector is all ones over
+// its PARENT's range (the root range below the root) - zeros beyond, as in a freshly allocated tree - and its size is
+// reconstructed like an ancestor's.  (In the reference the entries beyond keep whatever an earlier family left there.)
 #include <algorithm>
 
 #include "common.cuh"
@@ -55,7 +57,14 @@ k_viterbi_node(VitChild A, VitChild B, int Sp, int Vp, int W, int r0, int nrows,
             if (i < nrows) {
                 for (int u = 0; u < nf; ++u) {
                     const int cnt = C.counts[f0 + u];
-                    if (C.err_rowptr == nullptr) {
+                    if (cnt < 0) {
+                        // no data: L[j] = 1 for the sizes of this node's range (:236-250), so the factor is the row maximum
+                        const int last = is_root ? min(cm[u], nr[u] - 1) : cm[u];
+                        for (int j = 0; j <= last; ++j) {
+                            const double v = C.MT[(size_t)j * Sp + r0 + i];
+                            if (v > best[u]) { best[u] = v; arg[u] = j; }
+                        }
+                    } else if (C.err_rowptr == nullptr) {
                         // one-hot leaf (:262-266): the only non-zero product is M[s][count]
                         const double v = (cnt <= cm[u]) ? C.MT[(size_t)cnt * Sp + r0 + i] : 0.0;
                         if (v > 0.0) { best[u] = v; arg[u] = cnt; }
@@ -118,7 +127,10 @@ k_viterbi_backtrack(const int* __restrict__ prefix, int n_prefix, const int* __r
     int* sz = sizes_out + (size_t)(fam0 + f) * n_nodes;
     for (int p = 0; p < n_prefix; ++p) {
         const int v = prefix[p];
-        if (is_leaf[v]) { sz[v] = counts[(size_t)leaf_ord[v] * F_pad + fam0 + f]; continue; }
+        if (is_leaf[v]) {
+            const int c = counts[(size_t)leaf_ord[v] * F_pad + fam0 + f];
+            if (c >= 0) { sz[v] = c; continue; }  // observed leaves keep their size (:327); one without data is reconstructed
+        }
         if (v == root) {
             const double* L = Lroot + (size_t)f * Vp;
             double ml = (R > 0) ? L[0] : 0.0; int am = 0;

@@ -89,7 +89,10 @@ int cafe_gpu_set_lnc_table(cafe_gpu_ctx* ctx, const double* lnc, int rows, int c
 /* Unique family count patterns: counts[f*n_leaves + k] = size of family f in leaf k (leaf order).
  * multiplicity (NULL => 1): how many families of the original list share the pattern (the `ref`
  * short-cut of cafe/lambda.cpp:702-714, cafe/cafe_family.c:9-34).  first_index (NULL => f): index
- * of the first such family in the original list, reported by cafe_gpu_score on zero likelihood. */
+ * of the first such family in the original list, reported by cafe_gpu_score on zero likelihood.
+ * A count of -1 marks a species of the tree without data (familysize < 0 after cafe_family_set_size, cafe/cafe_family.c:214-216):
+ * cafe_gpu_viterbi reconstructs it; every likelihood entry point refuses such a table (the reference's pruning asserts,
+ * cafe/cafe_tree.c:207). */
 int cafe_gpu_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, const int32_t* counts,
                           const int32_t* multiplicity, const int32_t* first_index);
 
@@ -174,7 +177,9 @@ int cafe_gpu_family_likelihoods(cafe_gpu_ctx* ctx, double* L_out);
 /* Viterbi ancestral reconstruction (cafe_tree_viterbi, cafe/viterbi.cpp:494-521; max-product pruning :209-321 and
  * back-track :323-351) for every family with the current matrices: node_sizes_out[f * n_nodes + v] = reconstructed size of
  * node v (nlist order; leaves keep their observed size), max_likelihood_out[f] (nullable) = max_i of the root's max-product
- * vector.  Every leaf must carry an observed size (missing data, familysize < 0, is not supported). */
+ * vector.  A leaf with count -1 carries no data (the familysize < 0 branch, :236-250): its vector is all ones over its parent's
+ * range - zeros beyond, as in a freshly allocated tree; the reference keeps there what an earlier family left - and its size
+ * is reconstructed like an ancestor's. */
 int cafe_gpu_viterbi(cafe_gpu_ctx* ctx, int32_t* node_sizes_out, double* max_likelihood_out);
 /* The same as the `report` command runs it (viterbi_section, cafe/viterbi.cpp:88-119): every family with its own forced range
  * (cafe_family_set_size_with_family_forced, cafe/cafe_family.c:236-255: root 1..rint(1.25*max_f), sizes 0..max_f+max(50,max_f/5)),

@@ -377,7 +377,7 @@ double orc_family_pvalue(int n_nodes, const int *left, const int *right, int roo
 /* cafe_tree_viterbi (cafe/viterbi.cpp:494-521): max-product pruning in post-order
  * (__cafe_tree_node_compute_viterbi :209-321) followed by the back-track in prefix order
  * (__cafe_tree_node_backtrack_viterbi :323-351).  All leaves carry an observed size (the reference's
- * "familysize < 0" branch for missing data is not restated).  sizes_out[v] = reconstructed size of node v
+ * a leaf with leaf_count < 0 has no data: the "familysize < 0" branch, restated for a fresh tree, see vit_node).  sizes_out[v] = reconstructed size of node v
  * (leaves keep their observed size); *root_max_lik = max_i L_root[i].
  * Per child: factor[i] = max_j M_child[s][c] * L_child[j] with a strict ">" from 0 (first maximum wins; a row
  * whose products are all 0 keeps back-pointer 0, the calloc'ed initial value of pcnode->viterbi). */
@@ -389,12 +389,20 @@ typedef struct {
     double *lik; int *vit; double *f[2];
 } vit_ctx;
 
-static void vit_node(vit_ctx *cx, int v)
+static void vit_node(vit_ctx *cx, int v, int parent_is_root)
 {
     double *Lv = cx->lik + (size_t)v * cx->size_of_factor;
     if (cx->left[v] < 0) { /* leaf, :251-267 */
         memset(Lv, 0, sizeof(double) * cx->size_of_factor);
         int fs = cx->leaf_count[v];
+        if (fs < 0) {
+            /* no data for this species (:236-250): likelihoods[i] = 1 for the sizes of the PARENT's range - the root range when
+             * the parent is the root (:221-230) - and whatever the array held before elsewhere: zeros in a fresh tree, which is
+             * what is restated here.  (The leaf's own factors / viterbi pointers of :240-249 are overwritten by the parent.) */
+            int n1 = parent_is_root ? (cx->root_max - cx->root_min + 1) : (cx->rmax - cx->rmin + 1);
+            for (int i = 0; i < n1 && i < cx->size_of_factor; i++) Lv[i] = 1;
+            return;
+        }
         if (cx->leaf_err && cx->leaf_err[v]) {
             for (int j = 0; j < cx->size_of_factor; j++) Lv[j] = (fs < cx->E && j < cx->E) ? cx->leaf_err[v][(size_t)fs * cx->E + j] : 0.0;
         } else {
@@ -403,8 +411,8 @@ static void vit_node(vit_ctx *cx, int v)
         return;
     }
     int child[2] = { cx->left[v], cx->right[v] };
-    vit_node(cx, child[0]);
-    vit_node(cx, child[1]);
+    vit_node(cx, child[0], v == cx->root);
+    vit_node(cx, child[1], v == cx->root);
     int r0 = (v == cx->root) ? cx->root_min : cx->rmin, r1 = (v == cx->root) ? cx->root_max : cx->rmax; /* :273-286 */
     for (int idx = 0; idx < 2; idx++) { /* :291-311 */
         const double *M = cx->node_matrix[child[idx]];
@@ -434,12 +442,12 @@ int orc_viterbi(int n_nodes, const int *left, const int *right, int root, const 
     cx.size_of_factor = ORC_MAX(rsize, fsize);
     if (cx.size_of_factor < S) cx.size_of_factor = S;
     for (int v = 0; v < n_nodes; v += 2)
-        if (leaf_count[v] < 0 || leaf_count[v] >= cx.size_of_factor) return 1;
+        if (leaf_count[v] >= cx.size_of_factor) return 1; /* leaf_count < 0: a species without data (missing) */
     cx.lik = (double *)calloc((size_t)n_nodes * cx.size_of_factor, sizeof(double));
     cx.vit = (int *)calloc((size_t)n_nodes * cx.size_of_factor, sizeof(int));
     cx.f[0] = (double *)calloc(cx.size_of_factor, sizeof(double));
     cx.f[1] = (double *)calloc(cx.size_of_factor, sizeof(double));
-    vit_node(&cx, root);
+    vit_node(&cx, root, 0);
     /* back-track in prefix order: node, head subtree, tail subtree (tree.c:101-124) */
     int *parent = (int *)malloc(sizeof(int) * n_nodes), *stack = (int *)malloc(sizeof(int) * (n_nodes + 2));
     for (int i = 0; i < n_nodes; i++) parent[i] = -1;
@@ -449,7 +457,7 @@ int orc_viterbi(int n_nodes, const int *left, const int *right, int root, const 
     while (sp > 0) {
         int v = stack[--sp];
         if (left[v] >= 0) { stack[sp++] = right[v]; stack[sp++] = left[v]; }
-        if (left[v] < 0) { sizes_out[v] = leaf_count[v]; continue; } /* :327 */
+        if (left[v] < 0 && leaf_count[v] >= 0) { sizes_out[v] = leaf_count[v]; continue; } /* :327: observed leaves keep their size */
         if (v == root) { /* :329-339, __maxidx: first maximum */
             const double *L = cx.lik + (size_t)root * cx.size_of_factor;
             int am = 0; double ml = L[0];

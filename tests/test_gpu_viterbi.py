@@ -107,3 +107,37 @@ def test_viterbi_report_forced_ranges_and_branch_pvalues():
     counts = np.maximum(1, _counts(13, 40, 30, 14))
     rg = chost.init_family_size(int(counts.max()))
     _check_report(Problem(nw, counts, 0.01, ranges=(rg["min"], rg["max"], rg["root_min"], rg["root_max"])))
+
+
+@pytest.mark.parametrize("newick,missing,ranges", [
+    (EXAMPLE_TREE, [4], (0, 72, 1, 36)),        # dog: a child of the root, root range narrower than the vector
+    (EXAMPLE_TREE, [0, 1], (0, 72, 1, 36)),     # a whole cherry without data
+    (None, [2, 7], (0, 60, 3, 97)),             # random 13-taxon tree, root range wider than the vector
+])
+def test_viterbi_species_without_data(newick, missing, ranges):
+    """Leaf count -1 = a species of the tree without a column in the table (familysize < 0, cafe/viterbi.cpp:236-250): all-ones
+    leaf vector over the parent's range, the leaf's size reconstructed like an ancestor's.  The oracle is pinned against the
+    reference on exactly this (tests/test_oracle.py::test_ref_viterbi_missing_species_bitwise).  The likelihood paths refuse
+    such a table, as the reference's pruning asserts (cafe_tree.c:207)."""
+    from cafe_b200 import gpu as cgpu
+    nw = newick or random_tree(13, 4)
+    n_leaves = nw.count(",") + 1
+    counts = _counts(n_leaves, 41, 25, 11)
+    counts[:, missing] = -1
+    p = Problem(nw, counts, 0.006, ranges=ranges, prior_lambda=8.0)
+    g = p.make_gpu()
+    sizes, ml = g.viterbi()
+    with pytest.raises(cgpu.CafeGpuError):
+        g.score()
+    with pytest.raises(cgpu.CafeGpuError):
+        g.family_likelihoods()
+    g.close()
+    mats = p.oracle_mats()
+    obs = [k for k in range(n_leaves) if k not in missing]
+    n_diff = 0
+    for f in range(len(counts)):
+        s_o, ml_o = oracle.viterbi(p.otree, mats, counts[f], p.ranges)
+        assert rel_err(ml[f], ml_o, 1e-300) <= 1e-12
+        assert np.array_equal(sizes[f, 0::2][obs], counts[f][obs]) and (sizes[f, 0::2][missing] >= 0).all()
+        n_diff += not np.array_equal(sizes[f], s_o)
+    assert n_diff <= 1, n_diff
