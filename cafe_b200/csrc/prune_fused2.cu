@@ -278,6 +278,7 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
     long long t_wait_done = 0, t_wait_empty = 0;
     const long long t_begin = prof ? clock64() : 0;
     int cherry_units = 0;  // leaf-pair vectors needed so far, in the gatherers' order (pair, op, tile)
+    int p_item = 0;
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
         for (int oi = 0; oi < P.n_ops; ++oi) {
             const Op op = P.ops[oi];
@@ -286,6 +287,7 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
             const int n_chunks = (nrows + TN - 1) / TN;
             for (int h = 0; h < 2; ++h) {
                 if (2 * pair + h >= plan.n_tiles) continue;
+                const long long t_op = prof ? clock64() : 0;
                 if (op.a_kind == 0) {
                     // the vector to stream was stored by an earlier op of this tile: wait until it is visible
                     const long long t0 = prof ? clock64() : 0;
@@ -302,10 +304,12 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
                 }
                 const int a_row = scratch_row0 + (op.a_kind == 0 ? (h * P.n_slots + op.in_slot) * TILE_M : cherry_row(P, pair, h, op.in_slot));
                 for (int ch = 0; ch < n_chunks; ++ch) {
+                    const long long t_item = prof ? clock64() : 0;
+                    long long t_first = 0;
                     for (int kb = 0; kb < n_kblocks; kb += KB_PER_STAGE) {
                         const long long t0 = prof ? clock64() : 0;
                         mbar_wait_sleepy(&ctl->empty[stage], phase ^ 1);
-                        if (prof) t_wait_empty += clock64() - t0;
+                        if (prof) { t_wait_empty += clock64() - t0; if (kb == 0) t_first = clock64(); }
                         const int nsub = min(KB_PER_STAGE, n_kblocks - kb);
                         mbar_arrive_expect_tx(&ctl->full[stage], nsub * SUB_BYTES);
                         for (int j = 0; j < nsub; ++j) {
@@ -315,6 +319,11 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
                         }
                         advance(stage, phase);
                     }
+                    if (prof && P.timeline && p_item < 1024) {
+                        long long* tl = P.timeline + ((size_t)2 * 1024 + p_item) * 4;
+                        tl[0] = t_op; tl[1] = t_item; tl[2] = t_first; tl[3] = clock64();
+                    }
+                    ++p_item;
                 }
             }
         }
@@ -979,7 +988,7 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                     if (lane == 0 && !K2_DBG(2)) mbar_arrive(&ctl->c_done);
                     ++item;
                     if (prof && P.timeline && nw == 0 && lane == 0 && item <= 1024) {
-                        long long* tl = P.timeline + ((size_t)grp * 1024 + (item - 1)) * 4;
+                        long long* tl = P.timeline + ((size_t)grp * 1024 + (item - 1)) * 4;  // block 2 of the timeline: the producer, see producer_main
                         tl[0] = tk0; tl[1] = tk1; tl[2] = tk2; tl[3] = tk2b;
                     }
                     if (prof) { t_kloop += tk1 - tk0; t_wait_c += tk2 - tk1; t_epi += tk2b - tk2; if (flags & 2) t_kloop_cherry += tk1 - tk0; if (reduce_now) t_epi_root += tk2b - tk2; }
@@ -1318,8 +1327,8 @@ int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
     const char* trace_path = std::getenv("CAFE_GPU_TRACE");
     long long* d_trace = nullptr;
     if (trace_path) {
-        CAFE_CK(ctx, cudaMalloc(&d_trace, ((size_t)grid * 4 + 128 + 8192) * sizeof(long long)));
-        CAFE_CK(ctx, cudaMemsetAsync(d_trace, 0, ((size_t)grid * 4 + 128 + 8192) * sizeof(long long), ctx->stream));
+        CAFE_CK(ctx, cudaMalloc(&d_trace, ((size_t)grid * 4 + 128 + 12288) * sizeof(long long)));
+        CAFE_CK(ctx, cudaMemsetAsync(d_trace, 0, ((size_t)grid * 4 + 128 + 12288) * sizeof(long long), ctx->stream));
         P.cta_times = d_trace;
         P.warp_prof = d_trace + (size_t)grid * 4;
         P.timeline = P.warp_prof + 128;
@@ -1332,7 +1341,7 @@ int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
     ctx->launches++;
     CAFE_CK(ctx, cudaGetLastError());
     if (trace_path) {  // debug only: synchronous dump "cta <i> <smid> <start ns> <end ns> <8-family blocks>"
-        std::vector<long long> h((size_t)grid * 4 + 128 + 8192);
+        std::vector<long long> h((size_t)grid * 4 + 128 + 12288);
         CAFE_CK(ctx, cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
         CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(d_trace);
@@ -1345,7 +1354,7 @@ int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
                 std::fprintf(fp, "warp %d %lld %lld %lld %lld %lld %lld %lld %lld\n", w, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
             }
             // per pass of warps 0 and 4 (the two DMMA warps of sub-partition 0): K loop start, K loop end, C tile ready, epilogue end
-            for (int g2 = 0; g2 < 2; ++g2)
+            for (int g2 = 0; g2 < 3; ++g2)
                 for (int it = 0; it < 1024; ++it) {
                     const long long* o = &h[(size_t)grid * 4 + 128 + ((size_t)g2 * 1024 + it) * 4];
                     if (o[0]) std::fprintf(fp, "tl %d %d %lld %lld %lld %lld\n", g2, it, o[0], o[1], o[2], o[3]);
