@@ -292,15 +292,17 @@ static int one_set_error_model(cafe_gpu_ctx* ctx, int leaf, const double* errorm
     if (dim < ctx->rmax + 1) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_error_model: dim must be >= range_max+1");
     std::vector<int> rowptr(dim + 1, 0), col;
     std::vector<double> val;
+    int max_up = 0;
     for (int o = 0; o < dim; ++o) {
         for (int j = 0; j < dim; ++j) {
             double e = errormatrix[(size_t)o * dim + j];
-            if (e != 0.0) { col.push_back(j); val.push_back(e); }
+            if (e != 0.0) { col.push_back(j); val.push_back(e); max_up = std::max(max_up, j - o); }
         }
         rowptr[o + 1] = (int)col.size();
     }
     ErrModelDev E;
     E.dim = dim;
+    E.max_up = max_up;
     CAFE_CK(ctx, cudaMalloc(&E.d_rowptr, rowptr.size() * sizeof(int)));
     CAFE_CK(ctx, cudaMalloc(&E.d_col, std::max<size_t>(1, col.size()) * sizeof(int)));
     CAFE_CK(ctx, cudaMalloc(&E.d_val, std::max<size_t>(1, val.size()) * sizeof(double)));

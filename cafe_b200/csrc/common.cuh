@@ -49,6 +49,7 @@ struct BdKeyParams {
 // zeros for every other j, so the result is identical.
 struct ErrModelDev {
     int dim = 0;
+    int max_up = 0;           // largest (true size - observed size) with a non-zero entry: how far a row reaches above its diagonal
     int* d_rowptr = nullptr;  // [dim+1]
     int* d_col = nullptr;
     double* d_val = nullptr;

@@ -1136,12 +1136,17 @@ bool fused2_supported(const cafe_gpu_ctx* ctx) {
     if (ctx->max_count >= ctx->W) return false;          // a one-hot leaf outside the matvec columns needs the guarded path
     return true;
 }
-// windowed jobs (conditional distribution, p-values): leaves outside a family's window are handled by the window itself, but
-// an error-model leaf would need one matrix per window (k_err_leaf_matrix sums over the columns up to the window)
+// Windowed jobs (conditional distribution, p-values): leaves outside a family's window are handled by the window itself.  An
+// error-model leaf's factor is sum_{j <= window} M[i][j] E[observed][j]: the per-leaf matrix of k_err_leaf_matrix sums over ALL
+// columns, which is the same number as long as no non-zero entry of row `observed` lies above the window.  Every window reaches
+// at least 50 sizes above the family's largest count (cafe_family.c:253, conditional_distribution.cpp:29: max + MAX(50, max/5),
+// capped by the global range where the sums agree anyway), so error models whose rows reach less than 50 sizes above their
+// diagonal - every model the reference's reader and `esterror` produce is a band of a few sizes - take the fused kernel; a wider
+// one falls back to the per-node kernels.
 bool fused2_windowed_supported(const cafe_gpu_ctx* ctx) {
     if (!fused2_tree_supported(ctx)) return false;
     for (int e : ctx->leaf_err)
-        if (e >= 0) return false;
+        if (e >= 0 && ctx->errs[e].max_up >= 50) return false;
     return true;
 }
 

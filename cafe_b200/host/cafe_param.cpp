@@ -149,6 +149,16 @@ void sync_error_models(pCafeFamily f, pCafeTree t) {
     g_eng.err_signature = sig.str();
 }
 
+// The reference runs the conditional distribution, the family p-values / Viterbi pass and the likelihood-ratio test on
+// cafe_tree_copy(...) of the tree (conditional_distribution.cpp:77, viterbi.cpp:125, cafe_main.c:347), and cafe_tree_node_copy
+// (cafe_tree.c:485-494) copies lambda, family size and matrix pointer only: those passes see NO error model, whatever the
+// `errormodel` command attached (the stock binary's report is the same file with and without it).  So do ours.
+void sync_without_error_models() {
+    if (g_eng.err_signature == "-") return;
+    gpu_check(cafe_gpu_set_error_model(g_eng.ctx, -1, nullptr, 0), "set_error_model(clear)");
+    g_eng.err_signature = "-";
+}
+
 void sync_prior(const double* prior, int R) {
     if ((int)g_eng.prior.size() == R && std::equal(prior, prior + R, g_eng.prior.begin())) return;
     gpu_check(cafe_gpu_set_prior(g_eng.ctx, prior, R), "set_prior");
@@ -212,12 +222,13 @@ void cafe_gpu_engine_release() {
     g_eng = EngineState();
 }
 
-void cafe_gpu_sync_state(pCafeFamily pfamily, pCafeTree pcafe, const double* prior_rfsize) {
+void cafe_gpu_sync_state(pCafeFamily pfamily, pCafeTree pcafe, const double* prior_rfsize, bool with_error_models) {
     cafe_gpu_engine();
     sync_tree(pcafe);
     sync_ranges(pcafe->range);
     if (pfamily) sync_family(pfamily, pcafe);
-    sync_error_models(pfamily, pcafe);
+    if (with_error_models) sync_error_models(pfamily, pcafe);
+    else sync_without_error_models();
     if (prior_rfsize) sync_prior(prior_rfsize, pcafe->rfsize);
 }
 
@@ -543,6 +554,7 @@ matrix cafe_conditional_distribution(pCafeTree pTree, family_size_range* range, 
     family_size_range rg = pTree->range;
     rg.root_min = range->root_min; rg.root_max = range->root_max;
     sync_ranges(rg);
+    sync_without_error_models();  // the thread's tree copy carries none (conditional_distribution.cpp:77)
     if (!g_eng.matrices_valid) { push_rates(pTree); gpu_check(cafe_gpu_build_matrices(g_eng.ctx), "build_matrices"); g_eng.matrices_valid = true; }
     const int R = rg.root_max - rg.root_min + 1;
     std::vector<double> flat((size_t)R * num_random_samples);
@@ -565,7 +577,7 @@ matrix cafe_conditional_distribution(pCafeTree pTree, family_size_range* range, 
 
 void cafe_family_pvalues(pCafeParam param, std::vector<double>& max_pvalues) {
     if (param->cond_dist.empty()) throw std::runtime_error("conditional distribution not computed");
-    cafe_gpu_sync_state(param->pfamily, param->pcafe, param->prior_rfsize);
+    cafe_gpu_sync_state(param->pfamily, param->pcafe, param->prior_rfsize, false);  // viterbi.cpp:125: a copy without error models
     if (!g_eng.matrices_valid) {
         reset_birthdeath_cache(param->pcafe, 0, &param->family_size);
     }
@@ -580,7 +592,7 @@ void cafe_family_pvalues(pCafeParam param, std::vector<double>& max_pvalues) {
 
 void cafe_viterbi_all(pCafeParam param, std::vector<int>& node_sizes, std::vector<double>& branch_pvalues) {
     std::vector<double> unit_prior(param->pcafe->rfsize, 1.0);
-    cafe_gpu_sync_state(param->pfamily, param->pcafe, param->prior_rfsize ? param->prior_rfsize : unit_prior.data());
+    cafe_gpu_sync_state(param->pfamily, param->pcafe, param->prior_rfsize ? param->prior_rfsize : unit_prior.data(), false);  // viterbi.cpp:125
     if (!g_eng.matrices_valid) reset_birthdeath_cache(param->pcafe, 0, &param->family_size);
     const int nnodes = param->pcafe->num_nodes();
     const size_t nrows = param->pfamily->flist.size(), U = g_eng.unique_first.size();
@@ -599,7 +611,7 @@ void cafe_viterbi_all(pCafeParam param, std::vector<int>& node_sizes, std::vecto
 void cafe_likelihood_ratio_test(pCafeParam param, double* maximumPvalues) {
     cafe_log(param, "Running Likelihood Ratio Test....\n");
     std::vector<double> unit_prior(param->pcafe->rfsize, 1.0);
-    cafe_gpu_sync_state(param->pfamily, param->pcafe, param->prior_rfsize ? param->prior_rfsize : unit_prior.data());
+    cafe_gpu_sync_state(param->pfamily, param->pcafe, param->prior_rfsize ? param->prior_rfsize : unit_prior.data(), false);  // cafe_main.c:347
     if (!g_eng.matrices_valid) reset_birthdeath_cache(param->pcafe, 0, &param->family_size);
     const int nnodes = param->pcafe->num_nodes();
     const size_t nrows = param->pfamily->flist.size(), U = g_eng.unique_first.size();

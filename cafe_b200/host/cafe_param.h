@@ -70,7 +70,8 @@ cafe_gpu_ctx* cafe_gpu_engine();   // lazily created; throws std::runtime_error 
 void cafe_gpu_engine_release();
 std::vector<int> cafe_gpu_engine_devices();  // CAFE_GPUS as a device list; {-1} (the current device) when unset
 // push tree / ranges / families / error models / prior to the device when they changed
-void cafe_gpu_sync_state(pCafeFamily pfamily, pCafeTree pcafe, const double* prior_rfsize);
+// with_error_models = false: the passes the reference runs on a copy of the tree, which drops the leaves' error models (cafe_param.cpp)
+void cafe_gpu_sync_state(pCafeFamily pfamily, pCafeTree pcafe, const double* prior_rfsize, bool with_error_models = true);
 
 // cafe/cafe_main.c:319-326 — rebuild every (int t, lambda, mu) matrix for the tree's per-node rates   [K1]
 void reset_birthdeath_cache(pCafeTree tree, int k_value, family_size_range* range);

@@ -75,7 +75,7 @@ def lib():
     L.orc_random_familysize.restype = C.c_int
     L.orc_random_familysize.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, C.c_int, C.c_int, _dp, _lp, _ip]
     L.orc_random_probabilities.argtypes = [C.c_int, _ip, _ip, C.c_int, _dpp, C.c_int, C.c_int, C.c_int,
-                                           C.c_int, C.c_int, _dp, _lp, _dp, _dp, _ip, _ip]
+                                           C.c_int, C.c_int, _dp, _lp, _dp, _dp, _ip, _ip, _dpp, C.c_int]
     L.orc_pvalue.restype = C.c_double
     L.orc_pvalue.argtypes = [C.c_double, _dp, C.c_int]
     L.orc_init_family_size.argtypes = [C.c_int, _ip, _ip, _ip, _ip]
@@ -412,7 +412,7 @@ def prior_poisson(shift, lam, n=1000):
     return np.array([lib().orc_poisspdf(shift - 1 + i, lam) for i in range(n)])
 
 
-def random_probabilities(tree, mats, rng_min, rng_max, root_size, trials, uniforms=None):
+def random_probabilities(tree, mats, rng_min, rng_max, root_size, trials, uniforms=None, leaf_err=None):
     S = next(m for m in mats if m is not None).shape[0]
     mp, keep = _matrix_ptrs(mats)
     used = C.c_long(0)
@@ -424,9 +424,14 @@ def random_probabilities(tree, mats, rng_min, rng_max, root_size, trials, unifor
     if uniforms is not None:
         uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
         up = _dptr(uniforms)
+    E = 0
+    ep = None
+    if leaf_err is not None:
+        ep, keep2 = _matrix_ptrs(leaf_err)
+        E = next(m for m in leaf_err if m is not None).shape[0]
     lib().orc_random_probabilities(tree.n_nodes, _iptr(tree.left), _iptr(tree.right), tree.root, mp, S,
                                    rng_min, rng_max, root_size, trials, up, C.byref(used),
-                                   _dptr(srt), _dptr(uns), _iptr(sizes), _iptr(caps))
+                                   _dptr(srt), _dptr(uns), _iptr(sizes), _iptr(caps), ep, E)
     return {"sorted": srt, "unsorted": uns, "sizes": sizes, "caps": caps, "used": used.value}
 
 
@@ -497,7 +502,7 @@ def simulate_families(tree: FlatTree, lam_per_node, mu_per_node, maxfs, n_famili
     return sizes[:, 0::2].astype(np.int32)
 
 
-def conditional_distribution(tree: FlatTree, mats, ranges, n_samples, uniforms=None):
+def conditional_distribution(tree: FlatTree, mats, ranges, n_samples, uniforms=None, leaf_err=None):
     """cafe/conditional_distribution.cpp:48-57 single-threaded: rows for s = root_min..root_max.
     uniforms (optional): the unifrnd() stream in the reference's order; None draws from glibc rand()."""
     rmin, rmax, root_min, root_max = ranges
@@ -506,7 +511,7 @@ def conditional_distribution(tree: FlatTree, mats, ranges, n_samples, uniforms=N
     per_row = n_samples * (tree.n_nodes - 1)
     for s in range(root_min, root_max + 1):
         u = None if uniforms is None else uniforms[off:off + per_row]
-        r = random_probabilities(tree, mats, rmin, rmax, s, n_samples, u)
+        r = random_probabilities(tree, mats, rmin, rmax, s, n_samples, u, leaf_err=leaf_err)
         rows.append(r["sorted"])
         off += per_row
     return np.array(rows)

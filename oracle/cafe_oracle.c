@@ -300,8 +300,10 @@ static int cmp_double(const void *a, const void *b)
 void orc_random_probabilities(int n_nodes, const int *left, const int *right, int root,
                               const double *const *node_matrix, int S, int range_min, int range_max,
                               int root_size, int trials, const double *uniforms, long *n_used,
-                              double *probs_sorted, double *probs_unsorted, int *leaf_sizes, int *caps)
-/* conditional_distribution.cpp:10-44 */
+                              double *probs_sorted, double *probs_unsorted, int *leaf_sizes, int *caps,
+                              const double *const *leaf_err, int E)
+/* conditional_distribution.cpp:10-44.  leaf_err (nullable): the error models attached to the tree's leaves - compute_tree_likelihoods
+ * applies them to the simulated leaf sizes exactly as to observed ones (cafe_tree.c:196-203). */
 {
     int rmax = range_max;
     int maxFamilySize = ORC_MAX(root_size, range_max); /* :20 (root_max == root_size here) */
@@ -315,7 +317,7 @@ void orc_random_probabilities(int n_nodes, const int *left, const int *right, in
         double L0 = 0;
         /* a simulated leaf size above the (ratcheted) column window contributes 0 (cafe_tree.c:223);
          * in the reference the one-hot lands outside cols min..max of the matvec. */
-        orc_prune(n_nodes, left, right, root, node_matrix, S, sizes, NULL, 0, range_min, rmax, root_size, root_size, &L0);
+        orc_prune(n_nodes, left, right, root, node_matrix, S, sizes, leaf_err, E, range_min, rmax, root_size, root_size, &L0);
         probs_sorted[i] = L0;
     }
     if (probs_unsorted) memcpy(probs_unsorted, probs_sorted, sizeof(double) * trials);

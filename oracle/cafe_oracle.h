@@ -96,7 +96,8 @@ void orc_random_probabilities(int n_nodes, const int *left, const int *right, in
                               int range_min, int range_max, int root_size, int trials,
                               const double *uniforms, long *n_used, double *probs_sorted,
                               double *probs_unsorted /* optional */, int *leaf_sizes /* optional [trials][n_nodes] */,
-                              int *caps /* optional [trials] */);
+                              int *caps /* optional [trials] */,
+                              const double *const *leaf_err, int E);
 
 /* libcommon/mathfunc.c:663-689 */
 double orc_pvalue(double v, const double *conddist, int size);

@@ -202,3 +202,37 @@ def test_k4_k5_fused_windowed_path_equals_per_node_kernels(monkeypatch):
     ref = np.array([oracle.family_pvalue(p.otree, mats, counts[f], cd_fused)[0] for f in idx])
     assert np.abs(pv_fused[idx] - ref).max() <= 1.0 / n + 1e-12
     g.close()
+
+
+def _band_error_model(dim, eps, reach=1):
+    E = np.zeros((dim, dim))
+    for j in range(dim):
+        for d in range(-reach, reach + 1):
+            if 0 <= j + d < dim:
+                E[j + d, j] = (1 - 2 * eps) if d == 0 else eps / reach
+    return E
+
+
+@pytest.mark.parametrize("reach", [1, 3, 55])
+def test_k4_error_model_leaves_through_the_abi(reach, monkeypatch):
+    # The C-ABI applies the leaves' error models to the SIMULATED sizes, as get_random_probabilities does on a tree that carries
+    # them (test_oracle.py::test_ref_conditional_distribution_with_error_model_bitwise, part 2).  Band models (reach < 50 sizes
+    # above the diagonal) run in the windowed fused kernel; reach 55 must take the per-node kernels and give the same numbers.
+    ranges = (0, 90, 1, 20)
+    E = _band_error_model(91, 0.03, reach)
+    p = make(EXAMPLE_TREE, 0.006, mu=0.005, ranges=ranges, err={0: E, 2: E, 4: E})
+    g = p.make_gpu()
+    n = 120
+    R = ranges[3] - ranges[2] + 1
+    u = np.random.RandomState(17).random_sample(R * n * (p.tree.n_nodes - 1))
+    cd = g.conditional_distribution(n, uniforms=u)
+    ref = oracle.conditional_distribution(p.otree, p.oracle_mats(), p.ranges, n, uniforms=u, leaf_err=p.oracle_leaf_err())
+    plain = oracle.conditional_distribution(p.otree, p.oracle_mats(), p.ranges, n, uniforms=u)
+    assert not np.allclose(ref, plain, rtol=1e-6)
+    big = ref > 1e-290
+    assert rel_err(cd[big], ref[big]).max() < 1e-11
+    monkeypatch.setenv("CAFE_GPU_NO_FUSED", "1")
+    cd_node = g.conditional_distribution(n, uniforms=u)
+    monkeypatch.delenv("CAFE_GPU_NO_FUSED")
+    assert rel_err(cd[big], cd_node[big]).max() < 1e-12
+    g.close()
