@@ -90,6 +90,7 @@ static void destroy_one(cafe_gpu_ctx* ctx) {
     free_err_models(ctx);
     fused_release(ctx);
     fused2_release(ctx);
+    k1_release(ctx);
     for (cudaEvent_t e : ctx->ring) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -188,6 +189,7 @@ static int one_set_ranges(cafe_gpu_ctx* ctx, int range_min, int range_max, int r
 static int one_set_lnc_table(cafe_gpu_ctx* ctx, const double* lnc, int rows, int cols) {
     if (!ctx || !lnc || rows < 2 || cols < 2) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_lnc_table: bad arguments");
     cudaFree(ctx->d_lnc); cudaFree(ctx->d_lncT); ctx->d_lnc = ctx->d_lncT = nullptr;
+    k1_release(ctx);  // K1's ratio tables are derived from this table
     size_t bytes = (size_t)rows * cols * sizeof(double);
     CAFE_CK(ctx, cudaMalloc(&ctx->d_lnc, bytes));
     CAFE_CK(ctx, cudaMalloc(&ctx->d_lncT, bytes));
@@ -343,6 +345,13 @@ static BdKeyParams key_params(const BdKey& k) {
     P.log_beta = std::log(beta);
     P.log_coeff = std::log(coeff);
     P.mode = (k.mu < 0) ? 2 : 3;                     // birthdeath.c:272-275
+    // term(j+1) / term(j) = q (s-j)(c-j) / ((j+1)(s+c-1-j)); K1's recurrence kernel needs q finite and small enough that a term
+    // cannot climb from below 2^-2000 to the normal range within one 16-term segment (bd_matrix.cu) - anything else (mu = 0,
+    // lambda t below ~1e-6, ...) takes the term-by-term kernel
+    // (from the rounded logs, not from alpha and beta: the reference's terms are exp() of sums of THOSE)
+    P.q = (P.mode == 2) ? coeff * std::exp(-2 * P.log_alpha) : std::exp(P.log_coeff - P.log_alpha - P.log_beta);
+    P.rec = std::isfinite(P.q) && P.q > 0 && P.q < 1e12 && std::isfinite(P.log_alpha) && std::isfinite(P.log_beta) &&
+            std::isfinite(P.log_coeff);
     return P;
 }
 

@@ -40,8 +40,9 @@ struct BdKey {
 // Host-computed scalars of one key (libtree/birthdeath.c:246-262), uploaded for K1.
 struct BdKeyParams {
     double log_alpha, log_beta, log_coeff, coeff;
+    double q;  // coeff / (alpha * beta): the part of term(j+1) / term(j) that does not depend on (s, c, j)  (bd_matrix.cu)
     int mode;  // 0: rows>=1 zero (coeff<=0); 1: identity (coeff==1); 2: mu<0 sum; 3: mu>=0 sum
-    int pad;
+    int rec;   // 1: the anchored term recurrence of bd_matrix.cu applies (all scalars finite, q in range)
 };
 
 // Sparse rows of an error matrix: for observed count `o`, the non-zero (true size j, value) pairs in
@@ -146,6 +147,7 @@ struct cafe_gpu_ctx {
     size_t Lroot_cache_cap = 0;
     void* fused_state = nullptr;   // prune_fused.cu private state (device schedule, scratch)
     void* fused2_state = nullptr;  // prune_fused2.cu private state
+    void* k1_state = nullptr;      // bd_matrix.cu private state (ratio tables of the term recurrence)
 
     // multi-GPU (comm.cu): a context is one rank of an NCCL communicator.  Either one process per GPU (cafe_gpu_comm_init:
     // world ranks in world processes) or one process with several devices (cafe_gpu_create_multi: the leader context owns
@@ -183,6 +185,7 @@ int ensure_vec_buffers(cafe_gpu_ctx* ctx, size_t F_pad);                // api.c
 bool fused_supported(const cafe_gpu_ctx* ctx);                          // prune_fused.cu
 int launch_prune_fused(cafe_gpu_ctx* ctx, double* d_Lroot_out);         // prune_fused.cu (K2, fused persistent kernel)
 void fused_release(cafe_gpu_ctx* ctx);
+void k1_release(cafe_gpu_ctx* ctx);                                      // bd_matrix.cu
 bool fused2_supported(const cafe_gpu_ctx* ctx);                         // prune_fused2.cu
 int launch_prune_fused2(cafe_gpu_ctx* ctx, double* d_Lroot_out);        // prune_fused2.cu (K2, one CTA per SM, default)
 // The same kernel on any table of sizes: the observed families (score), or simulated / windowed ones (conditional distribution,

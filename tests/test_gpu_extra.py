@@ -157,3 +157,39 @@ def test_pvalue_out_in_round_trip(tmp_path):
     np.testing.assert_allclose(cd2, cd, rtol=1e-8, atol=1e-300)
     s.close()
     s2.close()
+
+
+def test_k1_recurrence_equals_the_term_by_term_kernel(monkeypatch):
+    # K1's default kernel carries 15 of every 16 terms by the ratio of consecutive terms (bd_matrix.cu); CAFE_GPU_K1_EXACT=1
+    # evaluates every term with its own exp(), the reference's arithmetic operation for operation.  They must agree within the
+    # 1e-12 the matrices are held to (measured on the bench shapes, tools/k1_check.py: <= 3.7e-13 up to S = 1001), entries
+    # below the double range included (no term lost to an underflowing anchor), and a key outside the recurrence's guard
+    # (lambda t ~ 1e-7: q = coeff / (alpha beta) ~ 1e14) must be bit-identical because it takes the term-by-term path.
+    newick = "(((a:31,b:31):12,c:43):20,(d:7,(e:2,f:2):5):56)"
+    tree = chost.parse_tree(newick)
+    n = tree.n_nodes
+    for maxsize, lam, mu in ((120, 0.004, None), (260, 0.0021, 0.0017), (260, 0.0005, 0.0005), (120, 1e-8, None)):
+        rg = chost.init_family_size(maxsize)
+        ranges = (rg["min"], rg["max"], rg["root_min"], rg["root_max"])
+        maxfs = max(ranges[1], ranges[3])
+        mats = {}
+        for mode in ("rec", "exact"):
+            if mode == "exact":
+                monkeypatch.setenv("CAFE_GPU_K1_EXACT", "1")
+            g = cgpu.CafeGpu()
+            g.set_tree(tree.left, tree.right, tree.branchlength)
+            g.set_ranges(*ranges)
+            g.set_lnc_table(chost.lnc_table(maxfs))
+            g.set_rates(np.full(n, lam), np.full(n, -1.0 if mu is None else mu))
+            g.build_matrices()
+            mats[mode] = [g.get_matrix(v) for v in range(n) if v != tree.root]
+            g.close()
+            monkeypatch.delenv("CAFE_GPU_K1_EXACT", raising=False)
+        for a, b in zip(mats["rec"], mats["exact"]):
+            if lam == 1e-8:
+                assert np.array_equal(a, b)
+                continue
+            big = b > 1e-300
+            assert rel_err(a[big], b[big]).max() < 1e-12
+            assert np.abs(a - b)[~big].max() < 1e-299
+            assert np.array_equal(a[0], b[0])
