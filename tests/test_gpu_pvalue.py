@@ -67,8 +67,11 @@ def test_k4_device_rng_is_statistically_equivalent():
     ref = oracle.conditional_distribution(p.otree, p.oracle_mats(), p.ranges, n)
     pv = []
     for r in (0, 3, 7, 14):
-        a = np.log(np.maximum(cd[r], 1e-300))
-        b = np.log(np.maximum(ref[r], 1e-300))
+        # logs rounded to 1e-8: at small root sizes a sizeable share of the draws is ONE family (every leaf empty), a block of equal
+        # values in both samples; the GPU's and the oracle's value of it agree to ~1e-13, and unrounded the statistic would see the
+        # whole block as a gap between the two distributions
+        a = np.round(np.log(np.maximum(cd[r], 1e-300)), 8)
+        b = np.round(np.log(np.maximum(ref[r], 1e-300)), 8)
         pv.append(stats.ks_2samp(a, b).pvalue)
     assert min(pv) > 1e-4, pv
     # a different seed gives a different sample
