@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <array>
 #include <string>
 #include <vector>
 
@@ -201,6 +202,7 @@ struct Fused2Job {
     bool posterior = false;
 };
 bool fused2_windowed_supported(const cafe_gpu_ctx* ctx);
+void fused2_tile_slots(const cafe_gpu_ctx* ctx, int F, std::vector<std::array<int, 3>>& slots);  // host mirror of the kernel's tile split
 int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job);
 void fused2_release(cafe_gpu_ctx* ctx);
 int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double* uniforms, uint64_t seed, int row_lo, int row_hi,

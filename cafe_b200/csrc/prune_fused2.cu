@@ -264,13 +264,34 @@ __device__ __forceinline__ void advance(uint32_t& stage, uint32_t& phase) {
     if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
 }
 
+// Windowed mode: 1 + the largest column window among the families of a tile.  No node vector of the tile has a non-zero size at or
+// above it (Params::colmax), so every K loop of the tile ends there and output sizes from there on are never computed: the
+// producer, the epilogue manager and the consumers all derive the tile's pass and K-block counts from this one number.  The rows
+// of the conditional distribution are ordered by root size, so the families of a tile have nearly the same window.
+__device__ __forceinline__ int tile_wmax_lane(const Params& P, int mb0, int m) {
+    int w = 0;
+    for (int r = 0; r < TILE_M; ++r) {
+        const int f = TilePlan::family_or_neg(mb0, m, r, P.F);
+        if (f >= 0) w = max(w, __ldg(P.colmax + f));
+    }
+    return min(P.W, w + 1);
+}
+__device__ __forceinline__ int tile_wmax_warp(const Params& P, int mb0, int m, int lane) {
+    int w = 0;
+    for (int r = lane; r < TILE_M; r += 32) {
+        const int f = TilePlan::family_or_neg(mb0, m, r, P.F);
+        if (f >= 0) w = max(w, __ldg(P.colmax + f));
+    }
+    return min(P.W, __reduce_max_sync(0xffffffffu, w) + 1);
+}
+
 // ================================ TMA producer (one lane) ================================ ================================
-template <bool PROF>
+template <bool PROF, bool WIN>
 __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUtensorMap* tmB, const CUtensorMap* tmBroot, const Params& P,
                                               unsigned char* stage_base, Ctl* ctl) {
     const TilePlan plan(P);
     const int scratch_row0 = blockIdx.x * cta_rows(P);
-    const int n_kblocks = (P.W + BK - 1) / BK;
+    const int n_kblocks_full = (P.W + BK - 1) / BK;
     if (K2_DBG_NOSYNC) return;
     uint32_t stage = 0, phase = 0;
     int ops_done_base = 0;
@@ -280,13 +301,22 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
     int cherry_units = 0;  // leaf-pair vectors needed so far, in the gatherers' order (pair, op, tile)
     int p_item = 0;
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        int wmax_h[2] = {P.W, P.W};
+        if (WIN) {
+            for (int h = 0; h < 2; ++h) {
+                int mb0, m;
+                if (plan.tile(2 * pair + h, mb0, m)) wmax_h[h] = tile_wmax_lane(P, mb0, m);
+            }
+        }
         for (int oi = 0; oi < P.n_ops; ++oi) {
             const Op op = P.ops[oi];
             const int r0 = op.is_root ? P.root_min : 0;
-            const int nrows = op.is_root ? P.R : P.W;
-            const int n_chunks = (nrows + TN - 1) / TN;
+            const int nrows_full = op.is_root ? P.R : P.W;
+            const int n_chunks_full = (nrows_full + TN - 1) / TN;
             for (int h = 0; h < 2; ++h) {
                 if (2 * pair + h >= plan.n_tiles) continue;
+                const int n_chunks = (WIN && !op.is_root) ? (wmax_h[h] + TN - 1) / TN : n_chunks_full;
+                const int n_kblocks = WIN ? (wmax_h[h] + BK - 1) / BK : n_kblocks_full;
                 const long long t_op = prof ? clock64() : 0;
                 if (op.a_kind == 0) {
                     // the vector to stream was stored by an earlier op of this tile: wait until it is visible
@@ -432,6 +462,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
     long long t_prep = 0, t_wait_cdone = 0, t_store = 0;
     const long long t_begin = prof ? clock64() : 0;
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
+        int wmax_h[2] = {P.W, P.W};
         if (WIN) {
             // windowed mode: the windows / root picks of the rows of this pair's tiles (every consumer has left the previous pair:
             // its last pass was handed back through c_done before this point)
@@ -444,19 +475,22 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                     ctl->colmax[h][r] = __ldg(P.colmax + f);
                     ctl->pick[h][r] = P.root_pick ? __ldg(P.root_pick + f) - P.root_min : -1;
                 }
+                wmax_h[h] = tile_wmax_warp(P, mb0, m, lane);
             }
             __syncwarp();
         }
         for (int oi = 0; oi < P.n_ops; ++oi) {
             const Op op = P.ops[oi];
             const int r0 = op.is_root ? P.root_min : 0;
-            const int nrows = op.is_root ? P.R : P.W;
-            const int n_chunks = (nrows + TN - 1) / TN;
             const bool reduce_now = op.is_root && op.other_kind != 0;
             const double* __restrict__ MTo = P.MT + (size_t)op.key_o * P.Sp * P.Sp;
+            const int nrows_full = op.is_root ? P.R : P.W;
+            const int n_chunks_full = (nrows_full + TN - 1) / TN;
             for (int h = 0; h < 2; ++h) {
                 int mb0, m;
                 if (!plan.tile(2 * pair + h, mb0, m)) continue;
+                const int nrows = (WIN && !op.is_root) ? wmax_h[h] : nrows_full;  // windowed: sizes from the tile's largest window on are not computed
+                const int n_chunks = WIN ? (nrows + TN - 1) / TN : n_chunks_full;
                 if (op.other_kind == 1) {
                     __syncwarp();
                     for (int r = lane; r < TILE_M; r += 32) {
@@ -761,8 +795,8 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
     // order there, i.e. two selects per element in the epilogue.
     const int sg = (0x13467520 >> (4 * g)) & 7;
     const int pcA = (0x13467520 >> (8 * q)) & 7, pcB = (0x13467520 >> (8 * q + 4)) & 7;  // sizes of this lane's accumulator pair in an 8-block
-    const int n_kblocks = (P.W + BK - 1) / BK;
-    const int tail_steps = ((P.W - (n_kblocks - 1) * BK) + 3) >> 2;  // k4-steps of the last K block (1..4)
+    const int n_kblocks_full = (P.W + BK - 1) / BK;
+    const int tail_steps_full = ((P.W - (n_kblocks_full - 1) * BK) + 3) >> 2;  // k4-steps of the last K block (1..4)
 
     // Byte offsets of this lane's two accumulator columns inside a C box, for even / odd 8-size blocks (128B swizzle).
     int coff[2][2];
@@ -782,23 +816,31 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
     const uint32_t ring_u32 = opaque_u32(smem_u32(stage_base)), bars_u32 = opaque_u32(smem_u32(&ctl->full[0]));
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
         // the two tiles of the pair: this group's 8-family blocks (everything else about a tile concerns the helper warps)
-        int mbv_h[2], f0_h[2];
+        int mbv_h[2], f0_h[2], wmax_h[2] = {0, 0};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             int mb0 = 0, m = 0;
-            mbv_h[h] = plan.tile(2 * pair + h, mb0, m) ? TilePlan::mbv(m, grp) : -1;
+            const bool have = plan.tile(2 * pair + h, mb0, m);
+            mbv_h[h] = have ? TilePlan::mbv(m, grp) : -1;
             f0_h[h] = (mb0 + TilePlan::pre(m, grp)) * 8;
+            if (WIN) wmax_h[h] = have ? tile_wmax_warp(P, mb0, m, lane) : P.W;
         }
         for (int oi = 0; oi < P.n_ops; ++oi) {
             const int flags = ctl->opflags[oi];
             const bool is_root = flags & 1;
             const int other_kind = (flags >> 2) & 3;
-            const int nrows = is_root ? P.R : P.W;
-            const int n_chunks = (nrows + TN - 1) / TN;
             const bool reduce_now = is_root && other_kind != 0;
+            const int nrows_full = is_root ? P.R : P.W;
+            const int n_chunks_full = (nrows_full + TN - 1) / TN;
             for (int h = 0; h < 2; ++h) {
                 const int mbv_t = h ? mbv_h[1] : mbv_h[0], f0_t = h ? f0_h[1] : f0_h[0];
                 if (mbv_t < 0) continue;
+                // windowed mode: the tile's own K extent and, below the root, output sizes (tile_wmax_warp)
+                const int wmax_t = h ? wmax_h[1] : wmax_h[0];
+                const int nrows = (WIN && !is_root) ? wmax_t : nrows_full;
+                const int n_chunks = WIN ? (nrows + TN - 1) / TN : n_chunks_full;
+                const int n_kblocks = WIN ? (wmax_t + BK - 1) / BK : n_kblocks_full;
+                const int tail_steps = WIN ? ((wmax_t - (n_kblocks - 1) * BK) + 3) >> 2 : tail_steps_full;
                 // running root reduction of one family row of this group, owned by the group's first HM threads
                 double run_ml = -1.0, run_mp = -INFINITY; int run_am = 0x7fffffff;
                 for (int ch = 0; ch < n_chunks; ++ch) {
@@ -1048,7 +1090,7 @@ k_prune_fused2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5;
     if (warp < N_AUX_WARPS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
-        if (warp == 0) { if ((threadIdx.x & 31) == 0) producer_main<PROF>(&tmA, &tmB, &tmBroot, P, stage_base, ctl); }
+        if (warp == 0) { if ((threadIdx.x & 31) == 0) producer_main<PROF, WIN>(&tmA, &tmB, &tmBroot, P, stage_base, ctl); }
         else if (warp == 3) cmanager_main<PROF, WIN>(&tmA, P, Cbuf, ctl);
         else gatherer_main<WIN>(P, P.scratch, ctl, warp - 1);
     } else {
@@ -1143,6 +1185,31 @@ bool fused2_supported(const cafe_gpu_ctx* ctx) {
 // capped by the global range where the sums agree anyway), so error models whose rows reach less than 50 sizes above their
 // diagonal - every model the reference's reader and `esterror` produce is a band of a few sizes - take the fused kernel; a wider
 // one falls back to the per-node kernels.
+// Host mirror of TilePlan (the kernel's static split of the 8-family blocks over CTAs and tiles): the family positions
+// [first, first + count) of every tile of a launch over F families, as {tile index inside its CTA, first, count}.  Used by
+// callers that choose the ORDER of the families (run_pvalues sorts them by window); a mismatch with TilePlan would cost speed,
+// never correctness - a family's result does not depend on its position.
+void fused2_tile_slots(const cafe_gpu_ctx* ctx, int F, std::vector<std::array<int, 3>>& slots) {
+    slots.clear();
+    const int n_mblocks = (F + 7) / 8;
+    const int G = std::max(1, std::min(ctx->sm_count, (n_mblocks + 1) / 2));
+    const int per_tile = fused2::TILE_M / 8;
+    for (int c = 0; c < G; ++c) {
+        const int mb_lo = (int)((long long)n_mblocks * c / G);
+        const int n_mb = (int)((long long)n_mblocks * (c + 1) / G) - mb_lo;
+        if (n_mb <= 0) continue;
+        int n_tiles = (n_mb + per_tile - 1) / per_tile;
+        if (n_mb >= 2 && (n_tiles & 1)) ++n_tiles;
+        const int e = (n_mb / n_tiles) & ~1, r = n_mb - e * n_tiles, n2 = r >> 1;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int m = e + (t < n2 ? 2 : 0) + ((r & 1) && t == n2 ? 1 : 0);
+            const int mb0 = mb_lo + e * t + 2 * std::min(t, n2) + ((r & 1) && t > n2 ? 1 : 0);
+            const int first = mb0 * 8, count = std::min(F, (mb0 + m) * 8) - first;
+            if (count > 0) slots.push_back({t, first, count});
+        }
+    }
+}
+
 bool fused2_windowed_supported(const cafe_gpu_ctx* ctx) {
     if (!fused2_tree_supported(ctx)) return false;
     for (int e : ctx->leaf_err)

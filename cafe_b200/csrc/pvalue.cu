@@ -7,6 +7,7 @@
 //   pvalue (libcommon/mathfunc.c:663-689): rank of L[s] in the ascending row, ties at their midpoint
 //   viterbi_set_max_pvalue (cafe/viterbi.cpp:32-39): max over s, 0 for an empty root range
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdlib>
 
@@ -39,9 +40,10 @@ __device__ __forceinline__ double pvalue_dev(double v, const double* __restrict_
 }
 
 // one warp per family: lanes take root sizes s, warp-max of the p-values
+// order (nullable): row f of Lroot / rfsize belongs to family order[f] of the table (run_pvalues sorts the families by window)
 __global__ void __launch_bounds__(256)
 k_family_pvalue(const double* __restrict__ Lroot, size_t Vp, int F, const int* __restrict__ rfsize, const double* __restrict__ cd,
-                int cd_rows, int n_samples, double* __restrict__ out) {
+                int cd_rows, int n_samples, const int* __restrict__ order, double* __restrict__ out) {
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (f >= F) return;
     const int rf = min(rfsize[f], cd_rows);
@@ -49,7 +51,13 @@ k_family_pvalue(const double* __restrict__ Lroot, size_t Vp, int F, const int* _
     for (int s = lane; s < rf; s += 32) best = fmax(best, pvalue_dev(Lroot[(size_t)f * Vp + s], cd + (size_t)s * n_samples, n_samples));
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, off));
-    if (lane == 0) out[f] = (rf > 0) ? best : 0.0;
+    if (lane == 0) out[order ? order[f] : f] = (rf > 0) ? best : 0.0;
+}
+
+// counts of the families in another order: dst[k][i] = src[k][order[i]] for every leaf k (leaf-major tables)
+__global__ void k_permute_counts(const int* __restrict__ src, int* __restrict__ dst, const int* __restrict__ order, int F, int F_pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (i < F) dst[(size_t)k * F_pad + i] = src[(size_t)k * F_pad + order[i]];
 }
 
 // ---------------------------------------------------------------- branch cutting (cafe/branch_cutting.cpp:20-44, :101-150)
@@ -113,9 +121,35 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
     }
     if (rf_max > ctx->Vp || 1 + rf_max > ctx->S)
         CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "pvalues: a family's root range rint(1.25*max) exceeds the matrices (set_ranges from the table's max first)");
-    int *d_colmax = nullptr, *d_rf = nullptr;
+    int *d_colmax = nullptr, *d_rf = nullptr, *d_order = nullptr, *d_counts_sorted = nullptr;
     double *d_cd = nullptr, *d_out = nullptr;
-    auto cleanup = [&]() { cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_cd); cudaFree(d_out); };
+    auto cleanup = [&]() { cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_cd); cudaFree(d_out); cudaFree(d_order); cudaFree(d_counts_sorted); };
+    // root rows 1..rf_max for everybody (rows beyond a family's own range are ignored by k_family_pvalue)
+    const int root_rows = std::min(rf_max, ctx->S - 1);
+    const bool fused = root_rows >= 1 && fused2_windowed_supported(ctx) && std::getenv("CAFE_GPU_NO_FUSED") == nullptr;
+    // The fused kernel ends a tile's K loops and output sizes at the tile's largest window (prune_fused2.cu, tile_wmax), so it
+    // gets the families in an order of its own: sorted by window (a counting sort, ties in table order), widest first, and dealt
+    // to the launch's tiles round by round - first tile of every CTA, then the second of every CTA, ... - so that a tile of 96
+    // holds families of nearly the same range AND every CTA gets the same mix of wide and narrow tiles (sorted order alone would
+    // hand all the wide families to the last few CTAs of the static split).  A family's result does not depend on its
+    // position; the p-values go back to the table's order.
+    std::vector<int> order;
+    if (fused && F > 1) {
+        std::vector<int> start(ctx->W + 1, 0), sorted(F);
+        for (int f = 0; f < F; ++f) start[colmax[f] + 1]++;
+        for (int w = 0; w < ctx->W; ++w) start[w + 1] += start[w];
+        for (int f = 0; f < F; ++f) sorted[start[colmax[f]]++] = f;          // ascending window
+        std::vector<std::array<int, 3>> slots;
+        fused2_tile_slots(ctx, F, slots);
+        std::stable_sort(slots.begin(), slots.end(), [](const std::array<int, 3>& a, const std::array<int, 3>& b) { return a[0] < b[0]; });
+        order.assign(ctx->F_pad, 0);
+        int next = F - 1;                                                       // widest first
+        for (const auto& sl : slots)
+            for (int i = 0; i < sl[2]; ++i) order[sl[1] + i] = sorted[next--];
+        if (next != -1) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "pvalues: the tile slots do not cover the families");
+        std::vector<int> cm(colmax), rf(rfsize);
+        for (int i = 0; i < F; ++i) { colmax[i] = cm[order[i]]; rfsize[i] = rf[order[i]]; }
+    }
 #define PV_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
     PV_CK(cudaMalloc(&d_colmax, ctx->F_pad * sizeof(int)));
     PV_CK(cudaMalloc(&d_rf, ctx->F_pad * sizeof(int)));
@@ -124,12 +158,10 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
     PV_CK(cudaMemcpyAsync(d_colmax, colmax.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PV_CK(cudaMemcpyAsync(d_rf, rfsize.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PV_CK(cudaMemcpyAsync(d_cd, cd, (size_t)cd_rows * n_samples * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    // root rows 1..rf_max for everybody (rows beyond a family's own range are ignored by k_family_pvalue)
-    const int root_rows = std::min(rf_max, ctx->S - 1);
     const double* Lroot = nullptr;
     size_t Lstride = 0;
     int rc = CAFE_GPU_OK;
-    if (root_rows >= 1 && fused2_windowed_supported(ctx) && std::getenv("CAFE_GPU_NO_FUSED") == nullptr) {
+    if (fused) {
         // the fused kernel in windowed mode: every family with its own forced range, all root rows copied out
         const size_t need = (size_t)F * root_rows;
         if (need > ctx->Lroot_cache_cap) {  // kept across calls: a malloc / free pair of this size costs more than the pass itself
@@ -138,8 +170,18 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
             ctx->Lroot_cache_cap = need;
         }
         double* d_Lroot = ctx->d_Lroot_cache;
+        const int* d_counts_job = ctx->d_counts;
+        if (!order.empty()) {
+            PV_CK(cudaMalloc(&d_order, ctx->F_pad * sizeof(int)));
+            PV_CK(cudaMalloc(&d_counts_sorted, (size_t)nl * ctx->F_pad * sizeof(int)));
+            PV_CK(cudaMemsetAsync(d_counts_sorted, 0, (size_t)nl * ctx->F_pad * sizeof(int), ctx->stream));
+            PV_CK(cudaMemcpyAsync(d_order, order.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            k_permute_counts<<<dim3((F + 255) / 256, nl), 256, 0, ctx->stream>>>(ctx->d_counts, d_counts_sorted, d_order, F, ctx->F_pad);
+            ctx->launches++;
+            d_counts_job = d_counts_sorted;
+        }
         Fused2Job job;
-        job.counts = ctx->d_counts; job.leaf_stride = (size_t)ctx->F_pad; job.F = F; job.F_pad = ctx->F_pad;
+        job.counts = d_counts_job; job.leaf_stride = (size_t)ctx->F_pad; job.F = F; job.F_pad = ctx->F_pad;
         job.d_colmax = d_colmax;
         job.root_r0 = 1; job.root_rows = root_rows;
         job.d_Lroot_out = d_Lroot;
@@ -154,7 +196,7 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
         if (rc) { cleanup(); return rc; }
         Lroot = ctx->d_vec + (size_t)root_slot * ctx->F_pad * ctx->Vp; Lstride = (size_t)ctx->Vp;
     }
-    k_family_pvalue<<<(F + 7) / 8, 256, 0, ctx->stream>>>(Lroot, Lstride, F, d_rf, d_cd, cd_rows, n_samples, d_out);
+    k_family_pvalue<<<(F + 7) / 8, 256, 0, ctx->stream>>>(Lroot, Lstride, F, d_rf, d_cd, cd_rows, n_samples, d_order, d_out);
     ctx->launches++;
     PV_CK(cudaGetLastError());
     PV_CK(cudaMemcpyAsync(out, d_out, F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
