@@ -198,6 +198,7 @@ struct Fused2Job {
     const int* d_colmax = nullptr;
     int root_r0 = 0, root_rows = 0;
     const int* d_root_pick = nullptr; double* d_L0_out = nullptr;
+    const int* d_root_need = nullptr;  // windowed jobs: of the root rows copied to d_Lroot_out only the first d_root_need[f] of family f are read
     double* d_Lroot_out = nullptr;
     bool posterior = false;
 };

@@ -18,7 +18,9 @@
 #include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
+#include <array>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -134,6 +136,22 @@ k_root_single_row(RootChild c0, RootChild c1, const double* __restrict__ M, cons
     if (lane == 0) L0[f] = prod;
 }
 
+// The simulated families of a chunk in the fused kernel's own order (see the dealing in run_conditional_distribution):
+// position p holds family order[p]; only the leaves' sizes travel (the kernel reads nothing else of the size table).
+__global__ void k_deal_chunk(const int* __restrict__ sizes, int Fc_pad, const int* __restrict__ colmax, const int* __restrict__ root_size,
+                             const int* __restrict__ order, int Fc, int* __restrict__ leaf_sizes_p, int* __restrict__ colmax_p,
+                             int* __restrict__ root_size_p) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (p >= Fc) return;
+    const int f = order[p];
+    leaf_sizes_p[(size_t)k * Fc_pad + p] = sizes[(size_t)(2 * k) * Fc_pad + f];
+    if (k == 0) { colmax_p[p] = colmax[f]; root_size_p[p] = root_size[f]; }
+}
+__global__ void k_undeal_L0(const double* __restrict__ L0p, const int* __restrict__ order, int Fc, double* __restrict__ L0) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < Fc) L0[order[p]] = L0p[p];
+}
+
 }  // namespace
 
 // rows [row_lo, row_hi) of the distribution (root sizes root_min + row): cd_out is [(row_hi - row_lo)][n_samples]; the replay
@@ -145,6 +163,9 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
     double* d_cdf = nullptr;
     int *d_prefix = nullptr, *d_parent = nullptr, *d_node_key = nullptr;
     int *d_sizes = nullptr, *d_trial_max = nullptr, *d_colmax = nullptr, *d_root_size = nullptr;
+    int *d_order = nullptr, *d_leaf_p = nullptr, *d_colmax_p = nullptr, *d_root_p = nullptr;
+    double* d_L0p = nullptr;
+    int order_Fc = -1;  // the chunk size d_order was built for
     // the fused kernel (prune_fused2.cu, windowed mode) prunes the simulated families whenever it can; the per-node kernels remain
     // for error-model leaves and as the A/B switch CAFE_GPU_NO_FUSED
     const bool fused = fused2_windowed_supported(ctx) && std::getenv("CAFE_GPU_NO_FUSED") == nullptr;
@@ -155,6 +176,7 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
     auto cleanup = [&]() {
         cudaFree(d_cdf); cudaFree(d_prefix); cudaFree(d_parent); cudaFree(d_node_key); cudaFree(d_sizes); cudaFree(d_trial_max);
         cudaFree(d_colmax); cudaFree(d_root_size); cudaFree(d_uniforms); cudaFree(d_L0); cudaFree(d_sorted); cudaFree(d_tmp); cudaFree(d_offsets);
+        cudaFree(d_order); cudaFree(d_leaf_p); cudaFree(d_colmax_p); cudaFree(d_root_p); cudaFree(d_L0p);
     };
 #define CD_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
 
@@ -210,6 +232,15 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
     if (!fused) {
         rc = ensure_vec_buffers(ctx, Fc_pad);
         if (rc) { cleanup(); return rc; }
+    } else {
+        CD_CK(cudaMalloc(&d_order, (size_t)Fc_pad * sizeof(int)));
+        CD_CK(cudaMalloc(&d_leaf_p, (size_t)ctx->n_leaves * Fc_pad * sizeof(int)));
+        CD_CK(cudaMemsetAsync(d_leaf_p, 0, (size_t)ctx->n_leaves * Fc_pad * sizeof(int), ctx->stream));
+        CD_CK(cudaMalloc(&d_colmax_p, (size_t)Fc_pad * sizeof(int)));
+        CD_CK(cudaMemsetAsync(d_colmax_p, 0, (size_t)Fc_pad * sizeof(int), ctx->stream));
+        CD_CK(cudaMalloc(&d_root_p, (size_t)Fc_pad * sizeof(int)));
+        CD_CK(cudaMemsetAsync(d_root_p, 0, (size_t)Fc_pad * sizeof(int), ctx->stream));
+        CD_CK(cudaMalloc(&d_L0p, (size_t)Fc_pad * sizeof(double)));
     }
     const size_t slot_stride = (size_t)Fc_pad * ctx->Vp;
 
@@ -225,13 +256,36 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
         if (fused) {
             // one persistent launch: every node with the per-trial column window, the root over its whole range, and of the
             // root's likelihoods the one of the family's own root size (the reference prunes with the root range {s})
+            //
+            // The kernel stops a tile's K loops and output passes at the tile's largest window, and it splits the families over
+            // its CTAs statically, so it gets them in an order of its own: largest root size first (the window grows with the root
+            // size and hardly changes along the draws of one root size), dealt to the launch's tiles round by round - first tile
+            // of every CTA, then the second of every CTA, ...  A tile of 96 then holds draws of one or two root sizes, and every CTA
+            // the same mix of wide and narrow tiles; in row order the CTAs at the end of a chunk would hold all the wide ones.
+            if (order_Fc != Fc) {
+                std::vector<std::array<int, 3>> slots;
+                fused2_tile_slots(ctx, Fc, slots);
+                std::stable_sort(slots.begin(), slots.end(), [](const std::array<int, 3>& a, const std::array<int, 3>& b) { return a[0] < b[0]; });
+                std::vector<int> order(Fc_pad, 0);
+                int next = Fc - 1;
+                for (const auto& sl : slots)
+                    for (int i = 0; i < sl[2]; ++i) order[sl[1] + i] = next--;
+                if (next != -1) { ctx->err = "conditional_distribution: the tile slots do not cover the chunk"; cleanup(); return CAFE_GPU_ERR_STATE; }
+                CD_CK(cudaMemcpyAsync(d_order, order.data(), (size_t)Fc_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+                CD_CK(cudaStreamSynchronize(ctx->stream));  // `order` is a local
+                order_Fc = Fc;
+            }
+            k_deal_chunk<<<dim3((Fc + 255) / 256, ctx->n_leaves), 256, 0, ctx->stream>>>(d_sizes, Fc_pad, d_colmax, d_root_size, d_order, Fc,
+                                                                                         d_leaf_p, d_colmax_p, d_root_p);
             Fused2Job job;
-            job.counts = d_sizes; job.leaf_stride = (size_t)2 * Fc_pad; job.F = Fc; job.F_pad = Fc_pad;  // leaf k is node 2k of the size table
-            job.d_colmax = d_colmax;
+            job.counts = d_leaf_p; job.leaf_stride = (size_t)Fc_pad; job.F = Fc; job.F_pad = Fc_pad;
+            job.d_colmax = d_colmax_p;
             job.root_r0 = ctx->root_min; job.root_rows = R;
-            job.d_root_pick = d_root_size; job.d_L0_out = d_L0 + (size_t)r_lo * n_samples;
+            job.d_root_pick = d_root_p; job.d_L0_out = d_L0p;
             rc = launch_prune_fused2_job(ctx, job);
             if (rc) { cleanup(); return rc; }
+            k_undeal_L0<<<(Fc + 255) / 256, 256, 0, ctx->stream>>>(d_L0p, d_order, Fc, d_L0 + (size_t)r_lo * n_samples);
+            ctx->launches += 2;
         } else {
             // all non-root nodes with the per-trial column window; leaf k is node 2k of the size table
             rc = launch_prune_ops(ctx, d_sizes, (size_t)2 * Fc_pad, Fc, Fc_pad, d_colmax, 0, 0, /*skip_root=*/true, nullptr);

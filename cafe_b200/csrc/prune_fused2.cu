@@ -107,6 +107,7 @@ struct Params {
     const int* colmax;           // nullable, [F_pad]
     const int* root_pick;        // nullable, [F_pad]: root SIZE whose likelihood goes to L0_out[f] (root range {s} of the distribution)
     double* L0_out;              // [F] with root_pick
+    const int* root_need;        // nullable, [F_pad]: root rows 0 .. root_need[f]-1 are all a caller reads of family f (p-values: the forced root range)
     const double* logprior;      // [R]
     const double* prior_mant;    // [R] prior = mant * 2^exp, mant in [1,2)  (host frexp; exp = -2^30 where the prior is 0)
     const int* prior_exp;        // [R]
@@ -268,21 +269,45 @@ __device__ __forceinline__ void advance(uint32_t& stage, uint32_t& phase) {
 // above it (Params::colmax), so every K loop of the tile ends there and output sizes from there on are never computed: the
 // producer, the epilogue manager and the consumers all derive the tile's pass and K-block counts from this one number.  The rows
 // of the conditional distribution are ordered by root size, so the families of a tile have nearly the same window.
-__device__ __forceinline__ int tile_wmax_lane(const Params& P, int mb0, int m) {
-    int w = 0;
+// The same goes for the root rows: of the R root sizes the conditional distribution reads ONE per family (Params::root_pick)
+// and the p-values the first root_need[f]; the root op of a tile runs only the 128-row passes [rch_lo, rch_hi) that hold a row
+// somebody reads.
+struct TileWin {
+    int wmax;            // K extent and, below the root, number of output sizes
+    int rch_lo, rch_hi;  // passes of the root op
+};
+__device__ __forceinline__ void tilewin_row(const Params& P, int f, int& w, int& lo, int& hi) {
+    w = max(w, __ldg(P.colmax + f));
+    if (P.root_pick) { const int r = __ldg(P.root_pick + f) - P.root_min; lo = min(lo, r); hi = max(hi, r); }
+    else if (P.root_need) { lo = 0; hi = max(hi, __ldg(P.root_need + f) - 1); }
+}
+__device__ __forceinline__ TileWin tilewin_finish(const Params& P, int w, int lo, int hi) {
+    TileWin t;
+    t.wmax = min(P.W, w + 1);
+    const int n_chunks = (P.R + TN - 1) / TN;
+    t.rch_lo = 0; t.rch_hi = n_chunks;
+    if (P.root_pick || P.root_need) {
+        lo = max(0, min(lo, P.R - 1)); hi = max(lo, min(hi, P.R - 1));
+        t.rch_lo = lo / TN; t.rch_hi = hi / TN + 1;
+    }
+    return t;
+}
+__device__ __forceinline__ TileWin tile_win_lane(const Params& P, int mb0, int m) {
+    int w = 0, lo = 0x7fffffff, hi = 0;
     for (int r = 0; r < TILE_M; ++r) {
         const int f = TilePlan::family_or_neg(mb0, m, r, P.F);
-        if (f >= 0) w = max(w, __ldg(P.colmax + f));
+        if (f >= 0) tilewin_row(P, f, w, lo, hi);
     }
-    return min(P.W, w + 1);
+    return tilewin_finish(P, w, lo, hi);
 }
-__device__ __forceinline__ int tile_wmax_warp(const Params& P, int mb0, int m, int lane) {
-    int w = 0;
+__device__ __forceinline__ TileWin tile_win_warp(const Params& P, int mb0, int m, int lane) {
+    int w = 0, lo = 0x7fffffff, hi = 0;
     for (int r = lane; r < TILE_M; r += 32) {
         const int f = TilePlan::family_or_neg(mb0, m, r, P.F);
-        if (f >= 0) w = max(w, __ldg(P.colmax + f));
+        if (f >= 0) tilewin_row(P, f, w, lo, hi);
     }
-    return min(P.W, __reduce_max_sync(0xffffffffu, w) + 1);
+    w = __reduce_max_sync(0xffffffffu, w); lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+    return tilewin_finish(P, w, lo, hi);
 }
 
 // ================================ TMA producer (one lane) ================================ ================================
@@ -301,11 +326,11 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
     int cherry_units = 0;  // leaf-pair vectors needed so far, in the gatherers' order (pair, op, tile)
     int p_item = 0;
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
-        int wmax_h[2] = {P.W, P.W};
+        int wmax_h[2] = {P.W, P.W}, rlo_h[2] = {0, 0}, rhi_h[2] = {0, 0};
         if (WIN) {
             for (int h = 0; h < 2; ++h) {
                 int mb0, m;
-                if (plan.tile(2 * pair + h, mb0, m)) wmax_h[h] = tile_wmax_lane(P, mb0, m);
+                if (plan.tile(2 * pair + h, mb0, m)) { const TileWin tw = tile_win_lane(P, mb0, m); wmax_h[h] = tw.wmax; rlo_h[h] = tw.rch_lo; rhi_h[h] = tw.rch_hi; }
             }
         }
         for (int oi = 0; oi < P.n_ops; ++oi) {
@@ -315,7 +340,8 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
             const int n_chunks_full = (nrows_full + TN - 1) / TN;
             for (int h = 0; h < 2; ++h) {
                 if (2 * pair + h >= plan.n_tiles) continue;
-                const int n_chunks = (WIN && !op.is_root) ? (wmax_h[h] + TN - 1) / TN : n_chunks_full;
+                const int n_chunks = WIN ? (op.is_root ? rhi_h[h] : (wmax_h[h] + TN - 1) / TN) : n_chunks_full;
+                const int ch_lo = (WIN && op.is_root) ? rlo_h[h] : 0;
                 const int n_kblocks = WIN ? (wmax_h[h] + BK - 1) / BK : n_kblocks_full;
                 const long long t_op = prof ? clock64() : 0;
                 if (op.a_kind == 0) {
@@ -333,7 +359,7 @@ __device__ __forceinline__ void producer_main(const CUtensorMap* tmA, const CUte
                     fence_proxy_async();
                 }
                 const int a_row = scratch_row0 + (op.a_kind == 0 ? (h * P.n_slots + op.in_slot) * TILE_M : cherry_row(P, pair, h, op.in_slot));
-                for (int ch = 0; ch < n_chunks; ++ch) {
+                for (int ch = ch_lo; ch < n_chunks; ++ch) {
                     const long long t_item = prof ? clock64() : 0;
                     long long t_first = 0;
                     for (int kb = 0; kb < n_kblocks; kb += KB_PER_STAGE) {
@@ -462,7 +488,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
     long long t_prep = 0, t_wait_cdone = 0, t_store = 0;
     const long long t_begin = prof ? clock64() : 0;
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
-        int wmax_h[2] = {P.W, P.W};
+        int wmax_h[2] = {P.W, P.W}, rlo_h[2] = {0, 0}, rhi_h[2] = {0, 0};
         if (WIN) {
             // windowed mode: the windows / root picks of the rows of this pair's tiles (every consumer has left the previous pair:
             // its last pass was handed back through c_done before this point)
@@ -475,7 +501,8 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                     ctl->colmax[h][r] = __ldg(P.colmax + f);
                     ctl->pick[h][r] = P.root_pick ? __ldg(P.root_pick + f) - P.root_min : -1;
                 }
-                wmax_h[h] = tile_wmax_warp(P, mb0, m, lane);
+                const TileWin tw = tile_win_warp(P, mb0, m, lane);
+                wmax_h[h] = tw.wmax; rlo_h[h] = tw.rch_lo; rhi_h[h] = tw.rch_hi;
             }
             __syncwarp();
         }
@@ -490,7 +517,8 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                 int mb0, m;
                 if (!plan.tile(2 * pair + h, mb0, m)) continue;
                 const int nrows = (WIN && !op.is_root) ? wmax_h[h] : nrows_full;  // windowed: sizes from the tile's largest window on are not computed
-                const int n_chunks = WIN ? (nrows + TN - 1) / TN : n_chunks_full;
+                const int n_chunks = WIN ? (op.is_root ? rhi_h[h] : (nrows + TN - 1) / TN) : n_chunks_full;  // one past the last pass
+                const int ch_lo = (WIN && op.is_root) ? rlo_h[h] : 0;
                 if (op.other_kind == 1) {
                     __syncwarp();
                     for (int r = lane; r < TILE_M; r += 32) {
@@ -502,7 +530,7 @@ __device__ __forceinline__ void cmanager_main(const CUtensorMap* tmA, const Para
                     __syncwarp();
                 }
                 const int out_row = scratch_row0 + (h * P.n_slots + op.out_slot) * TILE_M;
-                for (int ch = 0; ch < n_chunks; ++ch) {
+                for (int ch = ch_lo; ch < n_chunks; ++ch) {
                     const int nbx = min(C_BOXES, (P.Vp - ch * TN) / BK);  // boxes of this pass inside the vector
                     // sizes of the pass the consumers own: whole 8-size blocks up to nrows (consumer_main).  What lies beyond, up to
                     // the end of the stored boxes, must be zeros in the slot - staged here, never touched by the consumers.
@@ -816,14 +844,14 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
     const uint32_t ring_u32 = opaque_u32(smem_u32(stage_base)), bars_u32 = opaque_u32(smem_u32(&ctl->full[0]));
     for (int pair = 0; pair < plan.n_pairs; ++pair) {
         // the two tiles of the pair: this group's 8-family blocks (everything else about a tile concerns the helper warps)
-        int mbv_h[2], f0_h[2], wmax_h[2] = {0, 0};
+        int mbv_h[2], f0_h[2], wmax_h[2] = {0, 0}, rlo_h[2] = {0, 0}, rhi_h[2] = {0, 0};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             int mb0 = 0, m = 0;
             const bool have = plan.tile(2 * pair + h, mb0, m);
             mbv_h[h] = have ? TilePlan::mbv(m, grp) : -1;
             f0_h[h] = (mb0 + TilePlan::pre(m, grp)) * 8;
-            if (WIN) wmax_h[h] = have ? tile_wmax_warp(P, mb0, m, lane) : P.W;
+            if (WIN && have) { const TileWin tw = tile_win_warp(P, mb0, m, lane); wmax_h[h] = tw.wmax; rlo_h[h] = tw.rch_lo; rhi_h[h] = tw.rch_hi; }
         }
         for (int oi = 0; oi < P.n_ops; ++oi) {
             const int flags = ctl->opflags[oi];
@@ -838,12 +866,13 @@ __device__ __forceinline__ void consumer_main(const Params& P, unsigned char* st
                 // windowed mode: the tile's own K extent and, below the root, output sizes (tile_wmax_warp)
                 const int wmax_t = h ? wmax_h[1] : wmax_h[0];
                 const int nrows = (WIN && !is_root) ? wmax_t : nrows_full;
-                const int n_chunks = WIN ? (nrows + TN - 1) / TN : n_chunks_full;
+                const int n_chunks = WIN ? (is_root ? (h ? rhi_h[1] : rhi_h[0]) : (nrows + TN - 1) / TN) : n_chunks_full;  // one past the last pass
+                const int ch_lo = (WIN && is_root) ? (h ? rlo_h[1] : rlo_h[0]) : 0;
                 const int n_kblocks = WIN ? (wmax_t + BK - 1) / BK : n_kblocks_full;
                 const int tail_steps = WIN ? ((wmax_t - (n_kblocks - 1) * BK) + 3) >> 2 : tail_steps_full;
                 // running root reduction of one family row of this group, owned by the group's first HM threads
                 double run_ml = -1.0, run_mp = -INFINITY; int run_am = 0x7fffffff;
-                for (int ch = 0; ch < n_chunks; ++ch) {
+                for (int ch = ch_lo; ch < n_chunks; ++ch) {
                     // The 8-size blocks of the pass that hold a size < nrows go to the four N-warps of the group: four each in a
                     // full pass.  A pass with fewer blocks (the last one: 13 at W = 481) is split evenly instead, and group 1
                     // takes them in an order rotated by two warps - warp nw of both groups runs on SM sub-partition nw, so the
@@ -1379,7 +1408,7 @@ int launch_prune_fused2_job(cafe_gpu_ctx* ctx, const Fused2Job& job) {
     P.scratch = st.d_scratch;
     P.W = ctx->W; P.R = job.root_rows; P.root_min = job.root_r0; P.Sp = ctx->Sp; P.Vp = ctx->Vp; P.n_mblocks = n_mblocks;
     P.MT = ctx->d_MT; P.counts = job.counts; P.leaf_stride = job.leaf_stride;
-    P.colmax = job.d_colmax; P.root_pick = job.d_root_pick; P.L0_out = job.d_L0_out;
+    P.colmax = job.d_colmax; P.root_pick = job.d_root_pick; P.L0_out = job.d_L0_out; P.root_need = job.d_root_need;
     if (job.posterior) {
         P.logprior = ctx->d_logprior; P.prior_mant = ctx->d_prior_mant; P.prior_exp = ctx->d_prior_exp;
         P.logpost = ctx->d_logpost; P.maxlik = ctx->d_maxlik; P.argmax = ctx->d_argmax;

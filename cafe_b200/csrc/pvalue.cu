@@ -185,6 +185,7 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
         job.d_colmax = d_colmax;
         job.root_r0 = 1; job.root_rows = root_rows;
         job.d_Lroot_out = d_Lroot;
+        job.d_root_need = d_rf;  // k_family_pvalue reads the rows s < rfsize[f] only
         rc = launch_prune_fused2_job(ctx, job);
         if (rc) { cleanup(); return rc; }
         Lroot = d_Lroot; Lstride = (size_t)root_rows;
