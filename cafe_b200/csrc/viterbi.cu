@@ -47,6 +47,13 @@ k_viterbi_node(VitChild A, VitChild B, int Sp, int Vp, int W, int r0, int nrows,
         cm[u] = (colmax && u < nf) ? colmax[f0 + u] : W - 1;
         nr[u] = !colmax ? nrows : (u < nf ? (is_root ? rfsize[f0 + u] : cm[u] + 1) : 0);
     }
+    // forced ranges: nothing of this block's families lies above the widest window / beyond the longest range among them - the
+    // column loop ends there, and an output size no family has is a zero without looking (same values as the full loops)
+    int cm_blk = 0, nr_blk = 0;
+#pragma unroll
+    for (int u = 0; u < VT_FB; ++u) { if (u < nf) cm_blk = max(cm_blk, cm[u]); nr_blk = max(nr_blk, nr[u]); }
+    const int Wb = min(W, cm_blk + 1);
+    const bool live = i < nrows && i < nr_blk;
 
     for (int side = 0; side < 2; ++side) {
         const VitChild& C = side ? B : A;
@@ -54,7 +61,7 @@ k_viterbi_node(VitChild A, VitChild B, int Sp, int Vp, int W, int r0, int nrows,
 #pragma unroll
         for (int u = 0; u < VT_FB; ++u) { best[u] = 0.0; arg[u] = 0; }
         if (C.is_leaf) {
-            if (i < nrows) {
+            if (live) {
                 for (int u = 0; u < nf; ++u) {
                     const int cnt = C.counts[f0 + u];
                     if (cnt < 0) {
@@ -82,14 +89,14 @@ k_viterbi_node(VitChild A, VitChild B, int Sp, int Vp, int W, int r0, int nrows,
             }
         } else {
             __syncthreads();
-            for (int x = threadIdx.x; x < VT_FB * W; x += VT_THREADS) {
-                const int u = x / W, j = x - u * W;
-                sL[x] = (u < nf) ? C.L[(size_t)(f0 + u) * Vp + j] : 0.0;
+            for (int x = threadIdx.x; x < VT_FB * Wb; x += VT_THREADS) {
+                const int u = x / Wb, j = x - u * Wb;
+                sL[u * W + j] = (u < nf) ? C.L[(size_t)(f0 + u) * Vp + j] : 0.0;
             }
             __syncthreads();
-            if (i < nrows) {
+            if (live) {
                 const double* __restrict__ mcol = C.MT + r0 + i;
-                for (int j = 0; j < W; ++j) {
+                for (int j = 0; j < Wb; ++j) {
                     const double m = mcol[(size_t)j * Sp];
 #pragma unroll
                     for (int u = 0; u < VT_FB; ++u) {
