@@ -193,3 +193,56 @@ def test_k1_recurrence_equals_the_term_by_term_kernel(monkeypatch):
             assert rel_err(a[big], b[big]).max() < 1e-12
             assert np.abs(a - b)[~big].max() < 1e-299
             assert np.array_equal(a[0], b[0])
+
+
+def test_k1_recurrence_fuzz_over_rates_and_branch_lengths(monkeypatch):
+    # 96 random keys (t, lambda, mu) from lambda t ~ 1e-7 (outside the recurrence's guard) to lambda t ~ 30 (alpha -> 1, coeff <= 0:
+    # the zero matrix), mu from 0 (NaN terms, clamped like the reference's macros) to 5 lambda, and mu < 0: the default kernel
+    # against the term-by-term one on a 48-leaf caterpillar whose every branch has its own rates.
+    rng = np.random.RandomState(11)
+    n_leaves = 48
+    nw = "L0:1"
+    for k in range(1, n_leaves):
+        nw = f"({nw},L{k}:1):1"
+    nw = nw[: nw.rfind(":")]
+    tree = chost.parse_tree(nw)
+    n = tree.n_nodes
+    bl = np.array(tree.branchlength, dtype=np.float64)
+    nonroot = [v for v in range(n) if v != tree.root]
+    bl[nonroot] = np.round(10 ** rng.uniform(0, 3, size=len(nonroot)))            # 1 .. 1000
+    lam = np.full(n, 0.001); mu = np.full(n, -1.0)
+    lt = 10 ** rng.uniform(-7, 1.5, size=len(nonroot))
+    lam[nonroot] = lt / bl[nonroot]
+    kind = rng.randint(0, 4, size=len(nonroot))                                     # 0: mu < 0, 1: mu = lambda * u, 2: mu = 0, 3: mu = lambda
+    for i, v in enumerate(nonroot):
+        mu[v] = (-1.0, lam[v] * 10 ** rng.uniform(-2, 0.7), 0.0, lam[v])[kind[i]]
+    ranges = (0, 140, 1, 150)
+    maxfs = 150
+    mats = {}
+    for mode in ("rec", "exact"):
+        if mode == "exact":
+            monkeypatch.setenv("CAFE_GPU_K1_EXACT", "1")
+        g = cgpu.CafeGpu()
+        g.set_tree(tree.left, tree.right, bl)
+        g.set_ranges(*ranges)
+        g.set_lnc_table(chost.lnc_table(maxfs))
+        g.set_rates(lam, mu)
+        g.build_matrices()
+        mats[mode] = [g.get_matrix(v) for v in nonroot]
+        g.close()
+        monkeypatch.delenv("CAFE_GPU_K1_EXACT", raising=False)
+    worst = 0.0
+    for a, b in zip(mats["rec"], mats["exact"]):
+        assert not np.isnan(a).any() and not np.isnan(b).any()
+        big = b > 1e-300
+        if big.any():
+            worst = max(worst, rel_err(a[big], b[big]).max())
+        assert np.abs(a - b)[~big].max() < 1e-299
+    assert worst < 1e-12, worst
+    # and two of the keys against the CPU oracle (the reference's arithmetic), one per summation mode
+    for want in (0, 1):
+        i = next(i for i in range(len(nonroot)) if kind[i] == want and 1e-3 < lt[i] < 1.0)
+        v = nonroot[i]
+        ref = oracle.bd_matrix(int(bl[v]), lam[v], mu[v], maxfs)
+        big = ref > 1e-280
+        assert rel_err(mats["rec"][i][big], ref[big]).max() < 1e-12
