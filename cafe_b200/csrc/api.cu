@@ -213,6 +213,7 @@ static int one_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, con
     std::vector<int> T((size_t)n_leaves * F_pad, 0), mult(F_pad, 0), first(F_pad, 0);
     int mx = 0;
     bool missing = false;
+    std::vector<int> fam_max(F, 0);
     for (int f = 0; f < F; ++f) {
         for (int k = 0; k < n_leaves; ++k) {
             int c = counts[(size_t)f * n_leaves + k];
@@ -221,6 +222,7 @@ static int one_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, con
             if (c < -1) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_families: negative count");
             if (c < 0) missing = true;
             mx = std::max(mx, c);
+            fam_max[f] = std::max(fam_max[f], c);
             T[(size_t)k * F_pad + f] = c;
         }
         mult[f] = multiplicity ? multiplicity[f] : 1;
@@ -249,6 +251,7 @@ static int one_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, con
     CAFE_CK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->F = F; ctx->F_pad = F_pad; ctx->max_count = mx; ctx->has_missing = missing;
     ctx->h_counts.assign(counts, counts + (size_t)F * n_leaves);
+    ctx->h_fam_max.swap(fam_max);
     ctx->results_valid = false;
     return CAFE_GPU_OK;
 }

@@ -101,6 +101,7 @@ struct cafe_gpu_ctx {
     int* d_mult = nullptr;    // [F_pad]
     int* d_first = nullptr;   // [F_pad]
     std::vector<int> h_counts;  // [F][n_leaves] as given
+    std::vector<int> h_fam_max; // [F] largest count of a family: its forced range (cafe_family.c:236-255) follows from it
     int max_count = 0;
     bool has_missing = false;   // some leaf count is -1 (a species without data): Viterbi only
 

@@ -8,7 +8,9 @@
 //   viterbi_set_max_pvalue (cafe/viterbi.cpp:32-39): max over s, 0 for an empty root range
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -108,17 +110,28 @@ k_cut_pvalue_two(const double* __restrict__ L1, const double* __restrict__ L2, i
 
 int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples, double* out) {
     const int F = ctx->F, nl = ctx->n_leaves;
+    // CAFE_GPU_STAGE_TIMES=1: wall-clock of the stages of this call on stderr (each stage ends with a stream synchronisation)
+    const bool stage_times = std::getenv("CAFE_GPU_STAGE_TIMES") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_last = now();
+    auto stage = [&](const char* what) {
+        if (!stage_times) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto t = now();
+        std::fprintf(stderr, "pvalues stage %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     // per-family forced range (host: n_leaves ints per family)
     std::vector<int> colmax(ctx->F_pad, 0), rfsize(ctx->F_pad, 0);
     int rf_max = 0;
     for (int f = 0; f < F; ++f) {
-        int mx = 0;
-        for (int k = 0; k < nl; ++k) mx = std::max(mx, ctx->h_counts[(size_t)f * nl + k]);
+        const int mx = ctx->h_fam_max[f];
         const int root_max = (int)std::rint(mx * 1.25);
         colmax[f] = std::min(mx + std::max(50, mx / 5), ctx->W - 1);
         rfsize[f] = root_max;  // root_min is 1 in the forced range
         rf_max = std::max(rf_max, root_max);
     }
+    stage("forced ranges (host)");
     if (rf_max > ctx->Vp || 1 + rf_max > ctx->S)
         CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "pvalues: a family's root range rint(1.25*max) exceeds the matrices (set_ranges from the table's max first)");
     int *d_colmax = nullptr, *d_rf = nullptr, *d_order = nullptr, *d_counts_sorted = nullptr;
@@ -150,6 +163,7 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
         std::vector<int> cm(colmax), rf(rfsize);
         for (int i = 0; i < F; ++i) { colmax[i] = cm[order[i]]; rfsize[i] = rf[order[i]]; }
     }
+    stage("family order (host)");
 #define PV_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
     PV_CK(cudaMalloc(&d_colmax, ctx->F_pad * sizeof(int)));
     PV_CK(cudaMalloc(&d_rf, ctx->F_pad * sizeof(int)));
@@ -158,6 +172,7 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
     PV_CK(cudaMemcpyAsync(d_colmax, colmax.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PV_CK(cudaMemcpyAsync(d_rf, rfsize.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PV_CK(cudaMemcpyAsync(d_cd, cd, (size_t)cd_rows * n_samples * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    stage("allocations + uploads");
     const double* Lroot = nullptr;
     size_t Lstride = 0;
     int rc = CAFE_GPU_OK;
@@ -197,12 +212,15 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
         if (rc) { cleanup(); return rc; }
         Lroot = ctx->d_vec + (size_t)root_slot * ctx->F_pad * ctx->Vp; Lstride = (size_t)ctx->Vp;
     }
+    stage("pruning");
     k_family_pvalue<<<(F + 7) / 8, 256, 0, ctx->stream>>>(Lroot, Lstride, F, d_rf, d_cd, cd_rows, n_samples, d_order, d_out);
     ctx->launches++;
     PV_CK(cudaGetLastError());
     PV_CK(cudaMemcpyAsync(out, d_out, F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     PV_CK(cudaStreamSynchronize(ctx->stream));
+    stage("lookup + download");
     cleanup();
+    stage("frees");
     ctx->results_valid = false;
 #undef PV_CK
     return CAFE_GPU_OK;

@@ -182,6 +182,19 @@ k_viterbi_branch_pvalues(const double* __restrict__ M, const int* __restrict__ n
     if (lane == 0) out[w] = acc;
 }
 
+// the families in another order (run_viterbi sorts them by forced range): leaf-major count tables in, per-family rows out
+__global__ void k_vit_gather_counts(const int* __restrict__ src, int* __restrict__ dst, const int* __restrict__ order, int F, int F_pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (i < F) dst[(size_t)k * F_pad + i] = src[(size_t)k * F_pad + order[i]];
+}
+template <typename T>
+__global__ void k_vit_scatter_rows(const T* __restrict__ src, T* __restrict__ dst, const int* __restrict__ order, int F, int n) {
+    const long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= (long long)F * n) return;
+    const int i = (int)(x / n), v = (int)(x - (long long)i * n);
+    dst[(size_t)order[i] * n + v] = src[x];
+}
+
 }  // namespace
 
 // forced: per-family ranges as viterbi_section uses them (cafe_family_set_size_with_family_forced, cafe/cafe_family.c:236-255):
@@ -193,14 +206,27 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
         const int nl = ctx->n_leaves;
         h_colmax.assign(ctx->F_pad, 0); h_rf.assign(ctx->F_pad, 0);
         for (int f = 0; f < F; ++f) {
-            int mx = 0;
-            for (int k = 0; k < nl; ++k) mx = std::max(mx, ctx->h_counts[(size_t)f * nl + k]);
+            const int mx = ctx->h_fam_max[f];
             h_colmax[f] = std::min(mx + std::max(50, mx / 5), W - 1);
             h_rf[f] = (int)std::rint(mx * 1.25);
             if (h_rf[f] > Vp || 1 + h_rf[f] > ctx->S)
                 CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "viterbi: a family's root range rint(1.25*max) exceeds the matrices (set_ranges from the table's max first)");
         }
     }
+    // Forced ranges: k_viterbi_node ends its loops at the widest range among the VT_FB families of a block, so the families are
+    // processed sorted by range (a counting sort, ties in table order) and the results scattered back to the table's order at
+    // the end; a family's reconstruction does not depend on its position.
+    std::vector<int> order;
+    if (forced && F > VT_FB) {
+        std::vector<int> start(W + 1, 0);
+        for (int f = 0; f < F; ++f) start[h_colmax[f] + 1]++;
+        for (int w = 0; w < W; ++w) start[w + 1] += start[w];
+        order.assign(ctx->F_pad, 0);
+        for (int f = 0; f < F; ++f) order[start[h_colmax[f]]++] = f;
+        std::vector<int> cm(h_colmax), rf(h_rf);
+        for (int i = 0; i < F; ++i) { h_colmax[i] = cm[order[i]]; h_rf[i] = rf[order[i]]; }
+    }
+    const bool sorted = !order.empty();
     if (W > 32767) CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "viterbi: vector longer than the 16-bit back-pointers");
     const size_t mat = (size_t)Sp * Sp;
     // families per chunk: vectors (8 B) of the internal nodes + back-pointers (2 B) of all nodes, <= ~1.5 GB
@@ -228,8 +254,11 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
     int *d_colmax = nullptr, *d_rf = nullptr, *d_node_key = nullptr;
     double *d_L = nullptr, *d_ml = nullptr, *d_bpv = nullptr;
     short* d_vit = nullptr;
+    int *d_order = nullptr, *d_counts_sorted = nullptr, *d_sizes_tab = nullptr;
+    double *d_ml_tab = nullptr, *d_bpv_tab = nullptr;
     auto cleanup = [&]() { cudaFree(d_prefix); cudaFree(d_parent); cudaFree(d_is_leaf); cudaFree(d_leaf_ord); cudaFree(d_sizes); cudaFree(d_L); cudaFree(d_ml); cudaFree(d_vit);
-                           cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_node_key); cudaFree(d_bpv); };
+                           cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_node_key); cudaFree(d_bpv);
+                           cudaFree(d_order); cudaFree(d_counts_sorted); cudaFree(d_sizes_tab); cudaFree(d_ml_tab); cudaFree(d_bpv_tab); };
 #define VT_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return CAFE_GPU_ERR_CUDA; } } while (0)
     VT_CK(cudaMalloc(&d_prefix, n * sizeof(int)));
     VT_CK(cudaMalloc(&d_parent, n * sizeof(int)));
@@ -244,6 +273,16 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
         VT_CK(cudaMalloc(&d_rf, ctx->F_pad * sizeof(int)));
         VT_CK(cudaMemcpyAsync(d_colmax, h_colmax.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         VT_CK(cudaMemcpyAsync(d_rf, h_rf.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int* d_counts_use = ctx->d_counts;
+    if (sorted) {
+        VT_CK(cudaMalloc(&d_order, ctx->F_pad * sizeof(int)));
+        VT_CK(cudaMalloc(&d_counts_sorted, (size_t)ctx->n_leaves * ctx->F_pad * sizeof(int)));
+        VT_CK(cudaMemsetAsync(d_counts_sorted, 0, (size_t)ctx->n_leaves * ctx->F_pad * sizeof(int), ctx->stream));
+        VT_CK(cudaMemcpyAsync(d_order, order.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        k_vit_gather_counts<<<dim3((F + 255) / 256, ctx->n_leaves), 256, 0, ctx->stream>>>(ctx->d_counts, d_counts_sorted, d_order, F, ctx->F_pad);
+        ctx->launches++;
+        d_counts_use = d_counts_sorted;
     }
     VT_CK(cudaMemcpyAsync(d_prefix, prefix.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     VT_CK(cudaMemcpyAsync(d_parent, parent.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -282,7 +321,7 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
                 C.vit = d_vit + (size_t)c * node_stride;
                 if (C.is_leaf) {
                     const int k = c / 2;
-                    C.counts = ctx->d_counts + (size_t)k * ctx->F_pad + fam0;
+                    C.counts = d_counts_use + (size_t)k * ctx->F_pad + fam0;
                     const int e = ctx->leaf_err.empty() ? -1 : ctx->leaf_err[k];
                     if (e >= 0) { C.err_rowptr = ctx->errs[e].d_rowptr; C.err_col = ctx->errs[e].d_col; C.err_val = ctx->errs[e].d_val; }
                 } else {
@@ -297,7 +336,7 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
         }
         k_viterbi_backtrack<<<(nf + 127) / 128, 128, 0, ctx->stream>>>(
             d_prefix, n, d_parent, d_is_leaf, d_leaf_ord, ctx->root, d_L + (size_t)slot_of[ctx->root] * node_stride, d_vit, node_stride, Vp,
-            ctx->R, forced ? 1 : ctx->root_min, ctx->rmin, ctx->d_counts, ctx->F_pad, fam0, nf, n, d_sizes, d_ml, forced ? d_rf + fam0 : nullptr);
+            ctx->R, forced ? 1 : ctx->root_min, ctx->rmin, d_counts_use, ctx->F_pad, fam0, nf, n, d_sizes, d_ml, forced ? d_rf + fam0 : nullptr);
         ctx->launches++;
         VT_CK(cudaGetLastError());
     }
@@ -310,10 +349,35 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
             ctx->d_M, d_node_key, d_parent, Sp, n, F, d_sizes, forced ? d_colmax : nullptr, W, d_bpv);
         ctx->launches++;
         VT_CK(cudaGetLastError());
-        VT_CK(cudaMemcpyAsync(branch_pv_out, d_bpv, (size_t)F * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        const double* src = d_bpv;
+        if (sorted) {
+            VT_CK(cudaMalloc(&d_bpv_tab, (size_t)F * n * sizeof(double)));
+            k_vit_scatter_rows<double><<<(unsigned)((warps + 255) / 256), 256, 0, ctx->stream>>>(d_bpv, d_bpv_tab, d_order, F, n);
+            ctx->launches++;
+            src = d_bpv_tab;
+        }
+        VT_CK(cudaMemcpyAsync(branch_pv_out, src, (size_t)F * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    if (sizes_out) VT_CK(cudaMemcpyAsync(sizes_out, d_sizes, (size_t)F * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (maxlik_out) VT_CK(cudaMemcpyAsync(maxlik_out, d_ml, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (sizes_out) {
+        const int* src = d_sizes;
+        if (sorted) {
+            VT_CK(cudaMalloc(&d_sizes_tab, (size_t)F * n * sizeof(int)));
+            k_vit_scatter_rows<int><<<(unsigned)(((long long)F * n + 255) / 256), 256, 0, ctx->stream>>>(d_sizes, d_sizes_tab, d_order, F, n);
+            ctx->launches++;
+            src = d_sizes_tab;
+        }
+        VT_CK(cudaMemcpyAsync(sizes_out, src, (size_t)F * n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (maxlik_out) {
+        const double* src = d_ml;
+        if (sorted) {
+            VT_CK(cudaMalloc(&d_ml_tab, (size_t)F * sizeof(double)));
+            k_vit_scatter_rows<double><<<(F + 255) / 256, 256, 0, ctx->stream>>>(d_ml, d_ml_tab, d_order, F, 1);
+            ctx->launches++;
+            src = d_ml_tab;
+        }
+        VT_CK(cudaMemcpyAsync(maxlik_out, src, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     VT_CK(cudaStreamSynchronize(ctx->stream));
 #undef VT_CK
     cleanup();
