@@ -91,6 +91,7 @@ static void destroy_one(cafe_gpu_ctx* ctx) {
     fused_release(ctx);
     fused2_release(ctx);
     k1_release(ctx);
+    work_release_all(ctx);
     for (cudaEvent_t e : ctx->ring) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <array>
 #include <string>
 #include <vector>
@@ -150,6 +151,11 @@ struct cafe_gpu_ctx {
     void* fused_state = nullptr;   // prune_fused.cu private state (device schedule, scratch)
     void* fused2_state = nullptr;  // prune_fused2.cu private state
     void* k1_state = nullptr;      // bd_matrix.cu private state (ratio tables of the term recurrence)
+    // work buffers of the multi-launch passes (conditional distribution): handed out by work_malloc, taken back by work_free
+    // WITHOUT a cudaFree - a call allocates and frees a dozen buffers of up to 100 MB, and on a busy host the driver calls took
+    // anything from 30 to 600 ms per pass against 200 ms of kernels
+    struct WorkBlock { void* p; size_t bytes; bool used; };
+    std::vector<WorkBlock> work_blocks;
 
     // multi-GPU (comm.cu): a context is one rank of an NCCL communicator.  Either one process per GPU (cafe_gpu_comm_init:
     // world ranks in world processes) or one process with several devices (cafe_gpu_create_multi: the leader context owns
@@ -174,6 +180,42 @@ struct cafe_gpu_ctx {
     cudaEvent_t evt(int i, int which) { return ring[kEv * (i % kRing) + which]; }
 };
 enum { EV_K1_BEGIN = 0, EV_K1_END, EV_K2_BEGIN, EV_K2_END, EV_XCHG_BEGIN, EV_XCHG_END, EV_RED_BEGIN, EV_RED_END };
+
+template <class T>
+inline cudaError_t work_malloc(cafe_gpu_ctx* ctx, T** out, size_t bytes) {
+    bytes = std::max<size_t>(bytes, 16);
+    int best = -1;
+    for (int i = 0; i < (int)ctx->work_blocks.size(); ++i) {
+        const auto& b = ctx->work_blocks[i];
+        if (!b.used && b.bytes >= bytes && (best < 0 || b.bytes < ctx->work_blocks[best].bytes)) best = i;
+    }
+    if (best >= 0 && ctx->work_blocks[best].bytes <= 2 * bytes + (1u << 20)) {
+        ctx->work_blocks[best].used = true;
+        *out = (T*)ctx->work_blocks[best].p;
+        return cudaSuccess;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {  // give the cached blocks back and try once more
+        for (auto& b : ctx->work_blocks) if (!b.used) { cudaFree(b.p); b.p = nullptr; }
+        ctx->work_blocks.erase(std::remove_if(ctx->work_blocks.begin(), ctx->work_blocks.end(), [](const cafe_gpu_ctx::WorkBlock& b) { return b.p == nullptr; }),
+                               ctx->work_blocks.end());
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    ctx->work_blocks.push_back({p, bytes, true});
+    *out = (T*)p;
+    return cudaSuccess;
+}
+inline void work_free(cafe_gpu_ctx* ctx, const void* p) {
+    if (!p) return;
+    for (auto& b : ctx->work_blocks) if (b.p == p) { b.used = false; return; }
+}
+inline void work_release_all(cafe_gpu_ctx* ctx) {
+    for (auto& b : ctx->work_blocks) cudaFree(b.p);
+    ctx->work_blocks.clear();
+}
 
 // kernels (defined in the .cu files of this directory); all launch on ctx->stream
 int launch_bd_matrices(cafe_gpu_ctx* ctx);                              // bd_matrix.cu   (K1: M and MT of the keys [key_lo, key_hi))

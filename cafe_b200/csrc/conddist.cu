@@ -19,6 +19,8 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -169,14 +171,26 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
     // the fused kernel (prune_fused2.cu, windowed mode) prunes the simulated families whenever it can; the per-node kernels remain
     // for error-model leaves and as the A/B switch CAFE_GPU_NO_FUSED
     const bool fused = fused2_windowed_supported(ctx) && std::getenv("CAFE_GPU_NO_FUSED") == nullptr;
+    // CAFE_GPU_STAGE_TIMES=1: wall-clock of the stages of this call on stderr (each stage ends with a stream synchronisation)
+    const bool stage_times = std::getenv("CAFE_GPU_STAGE_TIMES") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto stage = [&](const char* what) {
+        if (!stage_times) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "cond_dist stage %-26s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     double *d_uniforms = nullptr, *d_L0 = nullptr, *d_sorted = nullptr;
     void* d_tmp = nullptr;
     int* d_offsets = nullptr;
     int rc = CAFE_GPU_OK;
     auto cleanup = [&]() {
-        cudaFree(d_cdf); cudaFree(d_prefix); cudaFree(d_parent); cudaFree(d_node_key); cudaFree(d_sizes); cudaFree(d_trial_max);
-        cudaFree(d_colmax); cudaFree(d_root_size); cudaFree(d_uniforms); cudaFree(d_L0); cudaFree(d_sorted); cudaFree(d_tmp); cudaFree(d_offsets);
-        cudaFree(d_order); cudaFree(d_leaf_p); cudaFree(d_colmax_p); cudaFree(d_root_p); cudaFree(d_L0p);
+        for (const void* p : {(const void*)d_cdf, (const void*)d_prefix, (const void*)d_parent, (const void*)d_node_key, (const void*)d_sizes,
+                              (const void*)d_trial_max, (const void*)d_colmax, (const void*)d_root_size, (const void*)d_uniforms, (const void*)d_L0,
+                              (const void*)d_sorted, (const void*)d_tmp, (const void*)d_offsets, (const void*)d_order, (const void*)d_leaf_p,
+                              (const void*)d_colmax_p, (const void*)d_root_p, (const void*)d_L0p})
+            work_free(ctx, p);
     };
 #define CD_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
 
@@ -203,15 +217,15 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
         }
     }
 
-    CD_CK(cudaMalloc(&d_cdf, mat_bytes));
+    CD_CK(work_malloc(ctx, &d_cdf, mat_bytes));
     {
         dim3 grid((ctx->S + 127) / 128, D);
         k_row_cdf<<<grid, 128, 0, ctx->stream>>>(ctx->d_M, d_cdf, ctx->S, ctx->Sp, D);
         ctx->launches++;
     }
-    CD_CK(cudaMalloc(&d_prefix, n_nonroot * sizeof(int)));
-    CD_CK(cudaMalloc(&d_parent, n * sizeof(int)));
-    CD_CK(cudaMalloc(&d_node_key, n * sizeof(int)));
+    CD_CK(work_malloc(ctx, &d_prefix, n_nonroot * sizeof(int)));
+    CD_CK(work_malloc(ctx, &d_parent, n * sizeof(int)));
+    CD_CK(work_malloc(ctx, &d_node_key, n * sizeof(int)));
     CD_CK(cudaMemcpyAsync(d_prefix, ctx->prefix_nonroot.data(), n_nonroot * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CD_CK(cudaMemcpyAsync(d_parent, ctx->parent.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CD_CK(cudaMemcpyAsync(d_node_key, ctx->node_key.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -219,30 +233,31 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
     // root sizes are processed in chunks that bound the vector-slot memory
     const int rows_per_chunk = std::max(1, std::min(R, (1 << 16) / std::max(1, n_samples)));
     const int Fc_max = rows_per_chunk * n_samples, Fc_pad = round_up(Fc_max, 128);
-    CD_CK(cudaMalloc(&d_sizes, (size_t)n * Fc_pad * sizeof(int)));
+    CD_CK(work_malloc(ctx, &d_sizes, (size_t)n * Fc_pad * sizeof(int)));
     CD_CK(cudaMemsetAsync(d_sizes, 0, (size_t)n * Fc_pad * sizeof(int), ctx->stream));
-    CD_CK(cudaMalloc(&d_trial_max, (size_t)Fc_pad * sizeof(int)));
-    CD_CK(cudaMalloc(&d_colmax, (size_t)Fc_pad * sizeof(int)));
+    CD_CK(work_malloc(ctx, &d_trial_max, (size_t)Fc_pad * sizeof(int)));
+    CD_CK(work_malloc(ctx, &d_colmax, (size_t)Fc_pad * sizeof(int)));
     CD_CK(cudaMemsetAsync(d_colmax, 0, (size_t)Fc_pad * sizeof(int), ctx->stream));
-    CD_CK(cudaMalloc(&d_root_size, (size_t)Fc_pad * sizeof(int)));
+    CD_CK(work_malloc(ctx, &d_root_size, (size_t)Fc_pad * sizeof(int)));
     CD_CK(cudaMemsetAsync(d_root_size, 0, (size_t)Fc_pad * sizeof(int), ctx->stream));
-    CD_CK(cudaMalloc(&d_L0, (size_t)R * n_samples * sizeof(double)));
-    CD_CK(cudaMalloc(&d_sorted, (size_t)R * n_samples * sizeof(double)));
-    if (uniforms) CD_CK(cudaMalloc(&d_uniforms, (size_t)Fc_max * n_nonroot * sizeof(double)));
+    CD_CK(work_malloc(ctx, &d_L0, (size_t)R * n_samples * sizeof(double)));
+    CD_CK(work_malloc(ctx, &d_sorted, (size_t)R * n_samples * sizeof(double)));
+    if (uniforms) CD_CK(work_malloc(ctx, &d_uniforms, (size_t)Fc_max * n_nonroot * sizeof(double)));
     if (!fused) {
         rc = ensure_vec_buffers(ctx, Fc_pad);
         if (rc) { cleanup(); return rc; }
     } else {
-        CD_CK(cudaMalloc(&d_order, (size_t)Fc_pad * sizeof(int)));
-        CD_CK(cudaMalloc(&d_leaf_p, (size_t)ctx->n_leaves * Fc_pad * sizeof(int)));
+        CD_CK(work_malloc(ctx, &d_order, (size_t)Fc_pad * sizeof(int)));
+        CD_CK(work_malloc(ctx, &d_leaf_p, (size_t)ctx->n_leaves * Fc_pad * sizeof(int)));
         CD_CK(cudaMemsetAsync(d_leaf_p, 0, (size_t)ctx->n_leaves * Fc_pad * sizeof(int), ctx->stream));
-        CD_CK(cudaMalloc(&d_colmax_p, (size_t)Fc_pad * sizeof(int)));
+        CD_CK(work_malloc(ctx, &d_colmax_p, (size_t)Fc_pad * sizeof(int)));
         CD_CK(cudaMemsetAsync(d_colmax_p, 0, (size_t)Fc_pad * sizeof(int), ctx->stream));
-        CD_CK(cudaMalloc(&d_root_p, (size_t)Fc_pad * sizeof(int)));
+        CD_CK(work_malloc(ctx, &d_root_p, (size_t)Fc_pad * sizeof(int)));
         CD_CK(cudaMemsetAsync(d_root_p, 0, (size_t)Fc_pad * sizeof(int), ctx->stream));
-        CD_CK(cudaMalloc(&d_L0p, (size_t)Fc_pad * sizeof(double)));
+        CD_CK(work_malloc(ctx, &d_L0p, (size_t)Fc_pad * sizeof(double)));
     }
     const size_t slot_stride = (size_t)Fc_pad * ctx->Vp;
+    stage("allocations + row CDFs");
 
     for (int r_lo = row_lo; r_lo < row_hi; r_lo += rows_per_chunk) {
         const int rows = std::min(rows_per_chunk, row_hi - r_lo), Fc = rows * n_samples, s_lo = ctx->root_min + r_lo;
@@ -296,23 +311,26 @@ int run_conditional_distribution(cafe_gpu_ctx* ctx, int n_samples, const double*
             ctx->launches++;
         }
         CD_CK(cudaGetLastError());
+        stage("chunk (simulate + prune)");
     }
 
     // ascending sort of every row (std::sort, conditional_distribution.cpp:41)
     {
         std::vector<int> off(R + 1);
         for (int r = 0; r <= R; ++r) off[r] = (row_lo + std::min(r, row_hi - row_lo)) * n_samples;  // segments of the requested rows only
-        CD_CK(cudaMalloc(&d_offsets, (R + 1) * sizeof(int)));
+        CD_CK(work_malloc(ctx, &d_offsets, (R + 1) * sizeof(int)));
         CD_CK(cudaMemcpyAsync(d_offsets, off.data(), (R + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         size_t tmp_bytes = 0;
         CD_CK(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_L0, d_sorted, R * n_samples, row_hi - row_lo, d_offsets, d_offsets + 1, ctx->stream));
-        CD_CK(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        CD_CK(work_malloc(ctx, &d_tmp, std::max<size_t>(tmp_bytes, 16)));
         CD_CK(cub::DeviceSegmentedSort::SortKeys(d_tmp, tmp_bytes, d_L0, d_sorted, R * n_samples, row_hi - row_lo, d_offsets, d_offsets + 1, ctx->stream));
         ctx->launches++;
     }
     CD_CK(cudaMemcpyAsync(cd_out, d_sorted + (size_t)row_lo * n_samples, (size_t)(row_hi - row_lo) * n_samples * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CD_CK(cudaStreamSynchronize(ctx->stream));
+    stage("sort + download");
     cleanup();
+    stage("frees");
     ctx->results_valid = false;  // the vector slots were reused
 #undef CD_CK
     return CAFE_GPU_OK;
