@@ -136,7 +136,9 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
         CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "pvalues: a family's root range rint(1.25*max) exceeds the matrices (set_ranges from the table's max first)");
     int *d_colmax = nullptr, *d_rf = nullptr, *d_order = nullptr, *d_counts_sorted = nullptr;
     double *d_cd = nullptr, *d_out = nullptr;
-    auto cleanup = [&]() { cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_cd); cudaFree(d_out); cudaFree(d_order); cudaFree(d_counts_sorted); };
+    auto cleanup = [&]() {  // work_free: the buffers stay with the context (common.cuh)
+        for (const void* q : {(const void*)d_colmax, (const void*)d_rf, (const void*)d_cd, (const void*)d_out, (const void*)d_order, (const void*)d_counts_sorted}) work_free(ctx, q);
+    };
     // root rows 1..rf_max for everybody (rows beyond a family's own range are ignored by k_family_pvalue)
     const int root_rows = std::min(rf_max, ctx->S - 1);
     const bool fused = root_rows >= 1 && fused2_windowed_supported(ctx) && std::getenv("CAFE_GPU_NO_FUSED") == nullptr;
@@ -165,10 +167,10 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
     }
     stage("family order (host)");
 #define PV_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); cleanup(); return CAFE_GPU_ERR_CUDA; } } while (0)
-    PV_CK(cudaMalloc(&d_colmax, ctx->F_pad * sizeof(int)));
-    PV_CK(cudaMalloc(&d_rf, ctx->F_pad * sizeof(int)));
-    PV_CK(cudaMalloc(&d_cd, (size_t)cd_rows * n_samples * sizeof(double)));
-    PV_CK(cudaMalloc(&d_out, ctx->F_pad * sizeof(double)));
+    PV_CK(work_malloc(ctx, &d_colmax, ctx->F_pad * sizeof(int)));
+    PV_CK(work_malloc(ctx, &d_rf, ctx->F_pad * sizeof(int)));
+    PV_CK(work_malloc(ctx, &d_cd, (size_t)cd_rows * n_samples * sizeof(double)));
+    PV_CK(work_malloc(ctx, &d_out, ctx->F_pad * sizeof(double)));
     PV_CK(cudaMemcpyAsync(d_colmax, colmax.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PV_CK(cudaMemcpyAsync(d_rf, rfsize.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PV_CK(cudaMemcpyAsync(d_cd, cd, (size_t)cd_rows * n_samples * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
@@ -187,8 +189,8 @@ int run_pvalues(cafe_gpu_ctx* ctx, const double* cd, int cd_rows, int n_samples,
         double* d_Lroot = ctx->d_Lroot_cache;
         const int* d_counts_job = ctx->d_counts;
         if (!order.empty()) {
-            PV_CK(cudaMalloc(&d_order, ctx->F_pad * sizeof(int)));
-            PV_CK(cudaMalloc(&d_counts_sorted, (size_t)nl * ctx->F_pad * sizeof(int)));
+            PV_CK(work_malloc(ctx, &d_order, ctx->F_pad * sizeof(int)));
+            PV_CK(work_malloc(ctx, &d_counts_sorted, (size_t)nl * ctx->F_pad * sizeof(int)));
             PV_CK(cudaMemsetAsync(d_counts_sorted, 0, (size_t)nl * ctx->F_pad * sizeof(int), ctx->stream));
             PV_CK(cudaMemcpyAsync(d_order, order.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             k_permute_counts<<<dim3((F + 255) / 256, nl), 256, 0, ctx->stream>>>(ctx->d_counts, d_counts_sorted, d_order, F, ctx->F_pad);

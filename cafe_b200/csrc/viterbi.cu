@@ -256,28 +256,31 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
     short* d_vit = nullptr;
     int *d_order = nullptr, *d_counts_sorted = nullptr, *d_sizes_tab = nullptr;
     double *d_ml_tab = nullptr, *d_bpv_tab = nullptr;
-    auto cleanup = [&]() { cudaFree(d_prefix); cudaFree(d_parent); cudaFree(d_is_leaf); cudaFree(d_leaf_ord); cudaFree(d_sizes); cudaFree(d_L); cudaFree(d_ml); cudaFree(d_vit);
-                           cudaFree(d_colmax); cudaFree(d_rf); cudaFree(d_node_key); cudaFree(d_bpv);
-                           cudaFree(d_order); cudaFree(d_counts_sorted); cudaFree(d_sizes_tab); cudaFree(d_ml_tab); cudaFree(d_bpv_tab); };
+    auto cleanup = [&]() {  // work_free: the buffers stay with the context (common.cuh)
+        for (const void* q : {(const void*)d_prefix, (const void*)d_parent, (const void*)d_is_leaf, (const void*)d_leaf_ord, (const void*)d_sizes, (const void*)d_L,
+                              (const void*)d_ml, (const void*)d_vit, (const void*)d_colmax, (const void*)d_rf, (const void*)d_node_key, (const void*)d_bpv,
+                              (const void*)d_order, (const void*)d_counts_sorted, (const void*)d_sizes_tab, (const void*)d_ml_tab, (const void*)d_bpv_tab})
+            work_free(ctx, q);
+    };
 #define VT_CK(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cleanup(); ctx->err = std::string(#expr) + ": " + cudaGetErrorString(e__); return CAFE_GPU_ERR_CUDA; } } while (0)
-    VT_CK(cudaMalloc(&d_prefix, n * sizeof(int)));
-    VT_CK(cudaMalloc(&d_parent, n * sizeof(int)));
-    VT_CK(cudaMalloc(&d_is_leaf, n * sizeof(int)));
-    VT_CK(cudaMalloc(&d_leaf_ord, n * sizeof(int)));
-    VT_CK(cudaMalloc(&d_sizes, (size_t)F * n * sizeof(int)));
-    VT_CK(cudaMalloc(&d_ml, (size_t)F * sizeof(double)));
-    VT_CK(cudaMalloc(&d_L, (size_t)n_internal * FC * Vp * sizeof(double)));
-    VT_CK(cudaMalloc(&d_vit, (size_t)n * FC * Vp * sizeof(short)));
+    VT_CK(work_malloc(ctx, &d_prefix, n * sizeof(int)));
+    VT_CK(work_malloc(ctx, &d_parent, n * sizeof(int)));
+    VT_CK(work_malloc(ctx, &d_is_leaf, n * sizeof(int)));
+    VT_CK(work_malloc(ctx, &d_leaf_ord, n * sizeof(int)));
+    VT_CK(work_malloc(ctx, &d_sizes, (size_t)F * n * sizeof(int)));
+    VT_CK(work_malloc(ctx, &d_ml, (size_t)F * sizeof(double)));
+    VT_CK(work_malloc(ctx, &d_L, (size_t)n_internal * FC * Vp * sizeof(double)));
+    VT_CK(work_malloc(ctx, &d_vit, (size_t)n * FC * Vp * sizeof(short)));
     if (forced) {
-        VT_CK(cudaMalloc(&d_colmax, ctx->F_pad * sizeof(int)));
-        VT_CK(cudaMalloc(&d_rf, ctx->F_pad * sizeof(int)));
+        VT_CK(work_malloc(ctx, &d_colmax, ctx->F_pad * sizeof(int)));
+        VT_CK(work_malloc(ctx, &d_rf, ctx->F_pad * sizeof(int)));
         VT_CK(cudaMemcpyAsync(d_colmax, h_colmax.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         VT_CK(cudaMemcpyAsync(d_rf, h_rf.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     const int* d_counts_use = ctx->d_counts;
     if (sorted) {
-        VT_CK(cudaMalloc(&d_order, ctx->F_pad * sizeof(int)));
-        VT_CK(cudaMalloc(&d_counts_sorted, (size_t)ctx->n_leaves * ctx->F_pad * sizeof(int)));
+        VT_CK(work_malloc(ctx, &d_order, ctx->F_pad * sizeof(int)));
+        VT_CK(work_malloc(ctx, &d_counts_sorted, (size_t)ctx->n_leaves * ctx->F_pad * sizeof(int)));
         VT_CK(cudaMemsetAsync(d_counts_sorted, 0, (size_t)ctx->n_leaves * ctx->F_pad * sizeof(int), ctx->stream));
         VT_CK(cudaMemcpyAsync(d_order, order.data(), ctx->F_pad * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         k_vit_gather_counts<<<dim3((F + 255) / 256, ctx->n_leaves), 256, 0, ctx->stream>>>(ctx->d_counts, d_counts_sorted, d_order, F, ctx->F_pad);
@@ -341,8 +344,8 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
         VT_CK(cudaGetLastError());
     }
     if (branch_pv_out) {
-        VT_CK(cudaMalloc(&d_node_key, n * sizeof(int)));
-        VT_CK(cudaMalloc(&d_bpv, (size_t)F * n * sizeof(double)));
+        VT_CK(work_malloc(ctx, &d_node_key, n * sizeof(int)));
+        VT_CK(work_malloc(ctx, &d_bpv, (size_t)F * n * sizeof(double)));
         VT_CK(cudaMemcpyAsync(d_node_key, ctx->node_key.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         const long long warps = (long long)F * n;
         k_viterbi_branch_pvalues<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(
@@ -351,7 +354,7 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
         VT_CK(cudaGetLastError());
         const double* src = d_bpv;
         if (sorted) {
-            VT_CK(cudaMalloc(&d_bpv_tab, (size_t)F * n * sizeof(double)));
+            VT_CK(work_malloc(ctx, &d_bpv_tab, (size_t)F * n * sizeof(double)));
             k_vit_scatter_rows<double><<<(unsigned)((warps + 255) / 256), 256, 0, ctx->stream>>>(d_bpv, d_bpv_tab, d_order, F, n);
             ctx->launches++;
             src = d_bpv_tab;
@@ -361,7 +364,7 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
     if (sizes_out) {
         const int* src = d_sizes;
         if (sorted) {
-            VT_CK(cudaMalloc(&d_sizes_tab, (size_t)F * n * sizeof(int)));
+            VT_CK(work_malloc(ctx, &d_sizes_tab, (size_t)F * n * sizeof(int)));
             k_vit_scatter_rows<int><<<(unsigned)(((long long)F * n + 255) / 256), 256, 0, ctx->stream>>>(d_sizes, d_sizes_tab, d_order, F, n);
             ctx->launches++;
             src = d_sizes_tab;
@@ -371,7 +374,7 @@ int run_viterbi(cafe_gpu_ctx* ctx, int32_t* sizes_out, double* maxlik_out, bool 
     if (maxlik_out) {
         const double* src = d_ml;
         if (sorted) {
-            VT_CK(cudaMalloc(&d_ml_tab, (size_t)F * sizeof(double)));
+            VT_CK(work_malloc(ctx, &d_ml_tab, (size_t)F * sizeof(double)));
             k_vit_scatter_rows<double><<<(F + 255) / 256, 256, 0, ctx->stream>>>(d_ml, d_ml_tab, d_order, F, 1);
             ctx->launches++;
             src = d_ml_tab;
