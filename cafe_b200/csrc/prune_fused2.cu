@@ -27,7 +27,10 @@
 // register epilogue straight to global memory (5.0 ms) lost against 3.72 ms for this structure; the lean stage boundary, the
 // sigma permutation of the matrix-tile rows (no lane-dependent access order in the C tile), compile-time epilogue
 // instantiations and the clipped B maps then took it to 3.58 ms at configs[1] and 132.8 ms (0.93 of cuBLAS DGEMM) at
-// configs[2].  k_prune_fused2<.., WIN = true> is the windowed instantiation for the conditional distribution and the p-values.
+// configs[2].  k_prune_fused2<.., WIN = true> is the windowed instantiation for the conditional distribution and the p-values:
+// per-family column windows, and every role ends a tile's K loops and output passes at the tile's largest window and runs the
+// root op only over the passes somebody reads (tile_win_*); its callers order the families so that a tile is homogeneous and
+// every CTA gets the same mix (fused2_tile_slots).  The score instantiation carries none of this.
 //
 // Bit-for-bit the same arithmetic as prune_fused.cu / prune.cu (same DMMA order over K, one rounding per product).
 #include <cuda.h>
