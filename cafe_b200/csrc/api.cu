@@ -116,6 +116,7 @@ static int one_synchronize(cafe_gpu_ctx* ctx) {
 static int one_set_tree(cafe_gpu_ctx* ctx, int n_nodes, const int32_t* left, const int32_t* right, const double* branchlength) {
     if (!ctx || n_nodes < 3 || (n_nodes & 1) == 0 || !left || !right || !branchlength)
         CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_tree: need an odd number (>=3) of nodes and non-null arrays");
+    work_release_all(ctx);  // cached work buffers were sized for the old problem
     ctx->n_nodes = n_nodes;
     ctx->n_leaves = (n_nodes + 1) / 2;
     ctx->left.assign(left, left + n_nodes);
@@ -169,6 +170,7 @@ static int one_set_ranges(cafe_gpu_ctx* ctx, int range_min, int range_max, int r
     if (!ctx) return CAFE_GPU_ERR_ARG;
     if (range_min != 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_UNSUPPORTED, "set_ranges: range_min must be 0 (init_family_size, cafe_family.c:357-364)");
     if (range_max < 1 || root_min < 0 || root_max < root_min) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_ranges: bad range");
+    if (range_max != ctx->rmax || std::max(range_max, root_max) + 1 != ctx->S) work_release_all(ctx);  // sized by the old vectors / matrices
     ctx->rmin = range_min; ctx->rmax = range_max; ctx->root_min = root_min; ctx->root_max = root_max;
     ctx->W = range_max - range_min + 1;
     ctx->R = root_max - root_min + 1;
@@ -211,6 +213,7 @@ static int one_set_families(cafe_gpu_ctx* ctx, int n_families, int n_leaves, con
     if (ctx->n_nodes == 0) CAFE_FAIL(ctx, CAFE_GPU_ERR_STATE, "set_families: set_tree first");
     if (n_leaves != ctx->n_leaves) CAFE_FAIL(ctx, CAFE_GPU_ERR_ARG, "set_families: n_leaves does not match the tree");
     const int F = n_families, F_pad = round_up(F, 128);
+    if (F_pad != ctx->F_pad) work_release_all(ctx);  // cached work buffers of the p-value / Viterbi passes follow the table's size
     std::vector<int> T((size_t)n_leaves * F_pad, 0), mult(F_pad, 0), first(F_pad, 0);
     int mx = 0;
     bool missing = false;
